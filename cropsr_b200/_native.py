@@ -1,0 +1,87 @@
+"""ctypes binding of libcropsr_b200.so (include/cropsr_b200.h).
+
+There is no CPU fallback: if the shared library is missing this module raises
+at import time, and if no CUDA device is usable every compute call raises
+``CropsrError`` with the library's message.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcropsr_b200.so")
+
+ABI_VERSION = 1
+
+CRP_SCAN_DEFAULT = 0
+CRP_SCAN_NO_SCORE = 1
+CRP_SCAN_LOGISTIC = 2
+CRP_SCAN_EXTRAS = 4
+
+CRP_CLASS_CANONICAL = 0
+CRP_CLASS_PAIR = 1
+CRP_CLASS_SINGLE = 2
+
+PACKED_IRREGULAR = 1 << 30
+PACKED_TRUNCATED = 1 << 31
+PACKED_UNSCORED = 1 << 62
+
+
+class CropsrError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libcropsr_b200 error {code}: {message}")
+        self.code = code
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `make -C {os.path.join(_HERE, 'csrc')}` "
+        "(or __graft_entry__.build()).  cropsr_b200 has no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+_vpp = C.POINTER(C.c_void_p)
+
+# name -> (restype, argtypes); mirrors include/cropsr_b200.h one to one
+SIGNATURES = {
+    "crp_init": (C.c_int, [C.c_int]),
+    "crp_shutdown": (C.c_int, []),
+    "crp_last_error": (C.c_char_p, []),
+    "crp_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "crp_abi_version": (C.c_int, []),
+    "crp_host_alloc": (C.c_int, [_vpp, C.c_uint64]),
+    "crp_host_free": (C.c_int, [C.c_void_p]),
+    "crp_genome_new": (C.c_int, [_vpp]),
+    "crp_genome_add_segment": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "crp_genome_commit": (C.c_int, [C.c_void_p]),
+    "crp_genome_num_segments": (C.c_int, [C.c_void_p, _u32p]),
+    "crp_genome_num_positions": (C.c_int, [C.c_void_p, _u64p]),
+    "crp_genome_free": (C.c_int, [C.c_void_p]),
+    "crp_scan_score": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, _vpp]),
+    "crp_result_totals": (C.c_int, [C.c_void_p, _u64p, _u64p]),
+    "crp_result_segment_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crp_result_device_counts": (C.c_int, [C.c_void_p, _vpp]),
+    "crp_result_fetch": (C.c_int, [C.c_void_p, C.c_char, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crp_result_free": (C.c_int, [C.c_void_p]),
+    "crp_rescore": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crp_genome_timing": (C.c_int, [C.c_void_p, _f32p, _f32p]),
+    "crp_result_timing": (C.c_int, [C.c_void_p, _f32p]),
+    "crp_launch_count": (C.c_int, [_u64p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)       # AttributeError here = library/header mismatch
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+if lib.crp_abi_version() != ABI_VERSION:
+    raise ImportError(f"{LIB_PATH}: ABI version {lib.crp_abi_version()} != binding {ABI_VERSION}; rebuild")
+
+
+def check(rc):
+    if rc != 0:
+        raise CropsrError(rc, lib.crp_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,1019 @@
+// libcropsr_b200: CROPSR Cas9 gRNA candidate scan + Rule-Set-1 score on B200 (sm_100a).
+//
+// Kernels (all HBM-bound integer / fp64 work -- no tensor cores on this path):
+//   k_pack        ASCII token bytes -> 4 bit-planes (code low bit, code high bit,
+//                 lower-case, other-byte), 0.5 byte per base resident in HBM.
+//   k_scan_score  one pass over the planes: PAM tests (+: .GG, -: CC.) as 32-wide
+//                 bit ops, block scan, decoupled look-back across tiles for the
+//                 ordered global offsets, then one thread per candidate extracts
+//                 the 30-base window from shared memory, scores it (fp64, canonical
+//                 OpenBLAS lane order) and stores (pos, packed 30-mer, x) coalesced.
+//   k_rescore     dense re-evaluation of selected candidates in any BLAS lane class.
+//   k_segment_counts  per-segment candidate counts from the tile prefix array.
+//
+// Reference semantics implemented here: /root/reference/CROPSR.py:413-434 (scan,
+// bounds, windows, transforms) and :285-313 (rs1_score); see DESIGN.md.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <stdlib.h>
+#include <new>
+#include <vector>
+
+#include "../../include/cropsr_b200.h"
+#include "rs1_weights.inc"
+
+#define CRP_ABI_VERSION 1
+
+// ------------------------------------------------------------------ geometry
+static constexpr int kTile = 8192;                 // positions per tile
+static constexpr int kTileWords = kTile / 32;      // 256 plane words
+static constexpr int kThreads = 256;               // one plane word per thread in phase 1
+static constexpr int kHaloWords = 1;               // 32 positions each side (need 25 left / 27 right)
+static constexpr int kSmemWords = kTileWords + 2 * kHaloWords;
+static constexpr uint32_t kAlign = 128;            // positions; segment placement granularity
+
+struct TileDesc {
+    uint32_t gword;     // plane word index of the tile's first position
+    uint32_t t_start;   // token-relative position of the tile's first position
+    uint32_t L;         // token length
+    uint32_t n;         // positions of this tile owned by the segment (<= kTile)
+};
+
+// status word of the decoupled look-back: [63:62] flag, [61:31] plus count, [30:0] minus count
+static constexpr unsigned long long kFlagAgg = 1ull << 62;
+static constexpr unsigned long long kFlagIncl = 2ull << 62;
+static constexpr unsigned long long kValMask = (1ull << 62) - 1;
+static constexpr unsigned long long kMinusMask = (1ull << 31) - 1;
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return fail(CRP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                \
+    } while (0)
+
+// ------------------------------------------------------------------ context
+struct Context {
+    bool ready = false;
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+};
+static Context g_ctx;
+
+// ------------------------------------------------------------------ k_pack
+// byte -> nibble: bit0 code low, bit1 code high (A0 T1 C2 G3), bit2 lower-case, bit3 other.
+// 'U' and 'Z' are "other" bytes that still score (reference replace chains,
+// CROPSR.py:120,128,458): they carry the code of T resp. G.
+__device__ __forceinline__ uint32_t classify(uint32_t c) {
+    uint32_t up = c & 0xDFu;
+    uint32_t r = 8u;
+    if (up == 'A') r = 0u;
+    else if (up == 'T') r = 1u;
+    else if (up == 'C') r = 2u;
+    else if (up == 'G') r = 3u;
+    if (r < 8u) return r | ((c & 0x20u) >> 3);
+    if (c == 'U') return 8u | 1u;
+    if (c == 'Z') return 8u | 3u;
+    return 8u;
+}
+
+__global__ void __launch_bounds__(256)
+k_pack(const uint4 *__restrict__ ascii, uint64_t n_words, uint32_t *__restrict__ p0,
+       uint32_t *__restrict__ p1, uint32_t *__restrict__ lower, uint32_t *__restrict__ other) {
+    __shared__ uint8_t lut[256];
+    lut[threadIdx.x] = (uint8_t)classify(threadIdx.x);
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+        uint4 a = __ldg(ascii + 2 * w);
+        uint4 b = __ldg(ascii + 2 * w + 1);
+        uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t o0 = 0, o1 = 0, ol = 0, oo = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t nib = lut[(v[i] >> (8 * k)) & 0xFFu];
+                int bit = 4 * i + k;
+                o0 |= (nib & 1u) << bit;
+                o1 |= ((nib >> 1) & 1u) << bit;
+                ol |= ((nib >> 2) & 1u) << bit;
+                oo |= ((nib >> 3) & 1u) << bit;
+            }
+        }
+        p0[w] = o0;
+        p1[w] = o1;
+        lower[w] = ol;
+        other[w] = oo;
+    }
+}
+
+// ------------------------------------------------------------------ RS1 scoring
+// Canonical lane order (rows handled by OpenBLAS' 4-row dgemv_t kernel): one
+// sequential accumulator per column-mod-4 lane, i.e. per base class for the
+// first-order term and per SECOND base for the dinucleotide term, columns in
+// ascending order; lanes combined (p0+p2)+(p1+p3) = (A+C)+(T+G).
+// s0/s1: planar code bits of the scored 30-mer (bit q = base q), valid: bases that score.
+__device__ __forceinline__ double rs1_canonical(uint32_t s0, uint32_t s1, uint32_t valid) {
+    const uint32_t m[4] = {~s1 & ~s0 & valid, ~s1 & s0 & valid, s1 & ~s0 & valid, s1 & s0 & valid};
+    double fA = 0.0, fT = 0.0, fC = 0.0, fG = 0.0;
+#define X1A(p, w) if (m[0] & (1u << (p))) fA = __dadd_rn(fA, w);
+#define X1T(p, w) if (m[1] & (1u << (p))) fT = __dadd_rn(fT, w);
+#define X1C(p, w) if (m[2] & (1u << (p))) fC = __dadd_rn(fC, w);
+#define X1G(p, w) if (m[3] & (1u << (p))) fG = __dadd_rn(fG, w);
+    RS1_FIRST_A(X1A) RS1_FIRST_T(X1T) RS1_FIRST_C(X1C) RS1_FIRST_G(X1G)
+#undef X1A
+#undef X1T
+#undef X1C
+#undef X1G
+    const double first = __dadd_rn(__dadd_rn(fA, fC), __dadd_rn(fT, fG));
+    // dinucleotide (c1 at p, c2 at p+1): bit p of m[c1] & (m[c2] >> 1)
+    const uint32_t nA = m[0] >> 1, nT = m[1] >> 1, nC = m[2] >> 1, nG = m[3] >> 1;
+    double dA = 0.0, dT = 0.0, dC = 0.0, dG = 0.0;
+#define X2A(p, c1, w) if (m[c1] & nA & (1u << (p))) dA = __dadd_rn(dA, w);
+#define X2T(p, c1, w) if (m[c1] & nT & (1u << (p))) dT = __dadd_rn(dT, w);
+#define X2C(p, c1, w) if (m[c1] & nC & (1u << (p))) dC = __dadd_rn(dC, w);
+#define X2G(p, c1, w) if (m[c1] & nG & (1u << (p))) dG = __dadd_rn(dG, w);
+    RS1_SECOND_A(X2A) RS1_SECOND_T(X2T) RS1_SECOND_C(X2C) RS1_SECOND_G(X2G)
+#undef X2A
+#undef X2T
+#undef X2C
+#undef X2G
+    const double second = __dadd_rn(__dadd_rn(dA, dC), __dadd_rn(dT, dG));
+    // (score_first + score_second + intersect + low_gc) * -1, CROPSR.py:312
+    return -__dadd_rn(__dadd_rn(__dadd_rn(first, second), RS1_INTERCEPT), RS1_LOW_GC);
+}
+
+__constant__ double c_w1[120] = RS1_DENSE_FIRST;
+__constant__ double c_w2[464] = RS1_DENSE_SECOND;
+
+// Dense emulation of one row of np.matmul(matrix, weights) for a given lane class.
+// ind(j) is the 0/1 matrix entry of column j.
+template <typename Ind>
+__device__ double blas_row(const double *w, int d, int cls, Ind ind) {
+    if (cls == CRP_CLASS_CANONICAL) {
+        double p[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int j = 0; j < d; ++j)
+            if (ind(j)) p[j & 3] = __dadd_rn(p[j & 3], w[j]);
+        return __dadd_rn(__dadd_rn(p[0], p[2]), __dadd_rn(p[1], p[3]));
+    }
+    if (cls == CRP_CLASS_PAIR) {
+        double q[2] = {0.0, 0.0};
+        for (int j = 0; j < d; ++j)
+            if (ind(j)) q[j & 1] = __dadd_rn(q[j & 1], w[j]);
+        return __dadd_rn(q[0], q[1]);
+    }
+    // CRP_CLASS_SINGLE: OpenBLAS ddot (AVX-512): 4 accumulators x 8 lanes over
+    // the 32-column blocks, folded to 4 lanes, one 16-column pass, lane-wise
+    // ((a0+a1)+a2)+a3, (l0+l2)+(l1+l3), then a sequential tail.
+    double acc[4][8];
+    for (int a = 0; a < 4; ++a)
+        for (int l = 0; l < 8; ++l) acc[a][l] = 0.0;
+    const int n32 = d & ~31;
+    for (int j = 0; j < n32; ++j)
+        if (ind(j)) {
+            int a = (j & 31) >> 3, l = j & 7;
+            acc[a][l] = __dadd_rn(acc[a][l], w[j]);
+        }
+    double f[4][4];
+    for (int a = 0; a < 4; ++a)
+        for (int i = 0; i < 4; ++i) f[a][i] = __dadd_rn(acc[a][i], acc[a][i + 4]);
+    int pos = n32;
+    if (d & 16) {
+        for (int a = 0; a < 4; ++a)
+            for (int i = 0; i < 4; ++i) {
+                int j = pos + 4 * a + i;
+                if (ind(j)) f[a][i] = __dadd_rn(f[a][i], w[j]);
+            }
+        pos += 16;
+    }
+    double t[4];
+    for (int i = 0; i < 4; ++i)
+        t[i] = __dadd_rn(__dadd_rn(__dadd_rn(f[0][i], f[1][i]), f[2][i]), f[3][i]);
+    double dot = __dadd_rn(__dadd_rn(t[0], t[2]), __dadd_rn(t[1], t[3]));
+    for (int j = pos; j < d; ++j)
+        if (ind(j)) dot = __dadd_rn(dot, w[j]);
+    return dot;
+}
+
+__device__ double rs1_dense(uint32_t s0, uint32_t s1, uint32_t valid, int cls1, int cls2) {
+    auto code = [&](int p) -> int { return (int)(((s1 >> p) & 1u) << 1 | ((s0 >> p) & 1u)); };
+    auto ok = [&](int p) -> bool { return (valid >> p) & 1u; };
+    double first = blas_row(c_w1, 120, cls1, [&](int j) { int p = j >> 2; return ok(p) && code(p) == (j & 3); });
+    double second = blas_row(c_w2, 464, cls2, [&](int j) {
+        int p = j >> 4;
+        return ok(p) && ok(p + 1) && code(p) == ((j >> 2) & 3) && code(p + 1) == (j & 3);
+    });
+    return -__dadd_rn(__dadd_rn(__dadd_rn(first, second), RS1_INTERCEPT), RS1_LOW_GC);
+}
+
+// ------------------------------------------------------------------ plane algebra
+struct Derived {
+    uint32_t s0p;    // scored low code bit, '+' strand (complement of upper-case bases)
+    uint32_t s0m;    // scored low code bit, '-' strand
+    uint32_t s1;     // scored high code bit (both strands)
+    uint32_t valid;  // base contributes to the score
+    uint32_t irr;    // byte is not an upper-case ACGT
+    uint32_t gup;    // upper-case G
+    uint32_t cup;    // upper-case C
+};
+
+__device__ __forceinline__ Derived derive(uint32_t p0, uint32_t p1, uint32_t lo, uint32_t ot) {
+    Derived d;
+    const uint32_t upper = ~lo & ~ot;       // upper-case ACGT
+    const uint32_t special = ot & p0;       // 'U' or 'Z'
+    d.s0p = p0 ^ upper;                     // A<->T, C<->G flips the low bit
+    d.s0m = p0 ^ special;                   // '-' strand: U scores as A, Z as C
+    d.s1 = p1;
+    d.valid = ~ot | special;
+    d.irr = lo | ot;
+    d.gup = p0 & p1 & upper;
+    d.cup = ~p0 & p1 & upper;
+    return d;
+}
+
+// bits b of a 32-position word starting at token position t0 with lo <= t0+b <= hi
+__device__ __forceinline__ uint32_t range_mask(int64_t t0, int64_t lo, int64_t hi) {
+    int64_t a = lo - t0, b = hi - t0;
+    if (a < 0) a = 0;
+    if (b > 31) b = 31;
+    if (a > b) return 0u;
+    return (0xFFFFFFFFu >> (31 - (int)b)) & (0xFFFFFFFFu << (int)a);
+}
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+struct ScanArgs {
+    const uint32_t *p0, *p1, *lower, *other;
+    const TileDesc *tiles;
+    uint32_t n_tiles;
+    int guide_len;
+    uint32_t flags;
+    unsigned long long *status;      // [n_tiles], zeroed before launch
+    unsigned int *ticket;            // zeroed before launch
+    uint64_t capacity;               // entries per strand stream
+    uint32_t *pos_plus, *pos_minus;
+    unsigned long long *packed_plus, *packed_minus;
+    double *x_plus, *x_minus;
+};
+
+template <bool kScore>
+__global__ void __launch_bounds__(kThreads)
+k_scan_score(const ScanArgs a) {
+    __shared__ uint4 s_quad_p[kSmemWords];      // {s0p, s1, valid, irr}
+    __shared__ uint4 s_quad_m[kSmemWords];      // {s0m, s1, valid, irr}
+    __shared__ uint32_t s_g[kSmemWords + 1];
+    __shared__ uint32_t s_c[kSmemWords + 1];
+    __shared__ uint16_t s_list_p[kTile];
+    __shared__ uint16_t s_list_m[kTile];
+    __shared__ uint32_t s_warp[kThreads / 32];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_excl;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int l = a.guide_len;
+
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= a.n_tiles) break;
+        const TileDesc td = a.tiles[tile];
+        const int nw = (int)((td.n + 31u) >> 5);          // owned words
+
+        // ---- stage planes (+1 halo word each side) into shared memory
+        for (int i = tid; i < nw + 2; i += kThreads) {
+            const uint64_t gw = (uint64_t)td.gword - 1 + i;
+            Derived d = derive(__ldg(a.p0 + gw), __ldg(a.p1 + gw), __ldg(a.lower + gw), __ldg(a.other + gw));
+            if (kScore) {
+                s_quad_p[i] = make_uint4(d.s0p, d.s1, d.valid, d.irr);
+                s_quad_m[i] = make_uint4(d.s0m, d.s1, d.valid, d.irr);
+            }
+            s_g[i] = d.gup;
+            s_c[i] = d.cup;
+        }
+        __syncthreads();
+
+        // ---- phase 1: PAM tests for the 32 positions of word `tid`
+        uint32_t hp = 0, hm = 0;
+        if (tid < nw) {
+            const uint32_t g0 = s_g[tid + 1], g1 = s_g[tid + 2];
+            const uint32_t c0 = s_c[tid + 1], c1 = s_c[tid + 2];
+            // '+': (?=.GG) at t  <=>  tok[t+1]==tok[t+2]=='G'   (CROPSR.py:415)
+            hp = __funnelshift_r(g0, g1, 1) & __funnelshift_r(g0, g1, 2);
+            // '-': (?=CC.) at t  <=>  tok[t]==tok[t+1]=='C' and t+2 < L   (CROPSR.py:426)
+            hm = c0 & __funnelshift_r(c0, c1, 1);
+            const int64_t t0 = (int64_t)td.t_start + 32 * tid;
+            const int64_t last_owned = (int64_t)td.t_start + td.n - 1;
+            const int64_t L = td.L;
+            // bounds tests of CROPSR.py:419 / :430 reduce to  t >= l+5  and  2 <= t <= L-l+7
+            int64_t hi_p = L - 3 < last_owned ? L - 3 : last_owned;
+            int64_t hi_m = L - l + 7 < hi_p ? L - l + 7 : hi_p;
+            hp &= range_mask(t0, l + 5, hi_p);
+            hm &= range_mask(t0, 2, hi_m);
+        }
+        const uint32_t cnt = __popc(hp) | (__popc(hm) << 16);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t warp_base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) {
+            const uint32_t v = s_warp[w];
+            if (w < warp) warp_base += v;
+            total += v;
+        }
+        const uint32_t excl = warp_base + incl - cnt;
+        const uint32_t n_plus = total & 0xFFFFu, n_minus = total >> 16;
+
+        // ---- decoupled look-back: publish this tile's counts, fetch the exclusive prefix
+        if (warp == 0) {
+            const unsigned long long mine = ((unsigned long long)n_plus << 31) | n_minus;
+            if (lane == 0) st_status(a.status + tile, (tile == 0 ? kFlagIncl : kFlagAgg) | mine);
+            unsigned long long prefix = 0;
+            if (tile > 0) {
+                int64_t j = (int64_t)tile - 1;
+                for (;;) {
+                    const int64_t idx = j - lane;
+                    unsigned long long v = kFlagIncl;
+                    if (idx >= 0) {
+                        do { v = ld_status(a.status + idx); } while ((v >> 62) == 0);
+                    }
+                    const uint32_t incl_mask = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
+                    const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;
+                    unsigned long long c = lane <= first ? (v & kValMask) : 0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+                    prefix += c;
+                    if (incl_mask) break;
+                    j -= 32;
+                }
+                if (lane == 0) st_status(a.status + tile, kFlagIncl | (prefix + mine));
+            }
+            if (lane == 0) s_excl = prefix;
+        }
+
+        // ---- compact hit positions (tile-local) in order into shared lists
+        {
+            uint32_t op = excl & 0xFFFFu, om = excl >> 16;
+            const uint32_t base = 32u * tid;
+            while (hp) {
+                const int b = __ffs(hp) - 1;
+                hp &= hp - 1;
+                s_list_p[op++] = (uint16_t)(base + b);
+            }
+            while (hm) {
+                const int b = __ffs(hm) - 1;
+                hm &= hm - 1;
+                s_list_m[om++] = (uint16_t)(base + b);
+            }
+        }
+        __syncthreads();
+        const unsigned long long pre = s_excl;
+        const uint64_t base_plus = pre >> 31, base_minus = pre & kMinusMask;
+
+        // ---- phase 2: one thread per candidate
+        for (uint32_t k = tid; k < n_plus; k += kThreads) {
+            const uint32_t tl = s_list_p[k];
+            const uint32_t t = td.t_start + tl;
+            const uint64_t o = base_plus + k;
+            if (o < a.capacity) {
+                a.pos_plus[o] = t;
+                if (kScore) {
+                    // window tok[t-25, t+5) read backwards: output base q = tok[t+4-q]
+                    const uint32_t ws = tl + 32u - 25u, wi = ws >> 5, sh = ws & 31u;
+                    const uint4 lo = s_quad_p[wi], hi = s_quad_p[wi + 1];
+                    const uint32_t s0 = __brev(__funnelshift_r(lo.x, hi.x, sh)) >> 2;
+                    const uint32_t s1 = __brev(__funnelshift_r(lo.y, hi.y, sh)) >> 2;
+                    const uint32_t va = __brev(__funnelshift_r(lo.z, hi.z, sh)) >> 2;
+                    const uint32_t ir = __funnelshift_r(lo.w, hi.w, sh) & 0x3FFFFFFFu;
+                    unsigned long long pk = (unsigned long long)s0 | ((unsigned long long)s1 << 32);
+                    if (ir) pk |= CRP_PACKED_IRREGULAR;
+                    if ((uint64_t)t + 5 > td.L) pk |= CRP_PACKED_TRUNCATED;
+                    if (va != 0x3FFFFFFFu) pk |= CRP_PACKED_UNSCORED;
+                    a.packed_plus[o] = pk;
+                    double x = rs1_canonical(s0, s1, va);
+                    if (a.flags & CRP_SCAN_LOGISTIC) x = 1.0 / (1.0 + exp(x));
+                    a.x_plus[o] = x;
+                }
+            }
+        }
+        for (uint32_t k = tid; k < n_minus; k += kThreads) {
+            const uint32_t tl = s_list_m[k];
+            const uint32_t t = td.t_start + tl;
+            const uint64_t o = base_minus + k;
+            if (o < a.capacity) {
+                a.pos_minus[o] = t;
+                if (kScore) {
+                    // window tok[t-2, t+28) read forwards: output base q = tok[t-2+q]
+                    const uint32_t ws = tl + 32u - 2u, wi = ws >> 5, sh = ws & 31u;
+                    const uint4 lo = s_quad_m[wi], hi = s_quad_m[wi + 1];
+                    const uint32_t s0 = __funnelshift_r(lo.x, hi.x, sh) & 0x3FFFFFFFu;
+                    const uint32_t s1 = __funnelshift_r(lo.y, hi.y, sh) & 0x3FFFFFFFu;
+                    const uint32_t va = __funnelshift_r(lo.z, hi.z, sh) & 0x3FFFFFFFu;
+                    const uint32_t ir = __funnelshift_r(lo.w, hi.w, sh) & 0x3FFFFFFFu;
+                    unsigned long long pk = (unsigned long long)s0 | ((unsigned long long)s1 << 32);
+                    if (ir) pk |= CRP_PACKED_IRREGULAR;
+                    if ((uint64_t)t + 28 > td.L) pk |= CRP_PACKED_TRUNCATED;
+                    if (va != 0x3FFFFFFFu) pk |= CRP_PACKED_UNSCORED;
+                    a.packed_minus[o] = pk;
+                    double x = rs1_canonical(s0, s1, va);
+                    if (a.flags & CRP_SCAN_LOGISTIC) x = 1.0 / (1.0 + exp(x));
+                    a.x_minus[o] = x;
+                }
+            }
+        }
+        __syncthreads();   // shared lists / planes are reused by the next tile
+    }
+}
+
+// per-segment counts from the inclusive tile prefixes left in `status`
+__global__ void k_segment_counts(const unsigned long long *__restrict__ status,
+                                 const uint32_t *__restrict__ seg_first_tile,
+                                 const uint32_t *__restrict__ seg_tile_count, uint32_t n_seg,
+                                 unsigned long long *__restrict__ counts /* [2*n_seg] */) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    const uint32_t f = seg_first_tile[s], c = seg_tile_count[s];
+    unsigned long long end = 0, begin = 0;
+    if (c > 0) end = status[f + c - 1] & kValMask;
+    else if (f > 0) end = status[f - 1] & kValMask;
+    if (f > 0) begin = status[f - 1] & kValMask;
+    counts[s] = (end >> 31) - (begin >> 31);
+    counts[n_seg + s] = (end & kMinusMask) - (begin & kMinusMask);
+}
+
+struct RescoreItem {
+    uint64_t gpos;     // plane position of token position t
+    uint32_t strand;   // '+' or '-'
+    uint32_t cls;
+};
+
+__device__ __forceinline__ uint32_t window32(const uint32_t *plane, uint64_t start) {
+    const uint64_t w = start >> 5;
+    return __funnelshift_r(plane[w], plane[w + 1], (uint32_t)(start & 31u));
+}
+
+__global__ void k_rescore(const uint32_t *__restrict__ p0, const uint32_t *__restrict__ p1,
+                          const uint32_t *__restrict__ lower, const uint32_t *__restrict__ other,
+                          const RescoreItem *__restrict__ items, uint64_t n, double *__restrict__ x_out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RescoreItem it = items[i];
+    const bool plus = it.strand == '+';
+    const uint64_t start = plus ? it.gpos - 25 : it.gpos - 2;
+    // derive() is bitwise, so it commutes with the window extraction
+    const Derived d = derive(window32(p0, start), window32(p1, start), window32(lower, start),
+                             window32(other, start));
+    uint32_t s0, s1, va;
+    if (plus) {
+        s0 = __brev(d.s0p) >> 2;
+        s1 = __brev(d.s1) >> 2;
+        va = __brev(d.valid) >> 2;
+    } else {
+        s0 = d.s0m & 0x3FFFFFFFu;
+        s1 = d.s1 & 0x3FFFFFFFu;
+        va = d.valid & 0x3FFFFFFFu;
+    }
+    x_out[i] = rs1_dense(s0, s1, va, (int)(it.cls & 15u), (int)(it.cls >> 4));
+}
+
+// ------------------------------------------------------------------ host objects
+struct Segment {
+    uint32_t token_id;
+    const uint8_t *token;
+    uint64_t token_len, begin, end;
+    uint64_t stage_begin, stage_end;   // token positions copied to the device
+    uint64_t gpos0;                    // plane position of token position stage_begin
+    uint32_t first_tile, n_tiles;
+};
+
+struct crp_genome {
+    std::vector<Segment> segs;
+    bool committed = false;
+    uint64_t n_positions = 0;          // owned positions
+    uint64_t g_total = 0;              // plane positions (multiple of 128)
+    uint32_t *planes = nullptr;        // 4 planes, each g_total/32 + 8 words
+    uint64_t plane_words = 0;
+    TileDesc *d_tiles = nullptr;
+    uint32_t n_tiles = 0;
+    uint32_t *d_seg_first = nullptr, *d_seg_count = nullptr;
+    float ms_h2d = 0.f, ms_pack = 0.f;
+    const uint32_t *plane(int i) const { return planes + (uint64_t)i * plane_words; }
+};
+
+struct crp_result {
+    const crp_genome *g = nullptr;
+    uint64_t capacity = 0;
+    uint64_t n_plus = 0, n_minus = 0;
+    bool scored = false;
+    uint32_t *pos[2] = {nullptr, nullptr};
+    unsigned long long *packed[2] = {nullptr, nullptr};
+    double *x[2] = {nullptr, nullptr};
+    unsigned long long *status = nullptr;
+    unsigned int *ticket = nullptr;
+    unsigned long long *d_counts = nullptr;    // [2*n_seg]
+    std::vector<uint64_t> seg_plus, seg_minus;
+    float ms_scan = 0.f;
+};
+
+static int need_ctx() {
+    if (!g_ctx.ready) return fail(CRP_ERR_STATE, "crp_init has not been called");
+    return 0;
+}
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+int crp_abi_version(void) { return CRP_ABI_VERSION; }
+
+const char *crp_last_error(void) { return g_err; }
+
+int crp_device_count(int *count) {
+    if (!count) return fail(CRP_ERR_ARG, "count is NULL");
+    CUDA_TRY(cudaGetDeviceCount(count));
+    return 0;
+}
+
+int crp_init(int device) {
+    if (g_ctx.ready) {
+        if (g_ctx.device == device) return 0;
+        return fail(CRP_ERR_STATE, "already initialised on device %d", g_ctx.device);
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(CRP_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    g_ctx.device = device;
+    g_ctx.sm_count = prop.multiProcessorCount;
+    g_ctx.launches = 0;
+    g_ctx.ready = true;
+    return 0;
+}
+
+int crp_shutdown(void) {
+    if (!g_ctx.ready) return 0;
+    cudaStreamSynchronize(g_ctx.stream);
+    cudaStreamDestroy(g_ctx.stream);
+    g_ctx = Context();
+    return 0;
+}
+
+int crp_launch_count(uint64_t *n) {
+    if (!n) return fail(CRP_ERR_ARG, "n is NULL");
+    *n = g_ctx.launches;
+    return 0;
+}
+
+int crp_host_alloc(void **ptr, uint64_t bytes) {
+    if (!ptr) return fail(CRP_ERR_ARG, "ptr is NULL");
+    if (int rc = need_ctx()) return rc;
+    CUDA_TRY(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return 0;
+}
+
+int crp_host_free(void *ptr) {
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return 0;
+}
+
+int crp_genome_new(crp_genome **g) {
+    if (!g) return fail(CRP_ERR_ARG, "g is NULL");
+    if (int rc = need_ctx()) return rc;
+    *g = new (std::nothrow) crp_genome();
+    if (!*g) return fail(CRP_ERR_NOMEM, "out of host memory");
+    return 0;
+}
+
+int crp_genome_add_segment(crp_genome *g, uint32_t token_id, const uint8_t *token_ascii,
+                           uint64_t token_len, uint64_t seg_begin, uint64_t seg_end) {
+    if (!g) return fail(CRP_ERR_ARG, "g is NULL");
+    if (g->committed) return fail(CRP_ERR_STATE, "genome already committed");
+    if (!token_ascii && token_len) return fail(CRP_ERR_ARG, "token_ascii is NULL");
+    if (seg_begin > seg_end || seg_end > token_len)
+        return fail(CRP_ERR_ARG, "segment [%llu,%llu) outside token of length %llu",
+                    (unsigned long long)seg_begin, (unsigned long long)seg_end, (unsigned long long)token_len);
+    if (seg_begin % kAlign) return fail(CRP_ERR_ARG, "seg_begin must be a multiple of %u", kAlign);
+    if (token_len >= (1ull << 31))
+        return fail(CRP_ERR_RANGE, "token of %llu positions exceeds the 31-bit position range",
+                    (unsigned long long)token_len);
+    Segment s{};
+    s.token_id = token_id;
+    s.token = token_ascii;
+    s.token_len = token_len;
+    s.begin = seg_begin;
+    s.end = seg_end;
+    g->segs.push_back(s);
+    return 0;
+}
+
+int crp_genome_num_segments(const crp_genome *g, uint32_t *n) {
+    if (!g || !n) return fail(CRP_ERR_ARG, "NULL argument");
+    *n = (uint32_t)g->segs.size();
+    return 0;
+}
+
+int crp_genome_num_positions(const crp_genome *g, uint64_t *n) {
+    if (!g || !n) return fail(CRP_ERR_ARG, "NULL argument");
+    *n = g->n_positions;
+    return 0;
+}
+
+int crp_genome_commit(crp_genome *g) {
+    if (!g) return fail(CRP_ERR_ARG, "g is NULL");
+    if (int rc = need_ctx()) return rc;
+    if (g->committed) return fail(CRP_ERR_STATE, "genome already committed");
+    cudaStream_t st = g_ctx.stream;
+
+    // ---- layout: every segment gets [128 positions of left context][data][>=32 right context]
+    uint64_t gp = 0;
+    std::vector<TileDesc> tiles;
+    std::vector<uint32_t> seg_first, seg_count;
+    g->n_positions = 0;
+    for (Segment &s : g->segs) {
+        s.stage_begin = s.begin >= kAlign ? s.begin - kAlign : 0;
+        s.stage_end = s.end + 64 < s.token_len ? s.end + 64 : s.token_len;
+        // plane position of token position s.begin is a multiple of 128, with 128 positions before it
+        const uint64_t g_begin = gp + kAlign;
+        s.gpos0 = g_begin - (s.begin - s.stage_begin);
+        const uint64_t g_end = g_begin + (s.stage_end - s.begin);
+        gp = (g_end + 64 + kAlign - 1) / kAlign * kAlign;
+        s.first_tile = (uint32_t)tiles.size();
+        for (uint64_t t = s.begin; t < s.end; t += kTile) {
+            TileDesc td;
+            const uint64_t gw = (g_begin + (t - s.begin)) >> 5;
+            if (gw >= (1ull << 32)) return fail(CRP_ERR_RANGE, "shard too large for 32-bit plane word index");
+            td.gword = (uint32_t)gw;
+            td.t_start = (uint32_t)t;
+            td.L = (uint32_t)s.token_len;
+            td.n = (uint32_t)((s.end - t) < (uint64_t)kTile ? (s.end - t) : (uint64_t)kTile);
+            tiles.push_back(td);
+        }
+        s.n_tiles = (uint32_t)tiles.size() - s.first_tile;
+        seg_first.push_back(s.first_tile);
+        seg_count.push_back(s.n_tiles);
+        g->n_positions += s.end - s.begin;
+    }
+    g->g_total = gp + kAlign;
+    g->plane_words = g->g_total / 32 + 8;
+    g->n_tiles = (uint32_t)tiles.size();
+
+    uint8_t *d_ascii = nullptr;
+    CUDA_TRY(cudaMalloc(&d_ascii, g->g_total));
+    if (cudaMalloc(&g->planes, 4 * g->plane_words * sizeof(uint32_t)) != cudaSuccess) {
+        cudaFree(d_ascii);
+        return fail(CRP_ERR_NOMEM, "cudaMalloc of %llu plane bytes failed",
+                    (unsigned long long)(4 * g->plane_words * sizeof(uint32_t)));
+    }
+    cudaEvent_t e0, e1, e2;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventCreate(&e2));
+    CUDA_TRY(cudaEventRecord(e0, st));
+    CUDA_TRY(cudaMemsetAsync(d_ascii, 0, g->g_total, st));
+    CUDA_TRY(cudaMemsetAsync(g->planes, 0, 4 * g->plane_words * sizeof(uint32_t), st));
+    for (const Segment &s : g->segs) {
+        if (s.stage_end > s.stage_begin)
+            CUDA_TRY(cudaMemcpyAsync(d_ascii + s.gpos0, s.token + s.stage_begin, s.stage_end - s.stage_begin,
+                                     cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaEventRecord(e1, st));
+    const uint64_t n_words = g->g_total / 32;
+    if (n_words) {
+        int blocks = (int)((n_words + 255) / 256 < (uint64_t)g_ctx.sm_count * 8 ? (n_words + 255) / 256
+                                                                                 : (uint64_t)g_ctx.sm_count * 8);
+        uint32_t *P = g->planes;
+        k_pack<<<blocks, 256, 0, st>>>((const uint4 *)d_ascii, n_words, P, P + g->plane_words,
+                                       P + 2 * g->plane_words, P + 3 * g->plane_words);
+        g_ctx.launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(e2, st));
+    if (g->n_tiles) {
+        CUDA_TRY(cudaMalloc(&g->d_tiles, g->n_tiles * sizeof(TileDesc)));
+        CUDA_TRY(cudaMemcpyAsync(g->d_tiles, tiles.data(), g->n_tiles * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
+    }
+    if (!g->segs.empty()) {
+        const size_t nb = g->segs.size() * sizeof(uint32_t);
+        CUDA_TRY(cudaMalloc(&g->d_seg_first, nb));
+        CUDA_TRY(cudaMalloc(&g->d_seg_count, nb));
+        CUDA_TRY(cudaMemcpyAsync(g->d_seg_first, seg_first.data(), nb, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(g->d_seg_count, seg_count.data(), nb, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaEventElapsedTime(&g->ms_h2d, e0, e1));
+    CUDA_TRY(cudaEventElapsedTime(&g->ms_pack, e1, e2));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    CUDA_TRY(cudaFree(d_ascii));
+    for (Segment &s : g->segs) s.token = nullptr;   // host tokens may be released now
+    g->committed = true;
+    return 0;
+}
+
+int crp_genome_timing(const crp_genome *g, float *ms_h2d, float *ms_pack) {
+    if (!g) return fail(CRP_ERR_ARG, "g is NULL");
+    if (ms_h2d) *ms_h2d = g->ms_h2d;
+    if (ms_pack) *ms_pack = g->ms_pack;
+    return 0;
+}
+
+int crp_genome_free(crp_genome *g) {
+    if (!g) return 0;
+    cudaFree(g->planes);
+    cudaFree(g->d_tiles);
+    cudaFree(g->d_seg_first);
+    cudaFree(g->d_seg_count);
+    delete g;
+    return 0;
+}
+
+static void free_streams(crp_result *r) {
+    for (int s = 0; s < 2; ++s) {
+        cudaFree(r->pos[s]);
+        cudaFree(r->packed[s]);
+        cudaFree(r->x[s]);
+        r->pos[s] = nullptr;
+        r->packed[s] = nullptr;
+        r->x[s] = nullptr;
+    }
+}
+
+static int alloc_streams(crp_result *r, uint64_t cap, bool scored) {
+    r->capacity = cap;
+    const uint64_t n = cap ? cap : 1;
+    for (int s = 0; s < 2; ++s) {
+        if (cudaMalloc(&r->pos[s], n * sizeof(uint32_t)) != cudaSuccess) goto oom;
+        if (scored) {
+            if (cudaMalloc(&r->packed[s], n * sizeof(unsigned long long)) != cudaSuccess) goto oom;
+            if (cudaMalloc(&r->x[s], n * sizeof(double)) != cudaSuccess) goto oom;
+        }
+    }
+    return 0;
+oom:
+    cudaGetLastError();
+    free_streams(r);
+    return fail(CRP_ERR_NOMEM, "cudaMalloc of candidate streams (%llu entries per strand) failed",
+                (unsigned long long)cap);
+}
+
+static int launch_scan(const crp_genome *g, crp_result *r, int guide_len, uint32_t flags, cudaEvent_t e0,
+                       cudaEvent_t e1) {
+    cudaStream_t st = g_ctx.stream;
+    ScanArgs a;
+    a.p0 = g->plane(0);
+    a.p1 = g->plane(1);
+    a.lower = g->plane(2);
+    a.other = g->plane(3);
+    a.tiles = g->d_tiles;
+    a.n_tiles = g->n_tiles;
+    a.guide_len = guide_len;
+    a.flags = flags;
+    a.status = r->status;
+    a.ticket = r->ticket;
+    a.capacity = r->capacity;
+    a.pos_plus = r->pos[0];
+    a.pos_minus = r->pos[1];
+    a.packed_plus = r->packed[0];
+    a.packed_minus = r->packed[1];
+    a.x_plus = r->x[0];
+    a.x_minus = r->x[1];
+    CUDA_TRY(cudaEventRecord(e0, st));
+    if (g->n_tiles) {
+        CUDA_TRY(cudaMemsetAsync(r->status, 0, (size_t)g->n_tiles * sizeof(unsigned long long), st));
+        CUDA_TRY(cudaMemsetAsync(r->ticket, 0, sizeof(unsigned int), st));
+        int per_sm = 0;
+        if (r->scored)
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_score<true>, kThreads, 0));
+        else
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_score<false>, kThreads, 0));
+        if (per_sm < 1) per_sm = 1;
+        uint64_t blocks = (uint64_t)g_ctx.sm_count * per_sm;
+        if (blocks > g->n_tiles) blocks = g->n_tiles;
+        if (r->scored)
+            k_scan_score<true><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+        else
+            k_scan_score<false><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+        g_ctx.launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    const uint32_t n_seg = (uint32_t)g->segs.size();
+    if (n_seg) {
+        if (g->n_tiles) {
+            k_segment_counts<<<(n_seg + 127) / 128, 128, 0, st>>>(r->status, g->d_seg_first, g->d_seg_count, n_seg,
+                                                                 r->d_counts);
+            g_ctx.launches++;
+            CUDA_TRY(cudaGetLastError());
+        } else {
+            CUDA_TRY(cudaMemsetAsync(r->d_counts, 0, 2 * (size_t)n_seg * sizeof(unsigned long long), st));
+        }
+    }
+    CUDA_TRY(cudaEventRecord(e1, st));
+    return 0;
+}
+
+int crp_scan_score(crp_genome *g, int guide_len, uint32_t flags, crp_result **res) {
+    if (!g || !res) return fail(CRP_ERR_ARG, "NULL argument");
+    if (int rc = need_ctx()) return rc;
+    if (!g->committed) return fail(CRP_ERR_STATE, "genome not committed");
+    if (guide_len < 1 || guide_len > 1000000) return fail(CRP_ERR_ARG, "guide_len %d out of range", guide_len);
+    crp_result *r = new (std::nothrow) crp_result();
+    if (!r) return fail(CRP_ERR_NOMEM, "out of host memory");
+    r->g = g;
+    r->scored = guide_len == 20 && !(flags & CRP_SCAN_NO_SCORE);
+    const uint32_t n_seg = (uint32_t)g->segs.size();
+    cudaStream_t st = g_ctx.stream;
+    int rc = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    std::vector<unsigned long long> counts(2 * (size_t)n_seg);
+    auto bail = [&](int code) {
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        crp_result_free(r);
+        return code;
+    };
+    if (cudaMalloc(&r->status, ((size_t)g->n_tiles + 1) * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&r->ticket, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMalloc(&r->d_counts, (2 * (size_t)n_seg + 1) * sizeof(unsigned long long)) != cudaSuccess)
+        return bail(fail(CRP_ERR_NOMEM, "cudaMalloc of scan state failed"));
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)
+        return bail(fail(CRP_ERR_CUDA, "cudaEventCreate failed"));
+    // First guess of the per-strand capacity: 1/8 candidate per position (GC 70 %
+    // upper-case sequence gives 0.1225); a second pass with the exact counts
+    // follows if it was too small.
+    {
+        uint64_t cap = g->n_positions / 8 + 4096;
+        if ((rc = alloc_streams(r, cap, r->scored))) return bail(rc);
+    }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if ((rc = launch_scan(g, r, guide_len, flags, e0, e1))) return bail(rc);
+        if (n_seg)
+            if (cudaMemcpyAsync(counts.data(), r->d_counts, counts.size() * sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, st) != cudaSuccess)
+                return bail(fail(CRP_ERR_CUDA, "D2H of segment counts failed"));
+        if (cudaStreamSynchronize(st) != cudaSuccess)
+            return bail(fail(CRP_ERR_CUDA, "scan kernels failed: %s", cudaGetErrorString(cudaGetLastError())));
+        r->n_plus = r->n_minus = 0;
+        r->seg_plus.assign(n_seg, 0);
+        r->seg_minus.assign(n_seg, 0);
+        for (uint32_t s = 0; s < n_seg; ++s) {
+            r->seg_plus[s] = counts[s];
+            r->seg_minus[s] = counts[n_seg + s];
+            r->n_plus += counts[s];
+            r->n_minus += counts[n_seg + s];
+        }
+        const uint64_t need = r->n_plus > r->n_minus ? r->n_plus : r->n_minus;
+        if (need <= r->capacity) break;
+        if (attempt == 1) return bail(fail(CRP_ERR_STATE, "candidate streams overflowed twice"));
+        free_streams(r);
+        if ((rc = alloc_streams(r, need, r->scored))) return bail(rc);
+    }
+    cudaEventElapsedTime(&r->ms_scan, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *res = r;
+    return 0;
+}
+
+int crp_result_totals(const crp_result *res, uint64_t *n_plus, uint64_t *n_minus) {
+    if (!res) return fail(CRP_ERR_ARG, "res is NULL");
+    if (n_plus) *n_plus = res->n_plus;
+    if (n_minus) *n_minus = res->n_minus;
+    return 0;
+}
+
+int crp_result_segment_counts(const crp_result *res, uint64_t *n_plus, uint64_t *n_minus) {
+    if (!res) return fail(CRP_ERR_ARG, "res is NULL");
+    for (size_t s = 0; s < res->seg_plus.size(); ++s) {
+        if (n_plus) n_plus[s] = res->seg_plus[s];
+        if (n_minus) n_minus[s] = res->seg_minus[s];
+    }
+    return 0;
+}
+
+int crp_result_device_counts(const crp_result *res, void **dev_ptr) {
+    if (!res || !dev_ptr) return fail(CRP_ERR_ARG, "NULL argument");
+    *dev_ptr = res->d_counts;
+    return 0;
+}
+
+int crp_result_fetch(const crp_result *res, char strand, uint64_t first, uint64_t count, uint32_t *pos,
+                     uint64_t *packed, double *x) {
+    if (!res) return fail(CRP_ERR_ARG, "res is NULL");
+    if (int rc = need_ctx()) return rc;
+    if (strand != '+' && strand != '-') return fail(CRP_ERR_ARG, "strand must be '+' or '-'");
+    const int s = strand == '+' ? 0 : 1;
+    const uint64_t total = s == 0 ? res->n_plus : res->n_minus;
+    if (first > total || count > total - first)
+        return fail(CRP_ERR_ARG, "range [%llu,+%llu) outside stream of %llu candidates", (unsigned long long)first,
+                    (unsigned long long)count, (unsigned long long)total);
+    if ((packed || x) && !res->scored && count)
+        return fail(CRP_ERR_STATE, "this result carries positions only (guide_len != 20 or CRP_SCAN_NO_SCORE)");
+    cudaStream_t st = g_ctx.stream;
+    if (count) {
+        if (pos) CUDA_TRY(cudaMemcpyAsync(pos, res->pos[s] + first, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (packed)
+            CUDA_TRY(cudaMemcpyAsync(packed, res->packed[s] + first, count * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        if (x) CUDA_TRY(cudaMemcpyAsync(x, res->x[s] + first, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int crp_result_timing(const crp_result *res, float *ms_scan) {
+    if (!res) return fail(CRP_ERR_ARG, "res is NULL");
+    if (ms_scan) *ms_scan = res->ms_scan;
+    return 0;
+}
+
+int crp_result_free(crp_result *r) {
+    if (!r) return 0;
+    free_streams(r);
+    cudaFree(r->status);
+    cudaFree(r->ticket);
+    cudaFree(r->d_counts);
+    delete r;
+    return 0;
+}
+
+int crp_rescore(const crp_genome *g, uint64_t n, const uint32_t *segment, const uint32_t *t, const char *strand,
+                const uint8_t *cls, double *x_out) {
+    if (!g) return fail(CRP_ERR_ARG, "g is NULL");
+    if (int rc = need_ctx()) return rc;
+    if (!g->committed) return fail(CRP_ERR_STATE, "genome not committed");
+    if (n == 0) return 0;
+    if (!segment || !t || !strand || !cls || !x_out) return fail(CRP_ERR_ARG, "NULL argument");
+    std::vector<RescoreItem> items(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        if (segment[i] >= g->segs.size()) return fail(CRP_ERR_ARG, "item %llu: bad segment", (unsigned long long)i);
+        const Segment &s = g->segs[segment[i]];
+        if (t[i] < s.begin || t[i] >= s.end)
+            return fail(CRP_ERR_ARG, "item %llu: t=%u outside segment", (unsigned long long)i, t[i]);
+        if (strand[i] != '+' && strand[i] != '-') return fail(CRP_ERR_ARG, "item %llu: bad strand", (unsigned long long)i);
+        if ((cls[i] & 15u) > CRP_CLASS_SINGLE || (cls[i] >> 4) > CRP_CLASS_SINGLE) return fail(CRP_ERR_ARG, "item %llu: bad class", (unsigned long long)i);
+        items[i].gpos = s.gpos0 + (t[i] - s.stage_begin);
+        items[i].strand = (uint32_t)strand[i];
+        items[i].cls = cls[i];
+    }
+    cudaStream_t st = g_ctx.stream;
+    RescoreItem *d_items = nullptr;
+    double *d_x = nullptr;
+    CUDA_TRY(cudaMalloc(&d_items, n * sizeof(RescoreItem)));
+    if (cudaMalloc(&d_x, n * sizeof(double)) != cudaSuccess) {
+        cudaFree(d_items);
+        return fail(CRP_ERR_NOMEM, "cudaMalloc failed");
+    }
+    int rc = 0;
+    do {
+        if (cudaMemcpyAsync(d_items, items.data(), n * sizeof(RescoreItem), cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            rc = fail(CRP_ERR_CUDA, "H2D of rescore items failed");
+            break;
+        }
+        k_rescore<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(g->plane(0), g->plane(1), g->plane(2), g->plane(3),
+                                                              d_items, n, d_x);
+        g_ctx.launches++;
+        if (cudaMemcpyAsync(x_out, d_x, n * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) {
+            rc = fail(CRP_ERR_CUDA, "rescore failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+    } while (0);
+    cudaFree(d_items);
+    cudaFree(d_x);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,202 @@
+"""Row emission: the reference's chunked, cumulative CSV writing, bug for bug.
+
+Host-side mirror of /root/reference/CROPSR.py:386-405 (header), :442-474
+(cumulative list, 1,000,000-row chunk plan, id indexing, row tuples),
+:155-158 (cut site) and :316-318 (ids).  All arithmetic on scores' inputs was
+done on the GPU (x per candidate, plus crp_rescore for the rows OpenBLAS sums
+in another lane order); here x only goes through the same ``1/(1+np.exp(x))``
+numpy expression the reference evaluates (CROPSR.py:313).
+"""
+import csv
+
+import numpy as np
+
+from . import blas_order
+
+HEADER = ["crispr_id", "crispr_sys", "sequence", "long_sequence", "chromosome", "start_pos",
+          "end_pos", "cutsite", "strand", "on_site_score", "features", "status"]
+CHUNK_ROWS = 1000000
+
+alphanum = np.array(list("ABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789"), dtype="|U1")
+
+
+def get_id(num_to_gen):
+    """CROPSR.py:316-318 -- same call on numpy's global legacy RNG, so a caller
+    that seeds np.random gets the reference's ids."""
+    return np.random.choice(alphanum, [num_to_gen, 7])
+
+
+def ids_to_strings(ids):
+    ids = np.ascontiguousarray(ids)
+    if ids.size == 0:
+        return []
+    return ids.view("<U7").ravel().tolist()
+
+
+def apply_cutsite(start_pos, end_pos, crispr_sys):
+    """CROPSR.py:155-158."""
+    if crispr_sys == "cas9":
+        cutsite = end_pos - 3
+    return cutsite
+
+
+def emission_slices(size):
+    """(start, count) of every slice of a cumulative list of `size` rows that
+    the reference scores and writes (CROPSR.py:451-472): full 1e6-row slices,
+    then -- because the start of the last slice is computed as count*counter --
+    a last partial slice that starts at r*q instead of 1e6*q; when size is an
+    exact multiple of 1e6 the final full slice is never written."""
+    q, r = divmod(size, CHUNK_ROWS)
+    if r:
+        return [(CHUNK_ROWS * j, CHUNK_ROWS) for j in range(q)] + [(r * q, r)]
+    return [(CHUNK_ROWS * j, CHUNK_ROWS) for j in range(max(q - 1, 0))]
+
+
+# byte translation of the reference's replace chains (CROPSR.py:120,128)
+def _table(pairs):
+    t = bytearray(range(256))
+    for a, b in pairs:
+        t[ord(a)] = ord(b)
+    return bytes(t)
+
+
+PLUS_TABLE = _table([("A", "U"), ("C", "G"), ("G", "C"), ("T", "A"), ("Z", "G")])    # gRNA(x), then reversed
+MINUS_TABLE = _table([("T", "U"), ("U", "A"), ("Z", "C")])                            # gRNA(revcomp(x)): forward
+
+
+def guide_strings(token, t, minus, guide_len):
+    """(short, long) CSV strings of the hit at regex position t (CROPSR.py:418-433),
+    with Python's silent slice truncation at the token end."""
+    if minus:
+        p0 = t + 3
+        p1 = p0 + guide_len
+        return (token[p0:p1].translate(MINUS_TABLE).decode("ascii"),
+                token[p0 - 5:p1 + 5].translate(MINUS_TABLE).decode("ascii"))
+    p0 = t - guide_len
+    return (token[p0:t].translate(PLUS_TABLE)[::-1].decode("ascii"),
+            token[p0 - 5:t + 5].translate(PLUS_TABLE)[::-1].decode("ascii"))
+
+
+class CandidateTable:
+    """Unique candidates of all tokens seen so far, in reference order
+    (per token: '+' by ascending t, then '-' by ascending t)."""
+
+    def __init__(self, guide_len):
+        self.guide_len = guide_len
+        self.tokens = []      # bytes per token
+        self.chroms = []      # CSV chromosome string per token (key[1:])
+        self.tok = np.empty(0, np.uint32)
+        self.seg = np.empty(0, np.uint32)
+        self.minus = np.empty(0, np.bool_)
+        self.t = np.empty(0, np.uint32)
+        self.x = np.empty(0, np.float64)
+
+    def __len__(self):
+        return len(self.t)
+
+    def append_token(self, key, token_bytes, seg_index, t_plus, x_plus, t_minus, x_minus):
+        k = len(self.tokens)
+        self.tokens.append(token_bytes)
+        self.chroms.append(key[1:])
+        n_p, n_m = len(t_plus), len(t_minus)
+        n = n_p + n_m
+        self.tok = np.concatenate((self.tok, np.full(n, k, np.uint32)))
+        self.seg = np.concatenate((self.seg, np.full(n, seg_index, np.uint32)))
+        self.minus = np.concatenate((self.minus, np.zeros(n_p, np.bool_), np.ones(n_m, np.bool_)))
+        self.t = np.concatenate((self.t, t_plus, t_minus)).astype(np.uint32)
+        nan = np.full(0, np.nan)
+        xp = x_plus if x_plus is not None else np.full(n_p, np.nan)
+        xm = x_minus if x_minus is not None else np.full(n_m, np.nan)
+        self.x = np.concatenate((self.x, xp, xm, nan))
+
+
+def long_length(table, idx):
+    """len(long_sequence) of candidates idx (vectorised Python-slice arithmetic)."""
+    l = table.guide_len
+    t = table.t[idx].astype(np.int64)
+    L = np.array([len(tok) for tok in table.tokens], dtype=np.int64)[table.tok[idx]]
+    minus = table.minus[idx]
+    lo = np.where(minus, t - 2, t - l - 5)
+    hi = np.where(minus, t + l + 8, t + 5)
+    return np.minimum(hi, L) - np.maximum(lo, 0)
+
+
+def slice_scores(table, genome, start, count, blas_threads=1):
+    """on_site_score of rows [start, start+count) scored as ONE reference
+    rs1_score call (CROPSR.py:461): x from the scan, the rows OpenBLAS sums in a
+    non-canonical lane order re-evaluated on the GPU, then the reference's
+    logistic.  Rows whose long_sequence is not 30 long get NaN (score -1 rows)."""
+    idx = np.arange(start, start + count)
+    x = table.x[idx].copy()
+    scored = long_length(table, idx) == 30
+    fix = {}
+    if table.guide_len != 20:
+        # a window truncated by the token end to exactly 30 bases is scored by the
+        # reference even though guide_len != 20; its bases are those of the
+        # guide_len == 20 window at a shifted position
+        for i in np.nonzero(scored)[0]:
+            fix[int(i)] = blas_order.CANONICAL
+    for i, cls in blas_order.slice_classes(count, blas_threads).items():
+        if scored[i]:
+            fix[i] = cls
+    if fix:
+        rows = np.array(sorted(fix), dtype=np.int64)
+        cand = idx[rows]
+        t = table.t[cand].astype(np.int64)
+        if table.guide_len != 20:
+            L = np.array([len(tok) for tok in table.tokens], dtype=np.int64)[table.tok[cand]]
+            t = np.where(table.minus[cand], t, L - 5)
+        strand = np.where(table.minus[cand], b"-", b"+").astype("S1")
+        cls = np.array([fix[int(i)] for i in rows], dtype=np.uint8)
+        x[rows] = genome.rescore(table.seg[cand], t, strand, cls)
+    x[~scored] = np.nan
+    with np.errstate(all="ignore"):
+        return 1 / (1 + np.exp(x)), scored
+
+
+def slice_rows(table, ids, scores, scored, start, count):
+    """Row tuples of one emitted slice (CROPSR.py:463-469)."""
+    l = table.guide_len
+    rows = []
+    tok_i = table.tok[start:start + count].tolist()
+    minus = table.minus[start:start + count].tolist()
+    ts = table.t[start:start + count].tolist()
+    sc = scores.tolist()
+    ok = scored.tolist()
+    for k in range(count):
+        t = ts[k]
+        token = table.tokens[tok_i[k]]
+        short, long_ = guide_strings(token, t, minus[k], l)
+        if minus[k]:
+            first, second, strand = t + 3 + l, t + 3, "-"
+        else:
+            first, second, strand = t - l, t, "+"
+        rid = ids[start - k - 1]
+        chrom = table.chroms[tok_i[k]]
+        if ok[k]:
+            rows.append((rid, "cas9", short, long_, chrom, first, second,
+                         apply_cutsite(first, second, "cas9"), strand, sc[k], "", "completed"))
+        else:
+            rows.append((rid, "cas9", short, long_, chrom, first, second, strand, -1, "", "completed"))
+    return rows
+
+
+def write_header(path):
+    with open(path, "w", newline="") as f:
+        csv.writer(f).writerow(HEADER)
+
+
+def emit_cumulative(path, table, genome, blas_threads=1):
+    """Append the rows the reference writes after one more token has been
+    scanned: ALL candidates accumulated so far (CROPSR.py:407,442), through the
+    chunk plan.  Returns the number of rows written."""
+    size = len(table)
+    written = 0
+    with open(path, "a", newline="") as f:
+        w = csv.writer(f)
+        ids = ids_to_strings(get_id(size))
+        for start, count in emission_slices(size):
+            scores, scored = slice_scores(table, genome, start, count, blas_threads)
+            w.writerows(slice_rows(table, ids, scores, scored, start, count))
+            written += count
+    return written

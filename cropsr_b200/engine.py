@@ -1,0 +1,223 @@
+"""Python face of the C ABI: device, packed genome shard, candidate streams.
+
+Everything that computes happens in libcropsr_b200.so on the GPU; this module
+only owns handles, numpy output buffers and index arithmetic.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from ._native import CropsrError, check, lib
+
+_device = None
+
+SEGMENT_ALIGN = 128   # crp_genome_add_segment: seg_begin granularity
+TILE = 8192           # positions per scan tile (csrc/cropsr_b200.cu kTile)
+
+
+def init(device=0):
+    """Bind this process to one GPU (one process per GPU)."""
+    global _device
+    if _device is not None and _device != device:
+        raise CropsrError(-3, f"already initialised on device {_device}")
+    check(lib.crp_init(int(device)))
+    _device = int(device)
+    return _device
+
+
+def shutdown():
+    global _device
+    check(lib.crp_shutdown())
+    _device = None
+
+
+def device_count():
+    n = C.c_int(0)
+    check(lib.crp_device_count(C.byref(n)))
+    return n.value
+
+
+def launch_count():
+    n = C.c_uint64(0)
+    check(lib.crp_launch_count(C.byref(n)))
+    return n.value
+
+
+def _as_u8(token):
+    """Token -> contiguous uint8 numpy view (str is encoded; must be ASCII)."""
+    if isinstance(token, str):
+        try:
+            token = token.encode("ascii")
+        except UnicodeEncodeError as e:
+            raise ValueError("sequence tokens must be ASCII (the reference's rs1 scoring "
+                             "raises on non-ASCII windows, CROPSR.py:458)") from e
+    arr = np.frombuffer(token, dtype=np.uint8) if not isinstance(token, np.ndarray) else token
+    if arr.dtype != np.uint8 or arr.ndim != 1:
+        raise ValueError("token must be bytes-like or a 1-D uint8 array")
+    return np.ascontiguousarray(arr)
+
+
+class PinnedBuffer:
+    """Page-locked host memory from crp_host_alloc, exposed as a numpy array."""
+
+    def __init__(self, nbytes):
+        self._ptr = C.c_void_p()
+        check(lib.crp_host_alloc(C.byref(self._ptr), int(nbytes)))
+        self.nbytes = int(nbytes)
+        buf = (C.c_uint8 * max(self.nbytes, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=np.uint8, count=self.nbytes)
+
+    def view(self, dtype, count, offset=0):
+        return self.array[offset:offset + count * np.dtype(dtype).itemsize].view(dtype)
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            check(lib.crp_host_free(self._ptr))
+            self._ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Genome:
+    """A genome shard: an ordered list of token segments packed into HBM."""
+
+    def __init__(self):
+        if _device is None:
+            init(0)
+        self._h = C.c_void_p()
+        check(lib.crp_genome_new(C.byref(self._h)))
+        self._keep = []          # host arrays that must outlive commit()
+        self.segments = []       # (token_id, token_len, begin, end)
+        self.committed = False
+
+    def add_segment(self, token_id, token, begin=0, end=None):
+        arr = _as_u8(token)
+        end = len(arr) if end is None else int(end)
+        check(lib.crp_genome_add_segment(self._h, int(token_id), arr.ctypes.data, len(arr), int(begin), end))
+        self._keep.append(arr)
+        self.segments.append((int(token_id), len(arr), int(begin), end))
+        return len(self.segments) - 1
+
+    def add_token(self, token, token_id=None):
+        return self.add_segment(len(self.segments) if token_id is None else token_id, token)
+
+    def commit(self):
+        check(lib.crp_genome_commit(self._h))
+        self._keep = []
+        self.committed = True
+        return self
+
+    @property
+    def num_positions(self):
+        n = C.c_uint64(0)
+        check(lib.crp_genome_num_positions(self._h, C.byref(n)))
+        return n.value
+
+    def timing(self):
+        a, b = C.c_float(0), C.c_float(0)
+        check(lib.crp_genome_timing(self._h, C.byref(a), C.byref(b)))
+        return {"h2d_ms": a.value, "pack_ms": b.value}
+
+    def scan(self, guide_len=20, flags=N.CRP_SCAN_DEFAULT):
+        res = C.c_void_p()
+        check(lib.crp_scan_score(self._h, int(guide_len), int(flags), C.byref(res)))
+        return ScanResult(self, res, guide_len, flags)
+
+    def rescore(self, segment, t, strand, cls):
+        """x of the given candidates re-summed in BLAS class cls (see blas_order)."""
+        segment = np.ascontiguousarray(segment, dtype=np.uint32)
+        t = np.ascontiguousarray(t, dtype=np.uint32)
+        strand = np.ascontiguousarray(strand, dtype="S1")
+        cls = np.ascontiguousarray(cls, dtype=np.uint8)
+        n = len(t)
+        out = np.empty(n, dtype=np.float64)
+        if n:
+            check(lib.crp_rescore(self._h, n, segment.ctypes.data, t.ctypes.data, strand.ctypes.data,
+                                  cls.ctypes.data, out.ctypes.data))
+        return out
+
+    def free(self):
+        if self._h:
+            check(lib.crp_genome_free(self._h))
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class ScanResult:
+    """Two ordered candidate streams ('+', '-') resident in HBM."""
+
+    def __init__(self, genome, handle, guide_len, flags):
+        self.genome = genome
+        self._h = handle
+        self.guide_len = int(guide_len)
+        self.flags = int(flags)
+        self.scored = self.guide_len == 20 and not (flags & N.CRP_SCAN_NO_SCORE)
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        check(lib.crp_result_totals(self._h, C.byref(a), C.byref(b)))
+        self.n_plus, self.n_minus = a.value, b.value
+        ns = len(genome.segments)
+        self.seg_plus = np.zeros(ns, dtype=np.uint64)
+        self.seg_minus = np.zeros(ns, dtype=np.uint64)
+        if ns:
+            check(lib.crp_result_segment_counts(self._h, self.seg_plus.ctypes.data, self.seg_minus.ctypes.data))
+        # first candidate of every segment inside each strand stream
+        self.off_plus = np.concatenate(([0], np.cumsum(self.seg_plus))).astype(np.uint64)
+        self.off_minus = np.concatenate(([0], np.cumsum(self.seg_minus))).astype(np.uint64)
+
+    def scan_ms(self):
+        v = C.c_float(0)
+        check(lib.crp_result_timing(self._h, C.byref(v)))
+        return v.value
+
+    def device_counts_ptr(self):
+        p = C.c_void_p()
+        check(lib.crp_result_device_counts(self._h, C.byref(p)))
+        return p.value
+
+    def fetch(self, strand, first=0, count=None, out=None, want=("pos", "packed", "x")):
+        """Copy [first, first+count) of one strand stream to host numpy arrays.
+        Returns dict(pos=uint32[], packed=uint64[], x=float64[]); packed / x only
+        exist for scored results.  `out` may supply preallocated (pinned) arrays."""
+        total = self.n_plus if strand == "+" else self.n_minus
+        count = total - first if count is None else count
+        out = {} if out is None else out
+        res = {}
+        for name, dt in (("pos", np.uint32), ("packed", np.uint64), ("x", np.float64)):
+            if name not in want or (name != "pos" and not self.scored):
+                res[name] = None
+                continue
+            arr = out.get(name)
+            if arr is None:
+                arr = np.empty(count, dtype=dt)
+            assert arr.dtype == dt and len(arr) >= count and arr.flags.c_contiguous
+            res[name] = arr[:count]
+        ptr = lambda a: a.ctypes.data if a is not None and len(a) else None
+        check(lib.crp_result_fetch(self._h, strand.encode(), int(first), int(count),
+                                   ptr(res["pos"]), ptr(res["packed"]), ptr(res["x"])))
+        return res
+
+    def fetch_segment(self, seg, strand, **kw):
+        off = self.off_plus if strand == "+" else self.off_minus
+        return self.fetch(strand, int(off[seg]), int(off[seg + 1] - off[seg]), **kw)
+
+    def free(self):
+        if self._h:
+            check(lib.crp_result_free(self._h))
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

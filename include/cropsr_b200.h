@@ -1,0 +1,147 @@
+/*
+ * cropsr_b200.h -- C ABI of libcropsr_b200.so: the B200 (sm_100a) implementation
+ * of CROPSR's genome-wide Cas9 gRNA candidate scan + Rule-Set-1 scoring.
+ *
+ * The reference (H2muller/CROPSR) has no FFI: its hot path is Python inside
+ * CROPSR.py main().  Each entry point below names the reference code it
+ * replaces (paths relative to /root/reference).  The Python host
+ * (cropsr_b200/) binds these with ctypes; INTEGRATION.md shows the binding a
+ * maintainer would add to the reference's own CROPSR.py.
+ *
+ * Conventions: every function returns 0 on success or a negative crp_status;
+ * crp_last_error() gives the message for the calling thread.  Device memory is
+ * owned by the opaque handles; host output buffers are caller-allocated.  All
+ * calls are synchronous with respect to the host unless stated.  One process
+ * drives one GPU (crp_init picks it); multi-GPU runs use one process per GPU.
+ * There is no CPU fallback: without a usable CUDA device every compute entry
+ * point fails with CRP_ERR_CUDA.
+ */
+#ifndef CROPSR_B200_H
+#define CROPSR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum crp_status {
+    CRP_OK = 0,
+    CRP_ERR_CUDA = -1,      /* CUDA runtime/driver error (message has the detail) */
+    CRP_ERR_ARG = -2,       /* bad argument                                        */
+    CRP_ERR_STATE = -3,     /* call out of order (e.g. scan before commit)         */
+    CRP_ERR_NOMEM = -4,     /* host or device allocation failed                    */
+    CRP_ERR_RANGE = -5      /* token/segment too large for the 31-bit position     */
+} crp_status;
+
+typedef struct crp_genome crp_genome;   /* packed genome shard resident in HBM     */
+typedef struct crp_result crp_result;   /* compacted candidate streams in HBM      */
+
+/* ---- scan flags --------------------------------------------------------- */
+#define CRP_SCAN_DEFAULT     0u
+#define CRP_SCAN_NO_SCORE    1u   /* positions only (forced when guide_len != 20)  */
+#define CRP_SCAN_LOGISTIC    2u   /* store 1/(1+exp(x)) instead of x (see below)   */
+#define CRP_SCAN_EXTRAS      4u   /* also compute the opt-in per-candidate extras  */
+
+/* ---- summation classes for crp_rescore -------------------- */
+#define CRP_CLASS_CANONICAL  0    /* 4 lanes by column mod 4, (p0+p2)+(p1+p3)      */
+#define CRP_CLASS_PAIR       1    /* 2 lanes by column mod 2, q0+q1                */
+#define CRP_CLASS_SINGLE     2    /* n==1 np.matmul -> ddot lane order             */
+
+/* ---- packed 30-mer layout (one uint64 per candidate) --------------------
+ * The scored 30-mer in output order q = 0..29 (the order of the CSV
+ * long_sequence column), 2 bits per base, PLANAR, code A0 T1 C2 G3
+ * (reference CROPSR.py:300-302):
+ *   bits  0..29  low  code bit of base q        bit 30  window has a byte that is
+ *   bits 32..61  high code bit of base q                not uppercase ACGT
+ *   bit 31  window truncated at the token end (reference emits an 11-field
+ *           "error row" with score -1, CROPSR.py:466-468)
+ *   bit 62  some base contributes nothing to the score (N, IUPAC, quote, ...)
+ *   bit 63  reserved (0)
+ */
+#define CRP_PACKED_IRREGULAR  (1ull << 30)
+#define CRP_PACKED_TRUNCATED  (1ull << 31)
+#define CRP_PACKED_UNSCORED   (1ull << 62)
+
+/* ---- library / device ---------------------------------------------------- */
+
+/* Select the CUDA device this process drives and create the library's stream. */
+int crp_init(int device);
+int crp_shutdown(void);
+const char *crp_last_error(void);
+int crp_device_count(int *count);
+/* ABI version of this header (bumped on any signature change). */
+int crp_abi_version(void);
+
+/* Pinned host memory for staging (FASTA bytes in, candidate arrays out). */
+int crp_host_alloc(void **ptr, uint64_t bytes);
+int crp_host_free(void *ptr);
+
+/* ---- ingest: replaces the per-token Python strings of the ingest dict -----
+ * (CROPSR.py:54-74 import_fasta_file; the values of the dict built by
+ * cropsr_functions.py:190-196 generate_dictionary).  A *token* is one dict
+ * value, decoration bytes of the formatted path included.  A *segment* is the
+ * part [seg_begin, seg_end) of a token whose PAM positions this GPU owns; the
+ * library stages the halo it needs from the token itself.
+ */
+int crp_genome_new(crp_genome **g);
+/* token_ascii points at position 0 of the whole token in host memory and must
+ * stay valid until crp_genome_commit returns.  seg_begin must be a multiple of
+ * 128 (0 for a whole token).  Segments are scanned in the order added. */
+int crp_genome_add_segment(crp_genome *g, uint32_t token_id,
+                           const uint8_t *token_ascii, uint64_t token_len,
+                           uint64_t seg_begin, uint64_t seg_end);
+/* H2D copy + pack kernel: ASCII -> 2-bit code planes + lower-case plane +
+ * other-byte plane (0.5 byte per base resident in HBM). */
+int crp_genome_commit(crp_genome *g);
+int crp_genome_num_segments(const crp_genome *g, uint32_t *n);
+int crp_genome_num_positions(const crp_genome *g, uint64_t *n);   /* sum of segment lengths */
+int crp_genome_free(crp_genome *g);
+
+/* ---- scan + score: replaces CROPSR.py:413-434 (regex PAM scan, bounds,
+ * window slicing, gRNA / reverse-complement transforms) and CROPSR.py:285-313
+ * (rs1_score) for every segment of the genome in one launch sequence.
+ * Output per strand is ONE ordered stream over (segment order, ascending t):
+ *   pos     uint32  t, the regex match position inside the token
+ *   packed  uint64  see layout above               (guide_len == 20 only)
+ *   x       float64 pre-activation -(((A+B)+0.59763615)+(-0.2026259)) summed
+ *                   in the canonical lane order; the reference's score is
+ *                   1/(1+np.exp(x)) (CROPSR.py:312-313).  With
+ *                   CRP_SCAN_LOGISTIC the stored value is 1/(1+exp(x)) using
+ *                   the device's exp (<= 2 ulp from numpy's).
+ * Reference order of a token's candidates = its '+' stream then its '-' stream
+ * (CROPSR.py:417-434).
+ */
+int crp_scan_score(crp_genome *g, int guide_len, uint32_t flags, crp_result **res);
+int crp_result_totals(const crp_result *res, uint64_t *n_plus, uint64_t *n_minus);
+/* Per-segment candidate counts, arrays of crp_genome_num_segments() entries. */
+int crp_result_segment_counts(const crp_result *res, uint64_t *n_plus, uint64_t *n_minus);
+/* Device pointer to uint64[2*num_segments] {plus[0..n), minus[0..n)} for the
+ * NCCL all-gather of per-shard counts (global offsets across GPUs). */
+int crp_result_device_counts(const crp_result *res, void **dev_ptr);
+/* Copy candidates [first, first+count) of one strand stream ('+' or '-') to
+ * caller-allocated host arrays; any output pointer may be NULL. */
+int crp_result_fetch(const crp_result *res, char strand, uint64_t first, uint64_t count,
+                     uint32_t *pos, uint64_t *packed, double *x);
+int crp_result_free(crp_result *res);
+
+/* Re-evaluate x for selected candidates in a given BLAS summation class
+ * (rows of an np.matmul call that OpenBLAS sums in a different lane order:
+ * the tail rows of each emitted slice).  Items are identified by
+ * (segment index, t, strand).  cls[i] = class of the first-order product
+ * (matrix1 @ first_matrix, CROPSR.py:305) | class of the dinucleotide product
+ * (matrix2 @ second_matrix, CROPSR.py:311) << 4. */
+int crp_rescore(const crp_genome *g, uint64_t n, const uint32_t *segment, const uint32_t *t,
+                const char *strand, const uint8_t *cls, double *x_out);
+
+/* Kernel timings (CUDA events on the library stream) of the last commit /
+ * scan: milliseconds. */
+int crp_genome_timing(const crp_genome *g, float *ms_h2d, float *ms_pack);
+int crp_result_timing(const crp_result *res, float *ms_scan);
+/* Number of kernel launches issued by this library since crp_init. */
+int crp_launch_count(uint64_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CROPSR_B200_H */

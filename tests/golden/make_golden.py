@@ -36,7 +36,7 @@ runpy.run_path(%r, run_name='__main__')
 #        name                     fasta                    -l  seed threads
 CASES = [
     ("sample",                "sample_genome.fa",          20, 11, 1),
-    ("sample_t8",             "sample_genome.fa",          20, 11, 8),
+    ("sample_t6",             "sample_genome.fa",          20, 11, 6),
     ("multi3",                "multi3.fa",                 20, 12, 1),
     ("multi3_l18",            "multi3.fa",                 18, 13, 1),
     ("multi3_l23",            "multi3.fa",                 23, 14, 1),
@@ -49,7 +49,7 @@ CASES = [
     ("dup_keys",              "dup_keys.fa",               20, 21, 1),
     ("empty_records",         "empty_records.fa",          20, 22, 1),
     ("mid50k",                "mid50k.fa",                 20, 23, 1),
-    ("mid50k_t8",             "mid50k.fa",                 20, 23, 8),
+    ("mid50k_t5",             "mid50k.fa",                 20, 23, 5),
 ]
 
 

@@ -1,0 +1,230 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and with the
+golden CSVs of the unmodified reference.  Everything here needs a B200."""
+import csv
+import io
+import os
+
+import numpy as np
+import pytest
+
+import cropsr_oracle as oracle
+from helpers import fixture_path, fixture_text, golden_csv, normalised_digest, synthetic_fasta
+
+pytestmark = pytest.mark.gpu
+
+ALL_CASES = ["sample", "sample_t6", "multi3", "multi3_l18", "multi3_l23", "clean3", "clean3_trailing_nl",
+             "edge_clean", "edge_fmt", "single_candidate", "ws_header", "dup_keys", "empty_records",
+             "mid50k", "mid50k_t5"]
+
+
+@pytest.fixture(scope="module")
+def eng(built_lib):
+    from cropsr_b200 import engine
+    engine.init(0)
+    return engine
+
+
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_cli_csv_is_byte_identical_to_reference(name, manifest, eng, tmp_path, capsys):
+    """Full drop-in run: FASTA -> CSV, ids seeded like the golden run."""
+    from cropsr_b200 import pipeline
+    case = manifest["cases"][name]
+    out = tmp_path / "out.csv"
+    np.random.seed(case["seed"])
+    lines = []
+    pipeline.run_cas9(fixture_path(case["fasta"]), fixture_path("sample_genome.gff"), str(out),
+                      case["guide_len"], False, case["blas_threads"], str(tmp_path / "time.txt"),
+                      out=lambda *a: lines.append(" ".join(a)))
+    got = out.read_bytes().decode()
+    assert got == golden_csv(name)
+    want_stdout = open(os.path.join(os.path.dirname(fixture_path("x")), "..", "cases", name + ".stdout")).read()
+    assert "\n".join(lines) + ("\n" if lines else "") == want_stdout
+    assert (tmp_path / "time.txt").read_text().count("Total runtime of the program is ") == case["time_txt_records"]
+
+
+def _check_against_oracle(eng, text, guide_len):
+    from cropsr_b200 import ingest, pipeline, _native as N
+    tokens = ingest.fasta_text_to_tokens(text)
+    genome, result, _ = pipeline.scan_tokens(tokens, guide_len)
+    try:
+        for seg, (key, tok) in enumerate(tokens.items()):
+            plus, minus = oracle.pam_hits(tok, guide_len)
+            gp = result.fetch_segment(seg, "+")
+            gm = result.fetch_segment(seg, "-")
+            assert gp["pos"].tolist() == plus
+            assert gm["pos"].tolist() == minus
+            if guide_len != 20:
+                assert gp["x"] is None
+                continue
+            cands = oracle.candidates_for_token(key, tok, guide_len)
+            x = np.concatenate((gp["x"], gm["x"]))
+            packed = np.concatenate((gp["packed"], gm["packed"]))
+            full = np.array([len(c[4]) == 30 for c in cands], dtype=bool)
+            assert np.array_equal((packed & np.uint64(N.PACKED_TRUNCATED)) != 0, ~full)
+            if full.any():
+                seqs = np.array([oracle.scored_bytes(c[4]) for c, f in zip(cands, full) if f])
+                want = oracle.preactivation_model(seqs, classes=np.zeros(len(seqs), dtype=np.int8))
+                assert np.array_equal(x[full], want)
+                # packed 30-mer: planar A0 T1 C2 G3 codes of the scored bases
+                code = np.full(seqs.shape, -1)
+                for c, b in enumerate(b"ATCG"):
+                    code[seqs == b] = c
+                lo = np.array([sum(((int(v) & 1) << q) for q, v in enumerate(row) if v >= 0) for row in code], dtype=np.uint64)
+                hi = np.array([sum((((int(v) >> 1) & 1) << q) for q, v in enumerate(row) if v >= 0) for row in code], dtype=np.uint64)
+                scoring = code >= 0
+                pk = packed[full]
+                got_lo = pk & np.uint64(0x3FFFFFFF)
+                got_hi = (pk >> np.uint64(32)) & np.uint64(0x3FFFFFFF)
+                mask = np.array([sum((1 << q) for q, v in enumerate(row) if v) for row in scoring], dtype=np.uint64)
+                assert np.array_equal(got_lo & mask, lo) and np.array_equal(got_hi & mask, hi)
+                assert np.array_equal((pk & np.uint64(N.PACKED_UNSCORED)) != 0, ~scoring.all(axis=1))
+                irregular = np.array([any(ch not in "AUCG" for ch in c[4]) for c, f in zip(cands, full) if f])
+                assert np.array_equal((pk & np.uint64(N.PACKED_IRREGULAR)) != 0, irregular)
+    finally:
+        result.free()
+        genome.free()
+
+
+@pytest.mark.parametrize("fasta", ["multi3.fa", "clean3.fa", "edge_clean.fa", "edge_fmt.fa", "ws_header.fa",
+                                   "dup_keys.fa", "empty_records.fa", "single_candidate.fa", "mid50k.fa",
+                                   "sample_genome.fa"])
+@pytest.mark.parametrize("guide_len", [20, 18, 23])
+def test_candidate_streams_match_oracle(eng, fasta, guide_len):
+    _check_against_oracle(eng, fixture_text(fasta), guide_len)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_fastas_match_oracle(eng, seed):
+    rng = np.random.default_rng(1000 + seed)
+    n_rec = int(rng.integers(1, 6))
+    alphabet = np.frombuffer(b"ACGTacgtNRYUZ", dtype=np.uint8)
+    p = np.array([20, 20, 20, 20, 3, 3, 3, 3, 1, .3, .3, .2, .2])
+    recs = []
+    for k in range(n_rec):
+        n = int(rng.integers(0, 30000)) if seed % 3 else int(rng.integers(0, 200))
+        recs.append((f"r{k}", rng.choice(alphabet, size=n, p=p / p.sum()).tobytes().decode()))
+    if seed % 2:
+        text = "".join(f">{h}\n" + "\n".join(s[i:i + 70] for i in range(0, len(s), 70)) + "\n" for h, s in recs)
+    else:
+        text = "\n".join(f">{h}\n{s}" for h, s in recs if s)
+    _check_against_oracle(eng, text, 20)
+
+
+def test_tile_boundaries_and_dense_hits(eng):
+    # PAMs straddling every 8192-position tile edge; poly-G / poly-C worst-case density
+    body = bytearray(b"AT" * 20000)
+    for edge in (8192, 16384, 24576, 32768):
+        for off in range(-3, 3):
+            body[edge + off] = ord("G")
+        body[edge - 40:edge - 36] = b"CCCC"
+    text = ">t\n" + body.decode() + "\n>g\n" + "G" * 20000 + "\n>c\n" + "C" * 20000 + "\n"
+    _check_against_oracle(eng, text, 20)
+
+
+def test_rescore_classes_match_oracle(eng):
+    from cropsr_b200 import ingest, pipeline
+    text = fixture_text("mid50k.fa")
+    tokens = ingest.fasta_text_to_tokens(text)
+    genome, result, _ = pipeline.scan_tokens(tokens, 20)
+    (key, tok), = tokens.items()
+    cands = [c for c in oracle.candidates_for_token(key, tok, 20) if len(c[4]) == 30][:600]
+    seqs = np.array([oracle.scored_bytes(c[4]) for c in cands])
+    t = np.array([c[1] - 3 if c[6] == "-" else c[1] for c in cands], dtype=np.uint32)
+    strand = np.array([c[6].encode() for c in cands], dtype="S1")
+    seg = np.zeros(len(cands), dtype=np.uint32)
+    for c1 in (0, 1, 2):
+        for c2 in (0, 1, 2):
+            m1, m2 = oracle.indicator_matrices(seqs)
+            a = oracle.lane_sums(m1, oracle.W1, np.full(len(seqs), c1, dtype=np.int8))
+            b = oracle.lane_sums(m2, oracle.W2, np.full(len(seqs), c2, dtype=np.int8))
+            want = (a + b + oracle.INTERCEPT + oracle.LOW_GC) * -1
+            got = genome.rescore(seg, t, strand, np.full(len(seqs), c1 | (c2 << 4), dtype=np.uint8))
+            assert np.array_equal(got, want), (c1, c2)
+    result.free()
+    genome.free()
+
+
+def test_sharded_scan_equals_whole_scan(eng):
+    """N logical shards on one GPU: segments with halos + offset arithmetic give
+    exactly the single-shard streams (the multi-GPU data path minus NCCL)."""
+    from cropsr_b200 import engine, ingest, shard
+    text = synthetic_fasta(7, [70000, 30000, 90000], gc=0.5)
+    tokens = ingest.fasta_text_to_tokens(text)
+    toks = [v.encode() for v in tokens.values()]
+    whole = engine.Genome()
+    for b in toks:
+        whole.add_token(b)
+    ref = whole.commit().scan(20)
+    ref_tab = []
+    for s in range(len(toks)):
+        for strand in "+-":
+            f = ref.fetch_segment(s, strand)
+            ref_tab += list(zip([s] * len(f["pos"]), [strand] * len(f["pos"]), f["pos"].tolist(), f["x"].tolist(), f["packed"].tolist()))
+    for ws in (2, 3, 4, 7):
+        plans = shard.plan([len(b) for b in toks], ws)
+        counts, rows = [], {}
+        for r, segs in enumerate(plans):
+            g = engine.Genome()
+            for k, a, b in segs:
+                g.add_segment(k, toks[k], a, b)
+            res = g.commit().scan(20)
+            counts.append((res.seg_plus.tolist(), res.seg_minus.tolist()))
+            rows[r] = [(res.fetch_segment(s, "+"), res.fetch_segment(s, "-")) for s in range(len(segs))]
+            res.free()
+            g.free()
+        offs, total = shard.global_offsets(plans, counts)
+        assert total == len(ref_tab)
+        table = [None] * total
+        for r, segs in enumerate(plans):
+            for s, (k, a, b) in enumerate(segs):
+                for si, strand in enumerate("+-"):
+                    f = rows[r][s][si]
+                    for i in range(len(f["pos"])):
+                        table[offs[r][s][si] + i] = (k, strand, int(f["pos"][i]), float(f["x"][i]), int(f["packed"][i]))
+        assert table == ref_tab, ws
+    ref.free()
+    whole.free()
+
+
+def test_full_size_properties(eng):
+    """At a BASELINE-scale chromosome (34 Mbp) the oracle is too slow for the
+    whole thing, so check size-independent properties: sorted, unique positions;
+    every reported hit is a PAM in the text; a sampled window re-scored through
+    the dense crp_rescore path equals the fused kernel's x; counts equal a
+    vectorised numpy PAM count."""
+    from cropsr_b200 import engine, ingest
+    text = synthetic_fasta(2, [34000000], gc=0.36, lower_frac=0.15)
+    tokens = ingest.fasta_text_to_tokens(text)
+    (key, tok), = tokens.items()
+    b = tok.encode()
+    arr = np.frombuffer(b, dtype=np.uint8)
+    g = engine.Genome()
+    g.add_token(b)
+    res = g.commit().scan(20)
+    L = len(arr)
+    isg, isc = arr == ord("G"), arr == ord("C")
+    plus = np.nonzero(isg[1:-1] & isg[2:])[0]
+    plus = plus[plus >= 25]
+    minus = np.nonzero(isc[:-2] & isc[1:-1])[0]
+    minus = minus[(minus >= 2) & (minus <= L - 13)]
+    gp, gm = res.fetch("+"), res.fetch("-")
+    assert np.array_equal(gp["pos"], plus.astype(np.uint32))
+    assert np.array_equal(gm["pos"], minus.astype(np.uint32))
+    rng = np.random.default_rng(0)
+    for strand, f in (("+", gp), ("-", gm)):
+        pick = rng.choice(len(f["pos"]), size=20000, replace=False)
+        x2 = g.rescore(np.zeros(len(pick), np.uint32), f["pos"][pick], np.full(len(pick), strand.encode(), "S1"),
+                       np.zeros(len(pick), np.uint8))
+        assert np.array_equal(x2, f["x"][pick])
+        # and a smaller sample against the oracle's literal string path
+        for i in pick[:300]:
+            t = int(f["pos"][i])
+            if strand == "+":
+                long_ = oracle.grna(tok[t - 25:t + 5])
+            else:
+                long_ = oracle.grna(oracle.reverse_complement(tok[t - 2:t + 28]))
+            if len(long_) == 30:
+                want = oracle.preactivation_model(np.array([oracle.scored_bytes(long_)]), classes=np.zeros(1, np.int8))
+                assert f["x"][i] == want[0]
+    res.free()
+    g.free()

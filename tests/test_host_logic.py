@@ -1,0 +1,130 @@
+"""Host-side logic of the product package, checked against the oracle on the CPU
+(no compute calls into the CUDA library)."""
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cropsr_oracle as oracle
+from helpers import GOLDEN, ROOT, fixture_text
+
+
+def test_library_loads_and_exports_header_symbols(built_lib):
+    header = open(os.path.join(ROOT, "include", "cropsr_b200.h")).read()
+    declared = set(re.findall(r"\b(crp_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(built_lib.SIGNATURES), declared ^ set(built_lib.SIGNATURES)
+    for name in declared:
+        getattr(built_lib.lib, name)
+    assert built_lib.lib.crp_abi_version() == built_lib.ABI_VERSION
+    assert built_lib.lib.crp_last_error() is not None
+
+
+def test_compute_fails_loudly_without_gpu(built_lib):
+    import ctypes as C
+    n = C.c_int(-1)
+    rc = built_lib.lib.crp_device_count(C.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a GPU is present")
+    from cropsr_b200 import engine
+    with pytest.raises(built_lib.CropsrError):
+        engine.init(0)
+    g = C.c_void_p()
+    assert built_lib.lib.crp_genome_new(C.byref(g)) != 0       # no silent CPU path
+    assert b"crp_init" in built_lib.lib.crp_last_error()
+
+
+def test_ingest_matches_oracle(built_lib):
+    from cropsr_b200 import ingest
+    for path in glob.glob(os.path.join(GOLDEN, "fixtures", "*.fa")):
+        text = fixture_text(os.path.basename(path))
+        assert ingest.formatted(text) == oracle.formatted(text)
+        assert list(ingest.fasta_text_to_tokens(text).items()) == list(oracle.import_fasta_text(text).items())
+    for text in ("", ">a", ">a\n", ">a\nACGT", ">a\nACGT\n>b\nGG", "no header at all\nACGT\n", ">x y\nAC\nGT\n"):
+        assert list(ingest.fasta_text_to_tokens(text).items()) == list(oracle.import_fasta_text(text).items())
+
+
+def test_drop_in_module_names(built_lib):
+    import cropsr_functions
+    assert cropsr_functions.formatted(">a\nAC\nGT\n") == "[('a', 'ACGT')]"
+    assert cropsr_functions.generate_dictionary("k1 v1 k2") == {"k1": "v1", "k2": ""}
+
+
+def test_guide_strings_match_reference_transforms(built_lib):
+    from cropsr_b200 import emit
+    for fasta in ("edge_clean.fa", "edge_fmt.fa", "multi3.fa", "clean3.fa"):
+        for key, tok in oracle.import_fasta_text(fixture_text(fasta)).items():
+            for l in (18, 20, 21, 22, 23, 30):
+                for c in oracle.candidates_for_token(key, tok, l):
+                    minus = c[6] == "-"
+                    t = c[1] - 3 if minus else c[1]
+                    assert emit.guide_strings(tok.encode(), t, minus, l) == (c[3], c[4])
+
+
+def test_emission_slices(built_lib):
+    from cropsr_b200 import emit
+    for n in list(range(0, 40)) + [999999, 1000000, 1000001, 1124799, 2000000, 2000001, 3000000, 3500007]:
+        assert emit.emission_slices(n) == oracle.emission_slices(n)
+
+
+def test_blas_row_classes_match_oracle_model(built_lib):
+    from cropsr_b200 import blas_order
+    for threads in (1, 2, 8, 64):
+        for n in list(range(1, 70)) + [993, 994, 1001, 3839, 3840, 3842, 5003, 12345, 99998, 250003, 1000000]:
+            for d in (120, 464):
+                want = {i: int(c) for i, c in enumerate(oracle.row_classes(n, d, threads)) if c}
+                assert blas_order.noncanonical_rows(n, d, threads) == want, (threads, n, d)
+
+
+def test_ids_reproduce_reference_rng(built_lib):
+    from cropsr_b200 import emit
+    np.random.seed(3)
+    a = emit.ids_to_strings(emit.get_id(1000))
+    np.random.seed(3)
+    b = oracle.make_ids(1000)
+    assert a == b and len(a[0]) == 7
+
+
+def test_float_repr_equals_numpy_str():
+    rng = np.random.default_rng(0)
+    v = np.concatenate([1 / (1 + np.exp(rng.uniform(-20, 10, 200000))), 10.0 ** rng.uniform(-300, 300, 20000)])
+    assert [repr(x) for x in v.tolist()] == [str(x) for x in v]
+
+
+def test_shard_plan_and_offsets(built_lib):
+    from cropsr_b200 import shard
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        lens = [int(x) for x in rng.integers(0, 200000, size=int(rng.integers(1, 8)))]
+        for ws in (1, 2, 3, 4, 8):
+            plans = shard.plan(lens, ws)
+            # every position owned exactly once, in order, boundaries on the tile granule
+            seen = []
+            for segs in plans:
+                for k, a, b in segs:
+                    assert a % shard.TILE == 0 and 0 <= a <= b <= lens[k]
+                    seen.append((k, a, b))
+            assert seen == sorted(seen)
+            for k, n in enumerate(lens):
+                pieces = [(a, b) for kk, a, b in seen if kk == k and b > a]
+                assert sum(b - a for a, b in pieces) == n
+                for (a0, b0), (a1, b1) in zip(pieces, pieces[1:]):
+                    assert b0 == a1
+            # offsets: simulate counts = number of "hits" at fake positions
+            counts = [([(b - a) // 7 for _, a, b in segs], [(b - a) // 11 for _, a, b in segs]) for segs in plans]
+            offs, total = shard.global_offsets(plans, counts)
+            assert total == sum(sum(c[0]) + sum(c[1]) for c in counts)
+            rows = []
+            for r, segs in enumerate(plans):
+                for s, (k, a, b) in enumerate(segs):
+                    rows.append((offs[r][s][0], counts[r][0][s], k, 0, a))
+                    rows.append((offs[r][s][1], counts[r][1][s], k, 1, a))
+            rows = [x for x in rows if x[1]]
+            rows.sort()
+            pos = 0
+            for off, c, *_ in rows:
+                assert off == pos
+                pos += c
+            assert [(k, st, a) for _, _, k, st, a in rows] == sorted((k, st, a) for _, _, k, st, a in rows)

@@ -1,0 +1,69 @@
+"""The oracle is only trustworthy if it reproduces the unmodified reference:
+byte-for-byte against the golden CSVs made by tests/golden/make_golden.py and
+against the SURVEY section-4 digests of the reference's shipped output.csv."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import cropsr_oracle as oracle
+import rs1_table
+from helpers import fixture_text, golden_csv, normalised_digest
+
+# digests of /root/reference/sample_data/output.csv
+SHIPPED_DIGEST_NO_SCORE = "16c177dd33f76fe7ff47c5953efa3c3ba4ce1c8c5f4c43d040bdc617edf80c9d"
+SHIPPED_DIGEST_SCORE_12G = "4cc3ee77c556c5b3e1df05912306631193fefeeeacf55762eb9e9dc08af5ae3b"
+
+
+def test_weight_table_digests():
+    rs1_table.check_digests()
+
+
+def test_manifest_matches_files(manifest):
+    for name, case in manifest["cases"].items():
+        assert hashlib.sha256(golden_csv(name).encode()).hexdigest() == case["csv_sha256"], name
+
+
+@pytest.mark.parametrize("name", [
+    "sample", "sample_t6", "multi3", "multi3_l18", "multi3_l23", "clean3", "clean3_trailing_nl",
+    "edge_clean", "edge_fmt", "single_candidate", "ws_header", "dup_keys", "empty_records",
+    "mid50k", "mid50k_t5"])
+def test_oracle_reproduces_reference_csv(name, manifest):
+    case = manifest["cases"][name]
+    np.random.seed(case["seed"])
+    got = oracle.run_to_string(fixture_text(case["fasta"]), case["guide_len"], "model", case["blas_threads"])
+    assert got == golden_csv(name)
+
+
+def test_sample_matches_shipped_output_digests():
+    text = golden_csv("sample")
+    assert normalised_digest(text) == SHIPPED_DIGEST_NO_SCORE
+    assert normalised_digest(text, "%.12g") == SHIPPED_DIGEST_SCORE_12G
+
+
+def test_thread_model_matters():
+    # the multi-thread goldens differ from the 1-thread ones only in a few score strings
+    assert golden_csv("mid50k") != golden_csv("mid50k_t5")
+    assert normalised_digest(golden_csv("mid50k")) == normalised_digest(golden_csv("mid50k_t5"))
+
+
+def test_model_order_equals_this_machines_blas():
+    """score_model (explicit lane order) vs score_blas (np.matmul) -- only
+    meaningful where numpy links the OpenBLAS build the model was derived on."""
+    import os
+    if os.environ.get("OPENBLAS_NUM_THREADS", "") != "1":
+        pytest.skip("needs OPENBLAS_NUM_THREADS=1 set before numpy is imported")
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 3, 4, 5, 6, 7, 50, 1003):
+        seqs = rng.choice(np.frombuffer(b"ATCGN", dtype=np.uint8), size=(n, 30))
+        a, b = oracle.score_blas(seqs), oracle.score_model(seqs, 1)
+        if not np.array_equal(a, b):
+            pytest.skip("this machine's BLAS sums in a different order than the build container's")
+
+
+def test_emission_slices_closed_form():
+    for n in list(range(0, 40)) + [999999, 1000000, 1000001, 1124799, 2000000, 2000001, 3000000, 3500007]:
+        assert oracle.emission_slices(n) == oracle.emission_slices_closed_form(n)
+    # 1,124,799 rows -> rows 0..999,999 then 124,799..249,597
+    assert oracle.emission_slices(1124799) == [(0, 1000000), (124799, 124799)]
+    assert oracle.emission_slices(1000000) == []
