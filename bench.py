@@ -15,6 +15,7 @@ Under torchrun (N > 1) each rank owns one GPU and one contiguous shard of the
 genome; the only collective is the NCCL all-gather of per-segment counts.
 """
 import argparse
+import faulthandler
 import json
 import os
 import subprocess
@@ -26,6 +27,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+faulthandler.enable()
 
 WORKLOADS = {
     # name: (seed, chromosome lengths in bp, GC, lower-case fraction)   SURVEY.md 8d
@@ -213,7 +215,7 @@ def main():
         ns = len(mine)
         if ns:
             class _Raw:
-                __cuda_array_interface__ = {"shape": (2 * ns,), "typestr": "<i8", "data": (res.device_counts_ptr(), True),
+                __cuda_array_interface__ = {"shape": (2 * ns,), "typestr": "<i8", "data": (res.device_counts_ptr(), False),
                                             "version": 2}
             raw = torch.as_tensor(_Raw(), device="cuda")
             buf[:ns] = raw[:ns]
@@ -268,9 +270,10 @@ def main():
         all_gather_counts(r)
         if out_bufs is None or out_bufs[0] < max(r.n_plus, r.n_minus):
             cap = int(max(r.n_plus, r.n_minus) * 1.05) + 1024
-            out_bufs = (cap, [{"pos": engine.PinnedBuffer(4 * cap).view(np.uint32, cap),
-                               "packed": engine.PinnedBuffer(8 * cap).view(np.uint64, cap),
-                               "x": engine.PinnedBuffer(8 * cap).view(np.float64, cap)} for _ in range(2)])
+            keep = [[engine.PinnedBuffer(4 * cap), engine.PinnedBuffer(8 * cap), engine.PinnedBuffer(8 * cap)]
+                    for _ in range(2)]          # the PinnedBuffer objects own the memory: keep them alive
+            out_bufs = (cap, [{"pos": k[0].view(np.uint32, cap), "packed": k[1].view(np.uint64, cap),
+                               "x": k[2].view(np.float64, cap)} for k in keep], keep)
         r.fetch("+", out=out_bufs[1][0])
         r.fetch("-", out=out_bufs[1][1])
         barrier()

@@ -29,11 +29,12 @@
 #define CRP_ABI_VERSION 1
 
 // ------------------------------------------------------------------ geometry
-static constexpr int kTile = 8192;                 // positions per tile
-static constexpr int kTileWords = kTile / 32;      // 256 plane words
-static constexpr int kThreads = 256;               // one plane word per thread in phase 1
-static constexpr int kHaloWords = 1;               // 32 positions each side (need 25 left / 27 right)
-static constexpr int kSmemWords = kTileWords + 2 * kHaloWords;
+static constexpr int kWarps = 8;                            // worker warps per CTA
+static constexpr int kCtaThreads = (kWarps + 1) * 32;       // + the service (look-back) warp
+static constexpr int kWarpWords = 64;                       // plane words per warp-tile (2 per lane)
+static constexpr int kWarpPos = kWarpWords * 32;            // 2048 positions
+static constexpr int kTile = kWarps * kWarpPos;             // positions per CTA tile
+static constexpr int kListCap = 128;                        // hits per strand compacted per round
 static constexpr uint32_t kAlign = 128;            // positions; segment placement granularity
 
 struct TileDesc {
@@ -273,186 +274,274 @@ struct ScanArgs {
     int guide_len;
     uint32_t flags;
     unsigned long long *status;      // [n_tiles], zeroed before launch
-    unsigned int *ticket;            // zeroed before launch
     uint64_t capacity;               // entries per strand stream
     uint32_t *pos_plus, *pos_minus;
     unsigned long long *packed_plus, *packed_minus;
     double *x_plus, *x_minus;
 };
 
+struct Hit {
+    uint32_t s0, s1, valid;              // planar codes / scoring mask of the 30-mer, output order
+    unsigned long long packed;
+};
+
+// 30-base window of one hit out of the warp's staged plane words.
+// '+': tok[t-25, t+5) read backwards (output base q = tok[t+4-q]), upper-case bases complemented;
+// '-': tok[t-2, t+28) read forwards.
+template <bool kMinus>
+__device__ __forceinline__ Hit extract_window(const uint4 *raw, uint32_t pl, uint32_t t, uint32_t L) {
+    const uint32_t ws = pl + 32u - (kMinus ? 2u : 25u);
+    const uint32_t wi = ws >> 5, sh = ws & 31u;
+    const uint4 lo = raw[wi], hi = raw[wi + 1];
+    const uint32_t p0 = __funnelshift_r(lo.x, hi.x, sh), p1 = __funnelshift_r(lo.y, hi.y, sh);
+    const uint32_t lw = __funnelshift_r(lo.z, hi.z, sh), ot = __funnelshift_r(lo.w, hi.w, sh);
+    const uint32_t upper = ~lw & ~ot;       // upper-case ACGT
+    const uint32_t special = ot & p0;       // 'U' / 'Z': "other" bytes that still score
+    const uint32_t valid = ~ot | special;
+    Hit h;
+    if (kMinus) {
+        h.s0 = (p0 ^ special) & 0x3FFFFFFFu;        // U scores as A, Z as C
+        h.s1 = p1 & 0x3FFFFFFFu;
+        h.valid = valid & 0x3FFFFFFFu;
+    } else {
+        h.s0 = __brev(p0 ^ upper) >> 2;             // A<->T, C<->G flips the low code bit
+        h.s1 = __brev(p1) >> 2;
+        h.valid = __brev(valid) >> 2;
+    }
+    h.packed = (unsigned long long)h.s0 | ((unsigned long long)h.s1 << 32);
+    if ((lw | ot) & 0x3FFFFFFFu) h.packed |= CRP_PACKED_IRREGULAR;
+    if ((uint64_t)t + (kMinus ? 28u : 5u) > L) h.packed |= CRP_PACKED_TRUNCATED;
+    if (h.valid != 0x3FFFFFFFu) h.packed |= CRP_PACKED_UNSCORED;
+    return h;
+}
+
+// Per-warp state of a tile whose hits are known but not yet scored.
+struct Pending {
+    TileDesc td;
+    uint32_t hit[2][2];     // [strand][word] hit masks of this lane's two words
+    uint32_t excl;          // packed (plus | minus << 16) rank of this lane's first hit inside the warp-tile
+    uint32_t wtot;          // packed hit totals of the warp-tile
+    uint32_t cta_excl;      // packed hits of the CTA tile that precede this warp-tile
+};
+
+__device__ __forceinline__ void spin_pause() { __nanosleep(32); }
+
+// Persistent, software-pipelined kernel.  CTA tile = kWarps warp-tiles of kWarpPos
+// positions; worker warp w owns warp-tile w; the extra (last) warp publishes the CTA's
+// counts and runs the decoupled look-back (128-tile window).  Phase 1 (stage planes,
+// PAM tests, counts) of tile i+1 runs BEFORE phase 2 (windows, scores, stores) of tile i,
+// so the look-back of a tile has a whole tile period to complete.  One __syncthreads per
+// tile; shared slots are double-buffered by tile parity.
 template <bool kScore>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kCtaThreads, 3)
 k_scan_score(const ScanArgs a) {
-    __shared__ uint4 s_quad_p[kSmemWords];      // {s0p, s1, valid, irr}
-    __shared__ uint4 s_quad_m[kSmemWords];      // {s0m, s1, valid, irr}
-    __shared__ uint32_t s_g[kSmemWords + 1];
-    __shared__ uint32_t s_c[kSmemWords + 1];
-    __shared__ uint16_t s_list_p[kTile];
-    __shared__ uint16_t s_list_m[kTile];
-    __shared__ uint32_t s_warp[kThreads / 32];
-    __shared__ uint32_t s_tile;
-    __shared__ unsigned long long s_excl;
+    __shared__ uint4 s_raw[2][kWarps][kWarpWords + 2];   // {p0, p1, lower, other} per word, 1 halo word each side
+    __shared__ uint16_t s_list[kWarps][2][kListCap];      // warp-tile-local hit positions, '+' then '-'
+    __shared__ uint32_t s_tot[2][kWarps];
+    __shared__ unsigned long long s_prefix[2];
+    __shared__ volatile uint32_t s_prefix_seq[2];
 
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int l = a.guide_len;
+    const bool service = warp == kWarps;
+    if (threadIdx.x < 2) s_prefix_seq[threadIdx.x] = 0;
+    __syncthreads();
+    if (blockIdx.x >= a.n_tiles) return;
 
-    for (;;) {
-        if (tid == 0) s_tile = atomicAdd(a.ticket, 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= a.n_tiles) break;
-        const TileDesc td = a.tiles[tile];
-        const int nw = (int)((td.n + 31u) >> 5);          // owned words
-
-        // ---- stage planes (+1 halo word each side) into shared memory
-        for (int i = tid; i < nw + 2; i += kThreads) {
-            const uint64_t gw = (uint64_t)td.gword - 1 + i;
-            Derived d = derive(__ldg(a.p0 + gw), __ldg(a.p1 + gw), __ldg(a.lower + gw), __ldg(a.other + gw));
-            if (kScore) {
-                s_quad_p[i] = make_uint4(d.s0p, d.s1, d.valid, d.irr);
-                s_quad_m[i] = make_uint4(d.s0m, d.s1, d.valid, d.irr);
-            }
-            s_g[i] = d.gup;
-            s_c[i] = d.cup;
-        }
-        __syncthreads();
-
-        // ---- phase 1: PAM tests for the 32 positions of word `tid`
-        uint32_t hp = 0, hm = 0;
-        if (tid < nw) {
-            const uint32_t g0 = s_g[tid + 1], g1 = s_g[tid + 2];
-            const uint32_t c0 = s_c[tid + 1], c1 = s_c[tid + 2];
-            // '+': (?=.GG) at t  <=>  tok[t+1]==tok[t+2]=='G'   (CROPSR.py:415)
-            hp = __funnelshift_r(g0, g1, 1) & __funnelshift_r(g0, g1, 2);
-            // '-': (?=CC.) at t  <=>  tok[t]==tok[t+1]=='C' and t+2 < L   (CROPSR.py:426)
-            hm = c0 & __funnelshift_r(c0, c1, 1);
-            const int64_t t0 = (int64_t)td.t_start + 32 * tid;
-            const int64_t last_owned = (int64_t)td.t_start + td.n - 1;
-            const int64_t L = td.L;
-            // bounds tests of CROPSR.py:419 / :430 reduce to  t >= l+5  and  2 <= t <= L-l+7
-            int64_t hi_p = L - 3 < last_owned ? L - 3 : last_owned;
-            int64_t hi_m = L - l + 7 < hi_p ? L - l + 7 : hi_p;
-            hp &= range_mask(t0, l + 5, hi_p);
-            hm &= range_mask(t0, 2, hi_m);
-        }
-        const uint32_t cnt = __popc(hp) | (__popc(hm) << 16);
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        uint32_t warp_base = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) {
-            const uint32_t v = s_warp[w];
-            if (w < warp) warp_base += v;
-            total += v;
-        }
-        const uint32_t excl = warp_base + incl - cnt;
-        const uint32_t n_plus = total & 0xFFFFu, n_minus = total >> 16;
-
-        // ---- decoupled look-back: publish this tile's counts, fetch the exclusive prefix
-        if (warp == 0) {
-            const unsigned long long mine = ((unsigned long long)n_plus << 31) | n_minus;
+    // ---------------- phase 1 of tile number `it` of this CTA
+    auto phase1 = [&](uint32_t it, Pending &pd) {
+        const uint32_t tile = blockIdx.x + it * gridDim.x;
+        const int par = it & 1;
+        pd.td = a.tiles[tile];
+        const TileDesc &td = pd.td;
+        if (service) {
+            __syncthreads();
+            const uint32_t v = lane < kWarps ? s_tot[par][lane] : 0u;
+            const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, v);
+            const unsigned long long mine = ((unsigned long long)(tot & 0xFFFFu) << 31) | (tot >> 16);
             if (lane == 0) st_status(a.status + tile, (tile == 0 ? kFlagIncl : kFlagAgg) | mine);
             unsigned long long prefix = 0;
             if (tile > 0) {
                 int64_t j = (int64_t)tile - 1;
                 for (;;) {
-                    const int64_t idx = j - lane;
-                    unsigned long long v = kFlagIncl;
-                    if (idx >= 0) {
-                        do { v = ld_status(a.status + idx); } while ((v >> 62) == 0);
+                    // lane reads 4 consecutive predecessors, nearest first (4 loads in flight)
+                    unsigned long long sv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int64_t idx = j - 4 * lane - q;
+                        sv[q] = idx >= 0 ? ld_status(a.status + idx) : kFlagIncl;
                     }
-                    const uint32_t incl_mask = __ballot_sync(0xFFFFFFFFu, (v >> 62) == 2);
-                    const int first = incl_mask ? __ffs(incl_mask) - 1 : 31;
-                    unsigned long long c = lane <= first ? (v & kValMask) : 0ull;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int64_t idx = j - 4 * lane - q;
+                        while ((sv[q] >> 62) == 0) {
+                            spin_pause();
+                            sv[q] = ld_status(a.status + idx);
+                        }
+                    }
+                    unsigned long long acc = 0;
+                    bool found = false;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (!found) acc += sv[q] & kValMask;
+                        found = found || (sv[q] >> 62) == 2;
+                    }
+                    const uint32_t fm = __ballot_sync(0xFFFFFFFFu, found);
+                    const int first = fm ? __ffs(fm) - 1 : 31;
+                    unsigned long long c = lane <= first ? acc : 0ull;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
                     prefix += c;
-                    if (incl_mask) break;
-                    j -= 32;
+                    if (fm) break;
+                    j -= 128;
                 }
                 if (lane == 0) st_status(a.status + tile, kFlagIncl | (prefix + mine));
             }
-            if (lane == 0) s_excl = prefix;
-        }
-
-        // ---- compact hit positions (tile-local) in order into shared lists
-        {
-            uint32_t op = excl & 0xFFFFu, om = excl >> 16;
-            const uint32_t base = 32u * tid;
-            while (hp) {
-                const int b = __ffs(hp) - 1;
-                hp &= hp - 1;
-                s_list_p[op++] = (uint16_t)(base + b);
+            if (lane == 0) {
+                s_prefix[par] = prefix;
+                __threadfence_block();
+                s_prefix_seq[par] = it + 1;
             }
-            while (hm) {
-                const int b = __ffs(hm) - 1;
-                hm &= hm - 1;
-                s_list_m[om++] = (uint16_t)(base + b);
+            return;
+        }
+        // ---- worker: stage this warp-tile, find its hits
+        uint4 *raw = s_raw[par][warp];
+        const int64_t n_w = (int64_t)td.n - (int64_t)warp * kWarpPos;      // owned positions of this warp-tile
+        pd.hit[0][0] = pd.hit[0][1] = pd.hit[1][0] = pd.hit[1][1] = 0u;
+        if (n_w > 0) {
+            const uint64_t w0 = (uint64_t)td.gword + (uint64_t)warp * kWarpWords + 2 * lane;
+            const uint2 q0 = __ldg((const uint2 *)(a.p0 + w0)), q1 = __ldg((const uint2 *)(a.p1 + w0));
+            const uint2 ql = __ldg((const uint2 *)(a.lower + w0)), qo = __ldg((const uint2 *)(a.other + w0));
+            uint4 edge = make_uint4(0u, 0u, 0u, 0u);
+            if (lane == 0 || lane == 31) {
+                const uint64_t we = lane == 0 ? w0 - 1 : w0 + 2;
+                edge = make_uint4(__ldg(a.p0 + we), __ldg(a.p1 + we), __ldg(a.lower + we), __ldg(a.other + we));
+                raw[lane == 0 ? 0 : kWarpWords + 1] = edge;
+            }
+            raw[1 + 2 * lane] = make_uint4(q0.x, q1.x, ql.x, qo.x);
+            raw[2 + 2 * lane] = make_uint4(q0.y, q1.y, ql.y, qo.y);
+            // upper-case G / C masks of my two words and of the word after them
+            const uint32_t uA = ~ql.x & ~qo.x, uB = ~ql.y & ~qo.y;
+            const uint32_t gA = q0.x & q1.x & uA, gB = q0.y & q1.y & uB;
+            const uint32_t cA = ~q0.x & q1.x & uA, cB = ~q0.y & q1.y & uB;
+            uint32_t gN = __shfl_down_sync(0xFFFFFFFFu, gA, 1), cN = __shfl_down_sync(0xFFFFFFFFu, cA, 1);
+            if (lane == 31) {
+                const uint32_t uN = ~edge.z & ~edge.w;
+                gN = edge.x & edge.y & uN;
+                cN = ~edge.x & edge.y & uN;
+            }
+            // '+': (?=.GG) at t <=> tok[t+1]==tok[t+2]=='G'   (CROPSR.py:415)
+            pd.hit[0][0] = __funnelshift_r(gA, gB, 1) & __funnelshift_r(gA, gB, 2);
+            pd.hit[0][1] = __funnelshift_r(gB, gN, 1) & __funnelshift_r(gB, gN, 2);
+            // '-': (?=CC.) at t <=> tok[t]==tok[t+1]=='C' and t+2 < L   (CROPSR.py:426)
+            pd.hit[1][0] = cA & __funnelshift_r(cA, cB, 1);
+            pd.hit[1][1] = cB & __funnelshift_r(cB, cN, 1);
+            // bounds tests of CROPSR.py:419 / :430:  '+' t >= l+5,  '-' 2 <= t <= L-l+7;
+            // plus ownership (t inside this segment's tile) and t+2 < L.  Interior warp-tiles skip this.
+            const int64_t t_w = (int64_t)td.t_start + (int64_t)warp * kWarpPos;
+            const int64_t L = td.L;
+            const int64_t last_owned = (int64_t)td.t_start + td.n - 1;
+            const int64_t hi_p = L - 3 < last_owned ? L - 3 : last_owned;
+            const int64_t hi_m = L - l + 7 < hi_p ? L - l + 7 : hi_p;
+            if (t_w < l + 5 || t_w + kWarpPos - 1 > hi_m) {
+                const int64_t t0 = t_w + 64 * lane;
+                pd.hit[0][0] &= range_mask(t0, l + 5, hi_p);
+                pd.hit[0][1] &= range_mask(t0 + 32, l + 5, hi_p);
+                pd.hit[1][0] &= range_mask(t0, 2, hi_m);
+                pd.hit[1][1] &= range_mask(t0 + 32, 2, hi_m);
             }
         }
+        const uint32_t cnt = (__popc(pd.hit[0][0]) + __popc(pd.hit[0][1])) |
+                             ((__popc(pd.hit[1][0]) + __popc(pd.hit[1][1])) << 16);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        pd.wtot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        pd.excl = incl - cnt;
+        if (lane == 31) s_tot[par][warp] = incl;
         __syncthreads();
-        const unsigned long long pre = s_excl;
-        const uint64_t base_plus = pre >> 31, base_minus = pre & kMinusMask;
+        const uint32_t tv = lane < kWarps ? s_tot[par][lane] : 0u;
+        pd.cta_excl = __reduce_add_sync(0xFFFFFFFFu, lane < warp ? tv : 0u);
+    };
 
-        // ---- phase 2: one thread per candidate
-        for (uint32_t k = tid; k < n_plus; k += kThreads) {
-            const uint32_t tl = s_list_p[k];
-            const uint32_t t = td.t_start + tl;
-            const uint64_t o = base_plus + k;
-            if (o < a.capacity) {
-                a.pos_plus[o] = t;
-                if (kScore) {
-                    // window tok[t-25, t+5) read backwards: output base q = tok[t+4-q]
-                    const uint32_t ws = tl + 32u - 25u, wi = ws >> 5, sh = ws & 31u;
-                    const uint4 lo = s_quad_p[wi], hi = s_quad_p[wi + 1];
-                    const uint32_t s0 = __brev(__funnelshift_r(lo.x, hi.x, sh)) >> 2;
-                    const uint32_t s1 = __brev(__funnelshift_r(lo.y, hi.y, sh)) >> 2;
-                    const uint32_t va = __brev(__funnelshift_r(lo.z, hi.z, sh)) >> 2;
-                    const uint32_t ir = __funnelshift_r(lo.w, hi.w, sh) & 0x3FFFFFFFu;
-                    unsigned long long pk = (unsigned long long)s0 | ((unsigned long long)s1 << 32);
-                    if (ir) pk |= CRP_PACKED_IRREGULAR;
-                    if ((uint64_t)t + 5 > td.L) pk |= CRP_PACKED_TRUNCATED;
-                    if (va != 0x3FFFFFFFu) pk |= CRP_PACKED_UNSCORED;
-                    a.packed_plus[o] = pk;
-                    double x = rs1_canonical(s0, s1, va);
-                    if (a.flags & CRP_SCAN_LOGISTIC) x = 1.0 / (1.0 + exp(x));
-                    a.x_plus[o] = x;
+    // ---------------- phase 2 (workers): compact hits, one lane per hit: window, score, store
+    auto phase2 = [&](uint32_t it, const Pending &pd) {
+        const int par = it & 1;
+        const TileDesc &td = pd.td;
+        const uint32_t np = pd.wtot & 0xFFFFu, nm = pd.wtot >> 16;
+        if ((np | nm) == 0u) return;
+        const uint4 *raw = s_raw[par][warp];
+        uint16_t(*list)[kListCap] = s_list[warp];
+        const uint32_t ex_p = pd.excl & 0xFFFFu, ex_m = pd.excl >> 16;
+        const uint32_t t_w = td.t_start + (uint32_t)warp * kWarpPos;
+        // global rows of this CTA tile (the look-back finished long ago in steady state)
+        while (s_prefix_seq[par] != it + 1) spin_pause();
+        __threadfence_block();
+        const unsigned long long pre = s_prefix[par];
+        const uint64_t base_p = (pre >> 31) + (pd.cta_excl & 0xFFFFu);
+        const uint64_t base_m = (pre & kMinusMask) + (pd.cta_excl >> 16);
+        for (uint32_t base = 0; base < np || base < nm; base += kListCap) {
+            // ---- my hits whose rank falls in [base, base + kListCap) go to the warp lists
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                uint32_t r = s == 0 ? ex_p : ex_m;
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    uint32_t m = pd.hit[s][w];
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        if (r - base < (uint32_t)kListCap) list[s][r - base] = (uint16_t)(64 * lane + 32 * w + b);
+                        ++r;
+                    }
                 }
             }
-        }
-        for (uint32_t k = tid; k < n_minus; k += kThreads) {
-            const uint32_t tl = s_list_m[k];
-            const uint32_t t = td.t_start + tl;
-            const uint64_t o = base_minus + k;
-            if (o < a.capacity) {
-                a.pos_minus[o] = t;
-                if (kScore) {
-                    // window tok[t-2, t+28) read forwards: output base q = tok[t-2+q]
-                    const uint32_t ws = tl + 32u - 2u, wi = ws >> 5, sh = ws & 31u;
-                    const uint4 lo = s_quad_m[wi], hi = s_quad_m[wi + 1];
-                    const uint32_t s0 = __funnelshift_r(lo.x, hi.x, sh) & 0x3FFFFFFFu;
-                    const uint32_t s1 = __funnelshift_r(lo.y, hi.y, sh) & 0x3FFFFFFFu;
-                    const uint32_t va = __funnelshift_r(lo.z, hi.z, sh) & 0x3FFFFFFFu;
-                    const uint32_t ir = __funnelshift_r(lo.w, hi.w, sh) & 0x3FFFFFFFu;
-                    unsigned long long pk = (unsigned long long)s0 | ((unsigned long long)s1 << 32);
-                    if (ir) pk |= CRP_PACKED_IRREGULAR;
-                    if ((uint64_t)t + 28 > td.L) pk |= CRP_PACKED_TRUNCATED;
-                    if (va != 0x3FFFFFFFu) pk |= CRP_PACKED_UNSCORED;
-                    a.packed_minus[o] = pk;
-                    double x = rs1_canonical(s0, s1, va);
-                    if (a.flags & CRP_SCAN_LOGISTIC) x = 1.0 / (1.0 + exp(x));
-                    a.x_minus[o] = x;
+            __syncwarp();
+            const uint32_t cp = np > base ? (np - base < (uint32_t)kListCap ? np - base : kListCap) : 0u;
+            const uint32_t cm = nm > base ? (nm - base < (uint32_t)kListCap ? nm - base : kListCap) : 0u;
+            for (uint32_t k = lane; k < cp; k += 32) {
+                const uint32_t pl = list[0][k], t = t_w + pl;
+                const uint64_t o = base_p + base + k;
+                if (o < a.capacity) {
+                    a.pos_plus[o] = t;
+                    if (kScore) {
+                        const Hit h = extract_window<false>(raw, pl, t, td.L);
+                        double x = rs1_canonical(h.s0, h.s1, h.valid);
+                        if (a.flags & CRP_SCAN_LOGISTIC) x = 1.0 / (1.0 + exp(x));
+                        a.packed_plus[o] = h.packed;
+                        a.x_plus[o] = x;
+                    }
                 }
             }
+            for (uint32_t k = lane; k < cm; k += 32) {
+                const uint32_t pl = list[1][k], t = t_w + pl;
+                const uint64_t o = base_m + base + k;
+                if (o < a.capacity) {
+                    a.pos_minus[o] = t;
+                    if (kScore) {
+                        const Hit h = extract_window<true>(raw, pl, t, td.L);
+                        double x = rs1_canonical(h.s0, h.s1, h.valid);
+                        if (a.flags & CRP_SCAN_LOGISTIC) x = 1.0 / (1.0 + exp(x));
+                        a.packed_minus[o] = h.packed;
+                        a.x_minus[o] = x;
+                    }
+                }
+            }
+            __syncwarp();
         }
-        __syncthreads();   // shared lists / planes are reused by the next tile
+    };
+
+    Pending cur, nxt;
+    phase1(0, cur);
+    for (uint32_t it = 0;; ++it) {
+        const bool has_next = (uint64_t)blockIdx.x + (uint64_t)(it + 1) * gridDim.x < a.n_tiles;
+        if (has_next) phase1(it + 1, nxt);
+        if (!service) phase2(it, cur);
+        if (!has_next) break;
+        cur = nxt;
     }
 }
 
@@ -555,6 +644,8 @@ static int need_ctx() {
 extern "C" {
 
 int crp_abi_version(void) { return CRP_ABI_VERSION; }
+
+int crp_tile_size(void) { return kTile; }
 
 const char *crp_last_error(void) { return g_err; }
 
@@ -687,7 +778,7 @@ int crp_genome_commit(crp_genome *g) {
         g->n_positions += s.end - s.begin;
     }
     g->g_total = gp + kAlign;
-    g->plane_words = g->g_total / 32 + 8;
+    g->plane_words = g->g_total / 32 + kTile / 32 + 128;   // any tile may read its full extent
     g->n_tiles = (uint32_t)tiles.size();
 
     uint8_t *d_ascii = nullptr;
@@ -803,7 +894,6 @@ static int launch_scan(const crp_genome *g, crp_result *r, int guide_len, uint32
     a.guide_len = guide_len;
     a.flags = flags;
     a.status = r->status;
-    a.ticket = r->ticket;
     a.capacity = r->capacity;
     a.pos_plus = r->pos[0];
     a.pos_minus = r->pos[1];
@@ -814,19 +904,22 @@ static int launch_scan(const crp_genome *g, crp_result *r, int guide_len, uint32
     CUDA_TRY(cudaEventRecord(e0, st));
     if (g->n_tiles) {
         CUDA_TRY(cudaMemsetAsync(r->status, 0, (size_t)g->n_tiles * sizeof(unsigned long long), st));
-        CUDA_TRY(cudaMemsetAsync(r->ticket, 0, sizeof(unsigned int), st));
         int per_sm = 0;
         if (r->scored)
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_score<true>, kThreads, 0));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_score<true>, kCtaThreads, 0));
         else
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_score<false>, kThreads, 0));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_score<false>, kCtaThreads, 0));
         if (per_sm < 1) per_sm = 1;
+        // persistent grid, every CTA resident (the look-back spins on predecessors)
         uint64_t blocks = (uint64_t)g_ctx.sm_count * per_sm;
         if (blocks > g->n_tiles) blocks = g->n_tiles;
+        void *params[] = {(void *)&a};
         if (r->scored)
-            k_scan_score<true><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+            CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_scan_score<true>, dim3((unsigned)blocks),
+                                                 dim3(kCtaThreads), params, 0, st));
         else
-            k_scan_score<false><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+            CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_scan_score<false>, dim3((unsigned)blocks),
+                                                 dim3(kCtaThreads), params, 0, st));
         g_ctx.launches++;
         CUDA_TRY(cudaGetLastError());
     }

@@ -13,7 +13,7 @@ from ._native import CropsrError, check, lib
 _device = None
 
 SEGMENT_ALIGN = 128   # crp_genome_add_segment: seg_begin granularity
-TILE = 8192           # positions per scan tile (csrc/cropsr_b200.cu kTile)
+TILE = lib.crp_tile_size()   # positions per scan tile (csrc/cropsr_b200.cu kTile)
 
 
 def init(device=0):

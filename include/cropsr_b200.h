@@ -72,6 +72,9 @@ const char *crp_last_error(void);
 int crp_device_count(int *count);
 /* ABI version of this header (bumped on any signature change). */
 int crp_abi_version(void);
+/* Positions per scan tile: segment boundaries chosen by the host should be
+ * multiples of this (any multiple of 128 is accepted). */
+int crp_tile_size(void);
 
 /* Pinned host memory for staging (FASTA bytes in, candidate arrays out). */
 int crp_host_alloc(void **ptr, uint64_t bytes);

@@ -252,6 +252,8 @@ def preactivation_model(seqs, threads=1, classes=None):
     """x = -(((A+B)+intercept)+low_gc) per row with the modelled BLAS order."""
     seqs = np.asarray(seqs)
     n = len(seqs)
+    if n == 0:
+        return np.empty(0)
     m1, m2 = indicator_matrices(seqs)
     c1 = row_classes(n, 120, threads) if classes is None else classes
     c2 = row_classes(n, 464, threads) if classes is None else classes

@@ -78,7 +78,10 @@ def _check_against_oracle(eng, text, guide_len):
                 mask = np.array([sum((1 << q) for q, v in enumerate(row) if v) for row in scoring], dtype=np.uint64)
                 assert np.array_equal(got_lo & mask, lo) and np.array_equal(got_hi & mask, hi)
                 assert np.array_equal((pk & np.uint64(N.PACKED_UNSCORED)) != 0, ~scoring.all(axis=1))
-                irregular = np.array([any(ch not in "AUCG" for ch in c[4]) for c, f in zip(cands, full) if f])
+                # irregular = the token window holds a byte that is not upper-case ACGT
+                def window(c):
+                    return tok[c[1] - 25:c[1] + 5] if c[6] == "+" else tok[c[1] - 5:c[1] + 25]
+                irregular = np.array([any(ch not in "ACGT" for ch in window(c)) for c, f in zip(cands, full) if f])
                 assert np.array_equal((pk & np.uint64(N.PACKED_IRREGULAR)) != 0, irregular)
     finally:
         result.free()
