@@ -324,14 +324,37 @@ struct Pending {
     uint32_t cta_excl;      // packed hits of the CTA tile that precede this warp-tile
 };
 
-__device__ __forceinline__ void spin_pause() { __nanosleep(32); }
+// Every spin in the kernel goes through here: back off, and trap instead of hanging the
+// GPU if a wait ever exceeds ~1 s (a logic error or a grid that is not co-resident).
+__device__ __forceinline__ void spin_pause(uint32_t &spins, int tag = 0, uint32_t a0 = 0, uint32_t a1 = 0, uint32_t a2 = 0) {
+    __nanosleep(32);
+    if (++spins > (tag == 3 ? (1u << 23) : (1u << 20))) {
+        if ((threadIdx.x & 31) == 0 || tag == 1)
+            printf("spin timeout tag=%d block=%d thread=%d a0=%u a1=%u a2=%u\n", tag, blockIdx.x, threadIdx.x, a0, a1, a2);
+        __nanosleep(1000000);
+        __trap();
+    }
+}
+
+// named barrier 3 = the worker warps among themselves (the service warp never joins, so a
+// look-back in flight never blocks the workers); hand-offs to and from the service warp go
+// through sequence-numbered shared-memory slots.
+template <int kId>
+__device__ __forceinline__ void bar_sync(int n) {
+    asm volatile("barrier.sync.aligned %0, %1;" ::"n"(kId), "r"(n) : "memory");
+}
+template <int kId>
+__device__ __forceinline__ void bar_arrive(int n) {
+    asm volatile("barrier.arrive.aligned %0, %1;" ::"n"(kId), "r"(n) : "memory");
+}
 
 // Persistent, software-pipelined kernel.  CTA tile = kWarps warp-tiles of kWarpPos
 // positions; worker warp w owns warp-tile w; the extra (last) warp publishes the CTA's
 // counts and runs the decoupled look-back (128-tile window).  Phase 1 (stage planes,
 // PAM tests, counts) of tile i+1 runs BEFORE phase 2 (windows, scores, stores) of tile i,
-// so the look-back of a tile has a whole tile period to complete.  One __syncthreads per
-// tile; shared slots are double-buffered by tile parity.
+// so the look-back of a tile has a whole tile period to complete.  Workers meet on one
+// named barrier per tile and never wait for the service warp except for a prefix that is
+// a tile period old; shared slots are double-buffered by tile parity.
 template <bool kScore>
 __global__ void __launch_bounds__(kCtaThreads, 3)
 k_scan_score(const ScanArgs a) {
@@ -340,11 +363,13 @@ k_scan_score(const ScanArgs a) {
     __shared__ uint32_t s_tot[2][kWarps];
     __shared__ unsigned long long s_prefix[2];
     __shared__ volatile uint32_t s_prefix_seq[2];
+    __shared__ volatile uint32_t s_tot_seq[2];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int l = a.guide_len;
     const bool service = warp == kWarps;
-    if (threadIdx.x < 2) s_prefix_seq[threadIdx.x] = 0;
+    uint32_t spins = 0;
+    if (threadIdx.x < 2) s_prefix_seq[threadIdx.x] = s_tot_seq[threadIdx.x] = 0;
     __syncthreads();
     if (blockIdx.x >= a.n_tiles) return;
 
@@ -355,7 +380,8 @@ k_scan_score(const ScanArgs a) {
         pd.td = a.tiles[tile];
         const TileDesc &td = pd.td;
         if (service) {
-            __syncthreads();
+            while (s_tot_seq[par] != it + 1) spin_pause(spins, 2, it, tile, s_tot_seq[par]);      // worker totals of this tile are ready
+            __threadfence_block();
             const uint32_t v = lane < kWarps ? s_tot[par][lane] : 0u;
             const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, v);
             const unsigned long long mine = ((unsigned long long)(tot & 0xFFFFu) << 31) | (tot >> 16);
@@ -375,7 +401,7 @@ k_scan_score(const ScanArgs a) {
                     for (int q = 0; q < 4; ++q) {
                         const int64_t idx = j - 4 * lane - q;
                         while ((sv[q] >> 62) == 0) {
-                            spin_pause();
+                            spin_pause(spins, 1, it, tile, (uint32_t)idx);
                             sv[q] = ld_status(a.status + idx);
                         }
                     }
@@ -462,7 +488,11 @@ k_scan_score(const ScanArgs a) {
         pd.wtot = __shfl_sync(0xFFFFFFFFu, incl, 31);
         pd.excl = incl - cnt;
         if (lane == 31) s_tot[par][warp] = incl;
-        __syncthreads();
+        bar_sync<3>(kWarps * 32);                 // workers only: never blocked by a look-back in flight
+        if (warp == 0 && lane == 0) {
+            __threadfence_block();
+            s_tot_seq[par] = it + 1;              // hand the totals to the service warp
+        }
         const uint32_t tv = lane < kWarps ? s_tot[par][lane] : 0u;
         pd.cta_excl = __reduce_add_sync(0xFFFFFFFFu, lane < warp ? tv : 0u);
     };
@@ -472,13 +502,16 @@ k_scan_score(const ScanArgs a) {
         const int par = it & 1;
         const TileDesc &td = pd.td;
         const uint32_t np = pd.wtot & 0xFFFFu, nm = pd.wtot >> 16;
-        if ((np | nm) == 0u) return;
         const uint4 *raw = s_raw[par][warp];
         uint16_t(*list)[kListCap] = s_list[warp];
         const uint32_t ex_p = pd.excl & 0xFFFFu, ex_m = pd.excl >> 16;
         const uint32_t t_w = td.t_start + (uint32_t)warp * kWarpPos;
-        // global rows of this CTA tile (the look-back finished long ago in steady state)
-        while (s_prefix_seq[par] != it + 1) spin_pause();
+        // Global rows of this CTA tile (the look-back finished long ago in steady state).
+        // Every worker warp waits here, hits or not: it is also the flow control that keeps
+        // the workers from reusing this parity's shared slots before the service warp has
+        // consumed them.
+        while (s_prefix_seq[par] != it + 1) spin_pause(spins, 3, it, s_prefix_seq[par], 0);
+        if ((np | nm) == 0u) return;
         __threadfence_block();
         const unsigned long long pre = s_prefix[par];
         const uint64_t base_p = (pre >> 31) + (pd.cta_excl & 0xFFFFu);
@@ -974,11 +1007,11 @@ int crp_scan_score(crp_genome *g, int guide_len, uint32_t flags, crp_result **re
     for (int attempt = 0; attempt < 2; ++attempt) {
         if ((rc = launch_scan(g, r, guide_len, flags, e0, e1))) return bail(rc);
         if (n_seg)
-            if (cudaMemcpyAsync(counts.data(), r->d_counts, counts.size() * sizeof(unsigned long long),
-                                cudaMemcpyDeviceToHost, st) != cudaSuccess)
-                return bail(fail(CRP_ERR_CUDA, "D2H of segment counts failed"));
-        if (cudaStreamSynchronize(st) != cudaSuccess)
-            return bail(fail(CRP_ERR_CUDA, "scan kernels failed: %s", cudaGetErrorString(cudaGetLastError())));
+            if (cudaError_t e = cudaMemcpyAsync(counts.data(), r->d_counts, counts.size() * sizeof(unsigned long long),
+                                                cudaMemcpyDeviceToHost, st))
+                return bail(fail(CRP_ERR_CUDA, "D2H of segment counts failed: %s", cudaGetErrorString(e)));
+        if (cudaError_t e = cudaStreamSynchronize(st))
+            return bail(fail(CRP_ERR_CUDA, "scan kernels failed: %s", cudaGetErrorString(e)));
         r->n_plus = r->n_minus = 0;
         r->seg_plus.assign(n_seg, 0);
         r->seg_minus.assign(n_seg, 0);
