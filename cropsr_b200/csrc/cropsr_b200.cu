@@ -35,6 +35,9 @@ static constexpr int kWarpWords = 64;                       // plane words per w
 static constexpr int kWarpPos = kWarpWords * 32;            // 2048 positions
 static constexpr int kTile = kWarps * kWarpPos;             // positions per CTA tile
 static constexpr int kListCap = 128;                        // hits per strand compacted per round
+static constexpr size_t kSmemTableBytes = (size_t)RS1_TABLE_DOUBLES * sizeof(double);
+static constexpr size_t kSmemBytes = kSmemTableBytes + 2 * (size_t)kWarps * (kWarpWords + 2) * sizeof(uint4) +
+                                     (size_t)kWarps * 2 * kListCap * sizeof(uint16_t);
 static constexpr uint32_t kAlign = 128;            // positions; segment placement granularity
 
 struct TileDesc {
@@ -74,6 +77,7 @@ struct Context {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
+    double *d_tables = nullptr;        // RS1 lane tables in device memory
 };
 static Context g_ctx;
 
@@ -126,39 +130,52 @@ k_pack(const uint4 *__restrict__ ascii, uint64_t n_words, uint32_t *__restrict__
 }
 
 // ------------------------------------------------------------------ RS1 scoring
-// Canonical lane order (rows handled by OpenBLAS' 4-row dgemv_t kernel): one
-// sequential accumulator per column-mod-4 lane, i.e. per base class for the
-// first-order term and per SECOND base for the dinucleotide term, columns in
-// ascending order; lanes combined (p0+p2)+(p1+p3) = (A+C)+(T+G).
+// Canonical lane order (rows handled by OpenBLAS' 4-row dgemv_t kernel): one sequential
+// accumulator per column-mod-4 lane, i.e. per base class for the first-order term and per
+// SECOND base for the dinucleotide term, columns in ascending order; lanes combined
+// (p0+p2)+(p1+p3) = (A+C)+(T+G).  A lane's value is a function of which of its entries
+// match, so the leading entries of every lane come from a table of exact sequential fp64
+// sums (built on the host at crp_init, staged in shared memory; rs1_weights.inc).
 // s0/s1: planar code bits of the scored 30-mer (bit q = base q), valid: bases that score.
-__device__ __forceinline__ double rs1_canonical(uint32_t s0, uint32_t s1, uint32_t valid) {
-    const uint32_t m[4] = {~s1 & ~s0 & valid, ~s1 & s0 & valid, s1 & ~s0 & valid, s1 & s0 & valid};
-    double fA = 0.0, fT = 0.0, fC = 0.0, fG = 0.0;
-#define X1A(p, w) if (m[0] & (1u << (p))) fA = __dadd_rn(fA, w);
-#define X1T(p, w) if (m[1] & (1u << (p))) fT = __dadd_rn(fT, w);
-#define X1C(p, w) if (m[2] & (1u << (p))) fC = __dadd_rn(fC, w);
-#define X1G(p, w) if (m[3] & (1u << (p))) fG = __dadd_rn(fG, w);
-    RS1_FIRST_A(X1A) RS1_FIRST_T(X1T) RS1_FIRST_C(X1C) RS1_FIRST_G(X1G)
-#undef X1A
-#undef X1T
-#undef X1C
-#undef X1G
+__device__ __forceinline__ double rs1_canonical(const double *__restrict__ T, uint32_t s0, uint32_t s1,
+                                                uint32_t valid) {
+    const uint32_t mA = ~s1 & ~s0 & valid, mT = ~s1 & s0 & valid, mC = s1 & ~s0 & valid, mG = s1 & s0 & valid;
+    RS1_LANE_SUMS(T, mA, mT, mC, mG)
     const double first = __dadd_rn(__dadd_rn(fA, fC), __dadd_rn(fT, fG));
-    // dinucleotide (c1 at p, c2 at p+1): bit p of m[c1] & (m[c2] >> 1)
-    const uint32_t nA = m[0] >> 1, nT = m[1] >> 1, nC = m[2] >> 1, nG = m[3] >> 1;
-    double dA = 0.0, dT = 0.0, dC = 0.0, dG = 0.0;
-#define X2A(p, c1, w) if (m[c1] & nA & (1u << (p))) dA = __dadd_rn(dA, w);
-#define X2T(p, c1, w) if (m[c1] & nT & (1u << (p))) dT = __dadd_rn(dT, w);
-#define X2C(p, c1, w) if (m[c1] & nC & (1u << (p))) dC = __dadd_rn(dC, w);
-#define X2G(p, c1, w) if (m[c1] & nG & (1u << (p))) dG = __dadd_rn(dG, w);
-    RS1_SECOND_A(X2A) RS1_SECOND_T(X2T) RS1_SECOND_C(X2C) RS1_SECOND_G(X2G)
-#undef X2A
-#undef X2T
-#undef X2C
-#undef X2G
     const double second = __dadd_rn(__dadd_rn(dA, dC), __dadd_rn(dT, dG));
     // (score_first + score_second + intersect + low_gc) * -1, CROPSR.py:312
     return -__dadd_rn(__dadd_rn(__dadd_rn(first, second), RS1_INTERCEPT), RS1_LOW_GC);
+}
+
+// Host side: exact sequential sums of every valid subset of each lane's table entries.
+static int build_rs1_tables(std::vector<double> &tab, char *err, size_t errlen) {
+    tab.assign(RS1_TABLE_DOUBLES, 0.0);
+    std::vector<char> used(RS1_TABLE_DOUBLES, 0);
+    for (const Rs1Lane &ln : kRs1Lanes) {
+        for (uint32_t sub = 0; sub < (1u << ln.n_table); ++sub) {
+            bool ok = true;                       // two entries at one position are mutually exclusive
+            for (int i = 0; i < ln.n_table && ok; ++i)
+                for (int j = i + 1; j < ln.n_table; ++j)
+                    if ((sub >> i & 1) && (sub >> j & 1) && ln.entries[i].pos == ln.entries[j].pos) ok = false;
+            if (!ok) continue;
+            uint32_t h = 0;
+            volatile double sum = 0.0;            // one IEEE add per entry, in ascending column order
+            for (int i = 0; i < ln.n_table; ++i) {
+                if (!(sub >> i & 1)) continue;
+                for (int g = 0; g < ln.n_groups; ++g)
+                    if (ln.groups[g].first_base == ln.entries[i].first_base) h += (1u << ln.entries[i].pos) * ln.groups[g].magic;
+                sum = sum + ln.entries[i].weight;
+            }
+            const uint32_t idx = ln.offset + (h >> (32 - ln.bits));
+            if (idx >= RS1_TABLE_DOUBLES || used[idx]) {
+                snprintf(err, errlen, "rs1 table hash of lane %s is not injective", ln.name);
+                return -1;
+            }
+            used[idx] = 1;
+            tab[idx] = sum;
+        }
+    }
+    return 0;
 }
 
 __constant__ double c_w1[120] = RS1_DENSE_FIRST;
@@ -267,6 +284,17 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// optional timeline instrumentation (tools/tile_timeline.py): 8 x u64 per tile, or NULL
+__device__ unsigned long long *g_dbg_times = nullptr;
+__device__ __forceinline__ void dbg_stamp(uint32_t tile, int slot) {
+    unsigned long long *p = g_dbg_times;
+    if (p) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p[8ull * tile + slot] = t;
+    }
+}
+
 struct ScanArgs {
     const uint32_t *p0, *p1, *lower, *other;
     const TileDesc *tiles;
@@ -274,6 +302,8 @@ struct ScanArgs {
     int guide_len;
     uint32_t flags;
     unsigned long long *status;      // [n_tiles], zeroed before launch
+    unsigned int *ticket;            // tile dispenser, zeroed before launch
+    const double *tables;            // RS1 lane tables (RS1_TABLE_DOUBLES doubles)
     uint64_t capacity;               // entries per strand stream
     uint32_t *pos_plus, *pos_minus;
     unsigned long long *packed_plus, *packed_minus;
@@ -318,6 +348,7 @@ __device__ __forceinline__ Hit extract_window(const uint4 *raw, uint32_t pl, uin
 // Per-warp state of a tile whose hits are known but not yet scored.
 struct Pending {
     TileDesc td;
+    uint32_t tile;
     uint32_t hit[2][2];     // [strand][word] hit masks of this lane's two words
     uint32_t excl;          // packed (plus | minus << 16) rank of this lane's first hit inside the warp-tile
     uint32_t wtot;          // packed hit totals of the warp-tile
@@ -326,14 +357,9 @@ struct Pending {
 
 // Every spin in the kernel goes through here: back off, and trap instead of hanging the
 // GPU if a wait ever exceeds ~1 s (a logic error or a grid that is not co-resident).
-__device__ __forceinline__ void spin_pause(uint32_t &spins, int tag = 0, uint32_t a0 = 0, uint32_t a1 = 0, uint32_t a2 = 0) {
+__device__ __forceinline__ void spin_pause(uint32_t &spins) {
     __nanosleep(32);
-    if (++spins > (tag == 3 ? (1u << 23) : (1u << 20))) {
-        if ((threadIdx.x & 31) == 0 || tag == 1)
-            printf("spin timeout tag=%d block=%d thread=%d a0=%u a1=%u a2=%u\n", tag, blockIdx.x, threadIdx.x, a0, a1, a2);
-        __nanosleep(1000000);
-        __trap();
-    }
+    if (++spins > (1u << 23)) __trap();
 }
 
 // named barrier 3 = the worker warps among themselves (the service warp never joins, so a
@@ -358,38 +384,73 @@ __device__ __forceinline__ void bar_arrive(int n) {
 template <bool kScore>
 __global__ void __launch_bounds__(kCtaThreads, 3)
 k_scan_score(const ScanArgs a) {
-    __shared__ uint4 s_raw[2][kWarps][kWarpWords + 2];   // {p0, p1, lower, other} per word, 1 halo word each side
-    __shared__ uint16_t s_list[kWarps][2][kListCap];      // warp-tile-local hit positions, '+' then '-'
+    // dynamic shared memory: [lane tables][staged plane words, 2 buffers][hit lists]
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    double *s_tab = reinterpret_cast<double *>(s_dyn);
+    typedef uint4 RawBuf[kWarps][kWarpWords + 2];          // {p0, p1, lower, other} per word, 1 halo word each side
+    RawBuf *s_raw = reinterpret_cast<RawBuf *>(s_dyn + kSmemTableBytes);
+    typedef uint16_t ListBuf[2][kListCap];                 // warp-tile-local hit positions, '+' then '-'
+    ListBuf *s_list = reinterpret_cast<ListBuf *>(s_dyn + kSmemTableBytes + 2 * sizeof(RawBuf));
     __shared__ uint32_t s_tot[2][kWarps];
     __shared__ unsigned long long s_prefix[2];
     __shared__ volatile uint32_t s_prefix_seq[2];
     __shared__ volatile uint32_t s_tot_seq[2];
+    __shared__ volatile uint32_t s_tile[2];          // tile id of iteration it (slot it & 1)
+    __shared__ uint32_t s_tile_seq[2];               // it + 1 once s_tile holds iteration it's tile
+    __shared__ uint32_t s_arrive[2];                 // worker warps that reached iteration it
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int l = a.guide_len;
     const bool service = warp == kWarps;
     uint32_t spins = 0;
-    if (threadIdx.x < 2) s_prefix_seq[threadIdx.x] = s_tot_seq[threadIdx.x] = 0;
+    if (threadIdx.x < 2) s_prefix_seq[threadIdx.x] = s_tot_seq[threadIdx.x] = s_tile_seq[threadIdx.x] = s_arrive[threadIdx.x] = 0;
+    if (kScore)
+        for (int i = threadIdx.x; i < RS1_TABLE_DOUBLES; i += kCtaThreads) s_tab[i] = a.tables[i];
     __syncthreads();
-    if (blockIdx.x >= a.n_tiles) return;
+
+    // ---------------- tile id of this CTA's iteration `it`.  Tiles are handed out in the order
+    // CTAs become READY for them: the global ticket is taken by the last worker warp to
+    // finish its previous scoring phase, so a tile's counts are published a fixed ~2 us after
+    // its ticket and the look-back of a later tile never waits for a CTA that is busy scoring.
+    auto get_tile = [&](uint32_t it) -> uint32_t {
+        const int par = it & 1;
+        uint32_t tile = 0;
+        if (lane == 0) {
+            volatile uint32_t *seq = (volatile uint32_t *)&s_tile_seq[par];
+            if (!service && atomicAdd(&s_arrive[par], 1u) == (uint32_t)kWarps - 1u) {
+                s_arrive[par] = 0;                       // next use: iteration it + 2
+                s_tile[par] = atomicAdd(a.ticket, 1u);
+                __threadfence_block();
+                *seq = it + 1;
+            } else {
+                while (*seq != it + 1) spin_pause(spins);
+            }
+            __threadfence_block();
+            tile = s_tile[par];
+        }
+        return __shfl_sync(0xFFFFFFFFu, tile, 0);
+    };
 
     // ---------------- phase 1 of tile number `it` of this CTA
-    auto phase1 = [&](uint32_t it, Pending &pd) {
-        const uint32_t tile = blockIdx.x + it * gridDim.x;
+    auto phase1 = [&](uint32_t it, uint32_t tile, Pending &pd) {
         const int par = it & 1;
+        pd.tile = tile;
         pd.td = a.tiles[tile];
         const TileDesc &td = pd.td;
         if (service) {
-            while (s_tot_seq[par] != it + 1) spin_pause(spins, 2, it, tile, s_tot_seq[par]);      // worker totals of this tile are ready
+            if (lane == 0) dbg_stamp(tile, 1);
+            while (s_tot_seq[par] != it + 1) spin_pause(spins);      // worker totals of this tile are ready
             __threadfence_block();
+            if (lane == 0) dbg_stamp(tile, 2);
             const uint32_t v = lane < kWarps ? s_tot[par][lane] : 0u;
             const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, v);
             const unsigned long long mine = ((unsigned long long)(tot & 0xFFFFu) << 31) | (tot >> 16);
-            if (lane == 0) st_status(a.status + tile, (tile == 0 ? kFlagIncl : kFlagAgg) | mine);
             unsigned long long prefix = 0;
+            uint32_t dbg_windows = 0, dbg_polls = 0;
             if (tile > 0) {
                 int64_t j = (int64_t)tile - 1;
                 for (;;) {
+                    ++dbg_windows;
                     // lane reads 4 consecutive predecessors, nearest first (4 loads in flight)
                     unsigned long long sv[4];
 #pragma unroll
@@ -401,7 +462,8 @@ k_scan_score(const ScanArgs a) {
                     for (int q = 0; q < 4; ++q) {
                         const int64_t idx = j - 4 * lane - q;
                         while ((sv[q] >> 62) == 0) {
-                            spin_pause(spins, 1, it, tile, (uint32_t)idx);
+                            spin_pause(spins);
+                            ++dbg_polls;
                             sv[q] = ld_status(a.status + idx);
                         }
                     }
@@ -421,9 +483,13 @@ k_scan_score(const ScanArgs a) {
                     if (fm) break;
                     j -= 128;
                 }
-                if (lane == 0) st_status(a.status + tile, kFlagIncl | (prefix + mine));
             }
+            // atomicMax: the inclusive word (flag 2) always wins over the counts word (flag 1)
+            if (lane == 0) atomicMax(a.status + tile, kFlagIncl | (prefix + mine));
+            dbg_polls = __reduce_max_sync(0xFFFFFFFFu, dbg_polls);
             if (lane == 0) {
+                dbg_stamp(tile, 3);
+                if (g_dbg_times) g_dbg_times[8ull * tile + 7] = ((unsigned long long)dbg_windows << 32) | dbg_polls;
                 s_prefix[par] = prefix;
                 __threadfence_block();
                 s_prefix_seq[par] = it + 1;
@@ -489,12 +555,19 @@ k_scan_score(const ScanArgs a) {
         pd.excl = incl - cnt;
         if (lane == 31) s_tot[par][warp] = incl;
         bar_sync<3>(kWarps * 32);                 // workers only: never blocked by a look-back in flight
-        if (warp == 0 && lane == 0) {
-            __threadfence_block();
-            s_tot_seq[par] = it + 1;              // hand the totals to the service warp
-        }
         const uint32_t tv = lane < kWarps ? s_tot[par][lane] : 0u;
         pd.cta_excl = __reduce_add_sync(0xFFFFFFFFu, lane < warp ? tv : 0u);
+        if (warp == 0) {
+            // publish this tile's counts at once (the service warp upgrades them to an
+            // inclusive prefix later) and hand the totals to the service warp
+            const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, tv);
+            if (lane == 0) {
+                atomicMax(a.status + tile, kFlagAgg | ((unsigned long long)(tot & 0xFFFFu) << 31) | (tot >> 16));
+                dbg_stamp(tile, 0);
+                __threadfence_block();
+                s_tot_seq[par] = it + 1;
+            }
+        }
     };
 
     // ---------------- phase 2 (workers): compact hits, one lane per hit: window, score, store
@@ -510,7 +583,9 @@ k_scan_score(const ScanArgs a) {
         // Every worker warp waits here, hits or not: it is also the flow control that keeps
         // the workers from reusing this parity's shared slots before the service warp has
         // consumed them.
-        while (s_prefix_seq[par] != it + 1) spin_pause(spins, 3, it, s_prefix_seq[par], 0);
+        if (warp == 0 && lane == 0) dbg_stamp(pd.tile, 4);
+        while (s_prefix_seq[par] != it + 1) spin_pause(spins);
+        if (warp == 0 && lane == 0) dbg_stamp(pd.tile, 5);
         if ((np | nm) == 0u) return;
         __threadfence_block();
         const unsigned long long pre = s_prefix[par];
@@ -542,7 +617,7 @@ k_scan_score(const ScanArgs a) {
                     a.pos_plus[o] = t;
                     if (kScore) {
                         const Hit h = extract_window<false>(raw, pl, t, td.L);
-                        double x = rs1_canonical(h.s0, h.s1, h.valid);
+                        double x = rs1_canonical(s_tab, h.s0, h.s1, h.valid);
                         if (a.flags & CRP_SCAN_LOGISTIC) x = 1.0 / (1.0 + exp(x));
                         a.packed_plus[o] = h.packed;
                         a.x_plus[o] = x;
@@ -556,7 +631,7 @@ k_scan_score(const ScanArgs a) {
                     a.pos_minus[o] = t;
                     if (kScore) {
                         const Hit h = extract_window<true>(raw, pl, t, td.L);
-                        double x = rs1_canonical(h.s0, h.s1, h.valid);
+                        double x = rs1_canonical(s_tab, h.s0, h.s1, h.valid);
                         if (a.flags & CRP_SCAN_LOGISTIC) x = 1.0 / (1.0 + exp(x));
                         a.packed_minus[o] = h.packed;
                         a.x_minus[o] = x;
@@ -565,13 +640,17 @@ k_scan_score(const ScanArgs a) {
             }
             __syncwarp();
         }
+        if (warp == 0 && lane == 0) dbg_stamp(pd.tile, 6);
     };
 
     Pending cur, nxt;
-    phase1(0, cur);
+    uint32_t tile = get_tile(0);
+    if (tile >= a.n_tiles) return;
+    phase1(0, tile, cur);
     for (uint32_t it = 0;; ++it) {
-        const bool has_next = (uint64_t)blockIdx.x + (uint64_t)(it + 1) * gridDim.x < a.n_tiles;
-        if (has_next) phase1(it + 1, nxt);
+        tile = get_tile(it + 1);
+        const bool has_next = tile < a.n_tiles;
+        if (has_next) phase1(it + 1, tile, nxt);
         if (!service) phase2(it, cur);
         if (!has_next) break;
         cur = nxt;
@@ -680,6 +759,13 @@ int crp_abi_version(void) { return CRP_ABI_VERSION; }
 
 int crp_tile_size(void) { return kTile; }
 
+/* debug only (not part of the public header): device buffer of 8 x u64 per tile, or NULL */
+int crp_debug_set_tile_times(void *dev_ptr) {
+    unsigned long long *p = (unsigned long long *)dev_ptr;
+    CUDA_TRY(cudaMemcpyToSymbol(g_dbg_times, &p, sizeof p));
+    return 0;
+}
+
 const char *crp_last_error(void) { return g_err; }
 
 int crp_device_count(int *count) {
@@ -700,6 +786,13 @@ int crp_init(int device) {
         return fail(CRP_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
                     prop.major, prop.minor);
     CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+    {
+        std::vector<double> tab;
+        char msg[128];
+        if (build_rs1_tables(tab, msg, sizeof msg)) return fail(CRP_ERR_STATE, "%s", msg);
+        CUDA_TRY(cudaMalloc(&g_ctx.d_tables, tab.size() * sizeof(double)));
+        CUDA_TRY(cudaMemcpy(g_ctx.d_tables, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     g_ctx.device = device;
     g_ctx.sm_count = prop.multiProcessorCount;
     g_ctx.launches = 0;
@@ -711,6 +804,7 @@ int crp_shutdown(void) {
     if (!g_ctx.ready) return 0;
     cudaStreamSynchronize(g_ctx.stream);
     cudaStreamDestroy(g_ctx.stream);
+    cudaFree(g_ctx.d_tables);
     g_ctx = Context();
     return 0;
 }
@@ -927,6 +1021,8 @@ static int launch_scan(const crp_genome *g, crp_result *r, int guide_len, uint32
     a.guide_len = guide_len;
     a.flags = flags;
     a.status = r->status;
+    a.ticket = r->ticket;
+    a.tables = g_ctx.d_tables;
     a.capacity = r->capacity;
     a.pos_plus = r->pos[0];
     a.pos_minus = r->pos[1];
@@ -937,22 +1033,17 @@ static int launch_scan(const crp_genome *g, crp_result *r, int guide_len, uint32
     CUDA_TRY(cudaEventRecord(e0, st));
     if (g->n_tiles) {
         CUDA_TRY(cudaMemsetAsync(r->status, 0, (size_t)g->n_tiles * sizeof(unsigned long long), st));
+        CUDA_TRY(cudaMemsetAsync(r->ticket, 0, sizeof(unsigned int), st));
+        const void *fn = r->scored ? (const void *)k_scan_score<true> : (const void *)k_scan_score<false>;
         int per_sm = 0;
-        if (r->scored)
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_score<true>, kCtaThreads, 0));
-        else
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_scan_score<false>, kCtaThreads, 0));
-        if (per_sm < 1) per_sm = 1;
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kCtaThreads, kSmemBytes));
+        if (per_sm < 1) return fail(CRP_ERR_CUDA, "scan kernel does not fit on an SM");
         // persistent grid, every CTA resident (the look-back spins on predecessors)
         uint64_t blocks = (uint64_t)g_ctx.sm_count * per_sm;
         if (blocks > g->n_tiles) blocks = g->n_tiles;
         void *params[] = {(void *)&a};
-        if (r->scored)
-            CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_scan_score<true>, dim3((unsigned)blocks),
-                                                 dim3(kCtaThreads), params, 0, st));
-        else
-            CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_scan_score<false>, dim3((unsigned)blocks),
-                                                 dim3(kCtaThreads), params, 0, st));
+        CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3((unsigned)blocks), dim3(kCtaThreads), params, kSmemBytes, st));
         g_ctx.launches++;
         CUDA_TRY(cudaGetLastError());
     }
