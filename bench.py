@@ -280,7 +280,7 @@ def main():
         dt = (time.perf_counter() - t0) * 1e3
         if i >= args.warmup:
             e2e_ms.append(dt)
-        h2d = sum(min(b + 64, lengths[k]) - max(a - 128, 0) for k, a, b in mine)
+        h2d = sum(min(b + 32, lengths[k]) - max(a - 32, 0) for k, a, b in mine)
         d2h = 20 * (r.n_plus + r.n_minus)
         r.free()
         g.free()
@@ -303,7 +303,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": CONFIG_NAME[args.workload] + (f" x{world} (one per GPU)" if world > 1 else ""), "bases": n_bases_total, "candidates": n_cand_total,
-                       "guide_len": 20, "sharding": f"{world} contiguous shard(s), tile-aligned, halo 128/64",
+                       "guide_len": 20, "sharding": f"{world} contiguous shard(s), tile-aligned, halo 32/32",
                        "l2": "flushed between steps (512 MiB memset)"},
             "e2e": {"value": n_bases_total / (e2e * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
