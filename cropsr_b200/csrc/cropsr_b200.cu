@@ -26,7 +26,7 @@
 
 #define CRP_ABI_VERSION 2
 
-static constexpr size_t kScanSmemFixed = 2 * (size_t)kRecBytes + kRs1TableBytes + 2 * (size_t)kListCap * sizeof(uint16_t);
+static constexpr size_t kScanSmemFixed = 2 * (size_t)kRecBytes + 2 * (size_t)kListCap * sizeof(uint16_t);
 
 // ------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -180,7 +180,7 @@ int crp_genome_add_segment(crp_genome *g, uint32_t token_id, const uint8_t *toke
         return fail(CRP_ERR_ARG, "segment [%llu,%llu) outside token of length %llu",
                     (unsigned long long)seg_begin, (unsigned long long)seg_end, (unsigned long long)token_len);
     if (seg_begin % kAlign) return fail(CRP_ERR_ARG, "seg_begin must be a multiple of %u", kAlign);
-    if (token_len >= (1ull << 31))
+    if (token_len >= (1ull << 31) - (1ull << 15))
         return fail(CRP_ERR_RANGE, "token of %llu positions exceeds the 31-bit position range",
                     (unsigned long long)token_len);
     Segment s{};

@@ -10,11 +10,22 @@ sequential fp64 sum of every possible subset can be tabulated once, exactly.
 
 This script emits
   * the dense weight vectors (for the dense re-scoring kernel),
-  * per lane: the entries, a multiply-shift perfect hash of the match bits
-    (found here by random search and re-verified on the host at crp_init),
-    the number of leading entries covered by the table and the tail entries
-    that are still added one by one,
-  * `rs1_lane_sums()` -- the device code that evaluates the 8 lanes.
+  * per lane: the entries, a perfect hash of the match bits (found here by
+    random search and re-verified on the host at crp_init), the number of
+    leading entries covered by the table and the tail entries that are still
+    added one by one,
+  * RS1_LANE_SUMS -- the device code that evaluates the 8 lanes.
+
+Hash of a lane (chosen for the instruction mix of the scan kernel, whose
+bottleneck is the integer ALU pipe): one IMAD.HI per group of match bits on the
+FMA pipe, one AND,
+    byte offset = (sum_g umulhi(bits_g, magic_g)) & (((1 << bits) - 1) << 3)
+i.e. bits [35, 35 + bits) of the 64-bit products, already scaled to doubles.
+
+Tail entries cost one AND and one DFMA: the match bit p (>= 20) of the class
+mask, used as the HIGH word of a double, is the power of two 2^(2^(p-20) - 1023);
+multiplied by the weight pre-scaled with the inverse power the product is the
+weight exactly (or +-0), so fma(bit, w', acc) rounds exactly like acc + w.
 
 usage: python gen_rs1_inc.py > rs1_weights.inc
 """
@@ -32,7 +43,7 @@ spec.loader.exec_module(rs1)
 BASES = rs1.BASES
 MAX_TABLE_ENTRIES = 10          # leading entries of a lane covered by its table
 TABLE_ENTRIES = {"fG": 9}       # per-lane override (keeps every table at <= 1024 doubles)
-WIDE_SHIFTS = (32, 34, 36, 30, 28, 26)   # windows of the 64-bit product tried for single-group lanes
+FIELD_SHIFT = 3                 # index field sits at bits [3, 3 + bits) of the summed high words
 
 
 def lanes():
@@ -54,7 +65,11 @@ def valid_states(entries):
 
 
 def find_hash(entries, seed):
-    """Smallest index width with an injective multiply-shift hash (per-c1 group magics)."""
+    """Smallest index width with an injective hash
+        h = sum over first-base groups of (umulhi(x_g, hi_g) + x_g * lo_g)   (mod 2^32)
+    whose bits [3, 3 + bits) are the table slot.  lo_g is tried as 0 first (one multiply
+    per group); match bits below position 4 cannot reach the field through the high word,
+    so lanes that have them need the low product as well."""
     groups = {}
     for i, (p, c1, _) in enumerate(entries):
         groups.setdefault(c1, []).append(i)
@@ -66,35 +81,35 @@ def find_hash(entries, seed):
             pat[gi, si] = sum(1 << entries[i][0] for i in s if i in idxs)
     need = int(np.ceil(np.log2(len(states))))
     rng = np.random.default_rng(seed)
+    batch = 1024
+    m32 = np.uint64(0xFFFFFFFF)
+
+    def sparse():
+        m = rng.integers(0, 2 ** 32, size=batch, dtype=np.uint64)
+        for _ in range(int(rng.integers(0, 4))):
+            m &= rng.integers(0, 2 ** 32, size=batch, dtype=np.uint64)
+        return m
+
     for bits in (need, need + 1, need + 2):
-        # 32-bit product: (sum of (x_g * magic_g)) >> (32 - bits)
-        for t in range((150000 if len(glist) > 1 else 60000) if bits == need else 30000):
-            magics = []
-            for _ in glist:
-                m = rng.integers(0, 2 ** 32, dtype=np.uint64) & rng.integers(0, 2 ** 32, dtype=np.uint64)
-                if t % 2:
-                    m &= rng.integers(0, 2 ** 32, dtype=np.uint64)
-                magics.append(m)
-            acc = np.zeros(len(states), dtype=np.uint64)
-            for gi, m in enumerate(magics):
-                acc = (acc + pat[gi] * m) & np.uint64(0xFFFFFFFF)
-            if len(np.unique(acc >> np.uint64(32 - bits))) == len(states):
-                return bits, [(c1, sum(1 << entries[i][0] for i in idxs), int(magics[gi]))
-                              for gi, (c1, idxs) in enumerate(glist)], 0
-        if len(glist) == 1:
-            # 64-bit product, window of `bits` bits at shift s: ((x * magic) >> s) & (2^bits - 1)
-            for t in range(600):
-                m = rng.integers(0, 2 ** 32, size=2048, dtype=np.uint64)
-                for _ in range(int(rng.integers(0, 4))):
-                    m &= rng.integers(0, 2 ** 32, size=2048, dtype=np.uint64)
-                prod = pat[0][None, :] * m[:, None]
-                for sh in WIDE_SHIFTS:
-                    h = (prod >> np.uint64(sh)) & np.uint64((1 << bits) - 1)
-                    h.sort(axis=1)
-                    ok = (np.diff(h.astype(np.int64), axis=1) != 0).all(axis=1)
-                    if ok.any():
-                        c1, idxs = glist[0]
-                        return bits, [(c1, sum(1 << entries[i][0] for i in idxs), int(m[np.argmax(ok)]))], sh
+        field = np.uint64((1 << bits) - 1)
+        for with_lo in (False, True):
+            for t in range(1500 if bits == need else 400):
+                acc = np.zeros((batch, len(states)), dtype=np.uint64)
+                his, los = [], []
+                for gi in range(len(glist)):
+                    hi = sparse()
+                    lo = sparse() if with_lo else np.zeros(batch, dtype=np.uint64)
+                    his.append(hi)
+                    los.append(lo)
+                    acc += (pat[gi][None, :] * hi[:, None]) >> np.uint64(32)
+                    acc += (pat[gi][None, :] * lo[:, None]) & m32
+                h = (acc >> np.uint64(FIELD_SHIFT)) & field
+                h.sort(axis=1)
+                ok = (np.diff(h.astype(np.int64), axis=1) != 0).all(axis=1)
+                if ok.any():
+                    k = int(np.argmax(ok))
+                    return bits, [(c1, sum(1 << entries[i][0] for i in idxs), int(his[gi][k]), int(los[gi][k]))
+                                  for gi, (c1, idxs) in enumerate(glist)]
     raise SystemExit("no perfect hash found")
 
 
@@ -114,11 +129,10 @@ def main():
 
     # ---- lane descriptors for the host-side table builder
     emit("struct Rs1Entry { int pos; int first_base; double weight; };     // first_base < 0: first-order term")
-    emit("struct Rs1Group { int first_base; unsigned mask; unsigned magic; };")
-    emit("// wide_shift == 0: index = (sum of (bits & mask) * magic, 32-bit) >> (32 - bits);")
-    emit("// wide_shift  > 0: index = (((bits & mask) * magic, 64-bit) >> wide_shift) & (2^bits - 1)")
+    emit("struct Rs1Group { int first_base; unsigned mask; unsigned magic_hi; unsigned magic_lo; };")
+    emit("// table slot of a set of matching entries = ((sum over groups of umulhi(x_g, magic_hi) + x_g * magic_lo) >> 3) & (2^bits - 1)")
     emit("struct Rs1Lane { const char *name; int lane_base; int n_entries; int n_table; int bits; int offset; "
-         "int wide_shift; int n_groups; Rs1Group groups[4]; Rs1Entry entries[16]; };")
+         "int n_groups; Rs1Group groups[4]; Rs1Entry entries[16]; };")
     descs, code, offset = [], [], 0
     mask_name = {0: "mA", 1: "mT", 2: "mC", 3: "mG"}
     next_name = {0: "nA", 1: "nT", 2: "nC", 3: "nG"}
@@ -127,38 +141,25 @@ def main():
         # never split a group of mutually exclusive entries (same position) across table / tail
         while n_table < len(entries) and n_table > 0 and entries[n_table][0] == entries[n_table - 1][0]:
             n_table -= 1
-        bits, groups, wide = find_hash(entries[:n_table], seed=100 + li)
+        bits, groups = find_hash(entries[:n_table], seed=100 + li)
         ents = ", ".join(f"{{{p}, {-1 if c1 is None else c1}, {hexf(v)}}}" for p, c1, v in entries)
-        grps = ", ".join(f"{{{-1 if c1 is None else c1}, 0x{m:x}u, 0x{mg:x}u}}" for c1, m, mg in groups)
-        descs.append(f'    {{"{name}", {base}, {len(entries)}, {n_table}, {bits}, {offset}, {wide}, {len(groups)}, {{{grps}}}, {{{ents}}}}}')
+        grps = ", ".join(f"{{{-1 if c1 is None else c1}, 0x{m:x}u, 0x{mh:x}u, 0x{ml:x}u}}" for c1, m, mh, ml in groups)
+        descs.append(f'    {{"{name}", {base}, {len(entries)}, {n_table}, {bits}, {offset}, {len(groups)}, {{{grps}}}, {{{ents}}}}}')
         # ---- device code of this lane
         second = name[0] == "d"
         terms = []
-        for c1, m, mg in groups:
-            src = f"({mask_name[c1]} & {next_name[base]} & 0x{m:x}u)" if second else f"({mask_name[base]} & 0x{m:x}u)"
-            terms.append(f"{src} * 0x{mg:x}u")
-        if wide:
-            c1, m, mg = groups[0]
-            code.append(f"    double {name} = T[{offset} + ((uint32_t)(((unsigned long long)({mask_name[base]} & 0x{m:x}u) * 0x{mg:x}ull) >> {wide}) & 0x{(1 << bits) - 1:x}u)];")
-        else:
-            code.append(f"    double {name} = T[{offset} + ((" + " + ".join(terms) + f") >> {32 - bits})];")
-        tail = entries[n_table:]
-        k = 0
-        while k < len(tail):
-            same = [e for e in tail if e[0] == tail[k][0]]
-            if len(same) == 1:
-                p, c1, v = tail[k]
-                cond = f"{mask_name[c1]} & {next_name[base]} & 0x{1 << p:x}u" if second else f"{mask_name[base]} & 0x{1 << p:x}u"
-                code.append(f"    if ({cond}) {name} = __dadd_rn({name}, {hexf(v)});   // {v!r}")
-            else:
-                # mutually exclusive entries at one position: one add of the selected weight (+0.0 is exact)
-                code.append("    {")
-                code.append("        double w = 0.0;")
-                for p, c1, v in same:
-                    code.append(f"        if ({mask_name[c1]} & {next_name[base]} & 0x{1 << p:x}u) w = {hexf(v)};   // {v!r}")
-                code.append(f"        {name} = __dadd_rn({name}, w);")
-                code.append("    }")
-            k += len(same)
+        for c1, m, mh, ml in groups:
+            src = f"{mask_name[c1]} & {next_name[base]} & 0x{m:x}u" if second else f"{mask_name[base]} & 0x{m:x}u"
+            terms.append(f"__umulhi({src}, 0x{mh:x}u)")
+            if ml:
+                terms.append(f"({src}) * 0x{ml:x}u")
+        code.append(f"    double {name} = RS1_LD(T, {8 * offset}u, (" + " + ".join(terms) + f") & 0x{((1 << bits) - 1) << FIELD_SHIFT:x}u);")
+        for p, c1, v in entries[n_table:]:
+            # entries at one position are mutually exclusive: at most one of the fma's adds a non-zero
+            assert p >= 20, "tail entry below bit 20: extend the generator with a shift"
+            e = 1 << (p - 20)
+            cond = f"{mask_name[c1]} & {next_name[base]} & 0x{1 << p:x}u" if second else f"{mask_name[base]} & 0x{1 << p:x}u"
+            code.append(f"    {name} = RS1_FMA_BIT({cond}, {hexf(v * 2.0 ** (1023 - e))}, {name});   // {v!r} * 2^{1023 - e}")
         offset += 1 << bits
     emit(f"#define RS1_TABLE_DOUBLES {offset}")
     emit("static const Rs1Lane kRs1Lanes[8] = {")

@@ -25,6 +25,12 @@ static constexpr size_t kRs1TableBytes = (size_t)RS1_TABLE_DOUBLES * sizeof(doub
 // table of exact sequential fp64 sums (built on the host at crp_init, staged in shared
 // memory; rs1_weights.inc).  s0/s1: planar code bits of the scored 30-mer (bit q = base q),
 // valid: bases that score.
+// lane table entry at a byte offset that is already a multiple of 8 (see gen_rs1_inc.py)
+#define RS1_LD(T, lane_off, byte_idx) (*reinterpret_cast<const double *>(reinterpret_cast<const char *>(T) + (lane_off) + (byte_idx)))
+// acc + w iff the match bit is set, as ONE DFMA: bit (a single bit p >= 20 of a class mask)
+// read as the high word of a double is a power of two, w_scaled = w / that power.
+#define RS1_FMA_BIT(bit, w_scaled, acc) __fma_rn(__hiloint2double((int)(bit), 0), (w_scaled), (acc))
+
 __device__ __forceinline__ double rs1_canonical(const double *__restrict__ T, uint32_t s0, uint32_t s1,
                                                 uint32_t valid) {
     const uint32_t mA = ~s1 & ~s0 & valid, mT = ~s1 & s0 & valid, mC = s1 & ~s0 & valid, mG = s1 & s0 & valid;
@@ -46,18 +52,17 @@ static int build_rs1_tables(std::vector<double> &tab, char *err, size_t errlen) 
                 for (int j = i + 1; j < ln.n_table; ++j)
                     if ((sub >> i & 1) && (sub >> j & 1) && ln.entries[i].pos == ln.entries[j].pos) ok = false;
             if (!ok) continue;
-            uint32_t h = 0, x0 = 0;
+            uint32_t h = 0;
             volatile double sum = 0.0;            // one IEEE add per entry, in ascending column order
-            for (int i = 0; i < ln.n_table; ++i) {
-                if (!(sub >> i & 1)) continue;
-                for (int g = 0; g < ln.n_groups; ++g)
-                    if (ln.groups[g].first_base == ln.entries[i].first_base) h += (1u << ln.entries[i].pos) * ln.groups[g].magic;
-                x0 |= 1u << ln.entries[i].pos;
-                sum = sum + ln.entries[i].weight;
+            for (int g = 0; g < ln.n_groups; ++g) {
+                uint32_t x = 0;                   // match bits of this first-base group
+                for (int i = 0; i < ln.n_table; ++i)
+                    if ((sub >> i & 1) && ln.groups[g].first_base == ln.entries[i].first_base) x |= 1u << ln.entries[i].pos;
+                h += (uint32_t)(((unsigned long long)x * ln.groups[g].magic_hi) >> 32) + x * ln.groups[g].magic_lo;
             }
-            uint32_t slot = h >> (32 - ln.bits);
-            if (ln.wide_shift)                    // single group: window of the 64-bit product
-                slot = (uint32_t)(((unsigned long long)x0 * ln.groups[0].magic) >> ln.wide_shift) & ((1u << ln.bits) - 1u);
+            for (int i = 0; i < ln.n_table; ++i)
+                if (sub >> i & 1) sum = sum + ln.entries[i].weight;
+            const uint32_t slot = (h >> 3) & ((1u << ln.bits) - 1u);
             const uint32_t idx = ln.offset + slot;
             if (idx >= RS1_TABLE_DOUBLES || used[idx]) {
                 snprintf(err, errlen, "rs1 table hash of lane %s is not injective", ln.name);

@@ -157,16 +157,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
 }
 
 // bits b of a 32-position word starting at token position t0 with lo <= t0+b <= hi
-__device__ __forceinline__ uint32_t range_mask(int64_t t0, int64_t lo, int64_t hi) {
-    int64_t a = lo - t0, b = hi - t0;
+__device__ __forceinline__ uint32_t range_mask(int32_t t0, int32_t lo, int32_t hi) {
+    int32_t a = lo - t0, b = hi - t0;
     if (a < 0) a = 0;
     if (b > 31) b = 31;
     if (a > b) return 0u;
-    return (0xFFFFFFFFu >> (31 - (int)b)) & (0xFFFFFFFFu << (int)a);
+    return (0xFFFFFFFFu >> (31 - b)) & (0xFFFFFFFFu << a);
 }
-
-__device__ __forceinline__ uint32_t upper_g(const uint4 w) { return w.x & w.y & ~w.z & ~w.w; }
-__device__ __forceinline__ uint32_t upper_c(const uint4 w) { return ~w.x & w.y & ~w.z & ~w.w; }
 
 struct Hits {
     uint32_t pA, mA, pB, mB;   // '+' / '-' hit masks of word tid (A) and word tid + 256 (B)
@@ -177,23 +174,25 @@ struct Hits {
 //   '-': (?=CC.) at t  <=>  tok[t]==tok[t+1]=='C' and t+2 < L  (CROPSR.py:426)
 //   bounds (CROPSR.py:419 / :430): '+' t >= l+5;  '-' 2 <= t <= L-l+7
 //   plus ownership: t inside the n positions of the tile that the segment owns.
+// All positions fit int32: L < 2^31 - 2^15 (crp_genome_add_segment), 1 <= l <= 10^6.
 __device__ __forceinline__ Hits tile_hits(const uint4 *__restrict__ rec, const TileDesc td, int l, int tid) {
     const uint4 a = rec[2 + tid], an = rec[3 + tid], b = rec[2 + kThreads + tid], bn = rec[3 + kThreads + tid];
-    const uint32_t gA = upper_g(a), gAn = upper_g(an), gB = upper_g(b), gBn = upper_g(bn);
-    const uint32_t cA = upper_c(a), cAn = upper_c(an), cB = upper_c(b), cBn = upper_c(bn);
+    const uint32_t uA = ~(a.z | a.w), uAn = ~(an.z | an.w), uB = ~(b.z | b.w), uBn = ~(bn.z | bn.w);   // upper-case ACGT
+    const uint32_t gA = a.x & a.y & uA, gAn = an.x & an.y & uAn, gB = b.x & b.y & uB, gBn = bn.x & bn.y & uBn;
+    const uint32_t cA = ~a.x & a.y & uA, cAn = ~an.x & an.y & uAn, cB = ~b.x & b.y & uB, cBn = ~bn.x & bn.y & uBn;
     Hits h;
     h.pA = __funnelshift_r(gA, gAn, 1) & __funnelshift_r(gA, gAn, 2);
     h.pB = __funnelshift_r(gB, gBn, 1) & __funnelshift_r(gB, gBn, 2);
     h.mA = cA & __funnelshift_r(cA, cAn, 1);
     h.mB = cB & __funnelshift_r(cB, cBn, 1);
-    const int64_t L = td.L;
-    const int64_t last_owned = (int64_t)td.t_start + td.n - 1;
-    const int64_t hi_p = L - 3 < last_owned ? L - 3 : last_owned;
-    const int64_t hi_m = L - l + 7 < hi_p ? L - l + 7 : hi_p;
-    if ((int64_t)td.t_start < (int64_t)l + 5 || (int64_t)td.t_start + kTile - 1 > hi_m) {   // edge tiles only
-        const int64_t tA = (int64_t)td.t_start + 32 * tid, tB = tA + 32 * kThreads;
-        h.pA &= range_mask(tA, (int64_t)l + 5, hi_p);
-        h.pB &= range_mask(tB, (int64_t)l + 5, hi_p);
+    const int32_t t0 = (int32_t)td.t_start, L = (int32_t)td.L;
+    const int32_t last_owned = t0 + (int32_t)td.n - 1;
+    const int32_t hi_p = min(L - 3, last_owned);
+    const int32_t hi_m = min(L - l + 7, hi_p);
+    if (t0 < l + 5 || t0 + kTile - 1 > hi_m) {   // edge tiles only
+        const int32_t tA = t0 + 32 * tid, tB = tA + 32 * kThreads;
+        h.pA &= range_mask(tA, l + 5, hi_p);
+        h.pB &= range_mask(tB, l + 5, hi_p);
         h.mA &= range_mask(tA, 2, hi_m);
         h.mB &= range_mask(tB, 2, hi_m);
     }
@@ -226,31 +225,31 @@ struct Window {
 // 30-base window of one hit out of the staged record.
 // '+': tok[t-25, t+5) read backwards (output base q = tok[t+4-q]), upper-case bases complemented;
 // '-': tok[t-2, t+28) read forwards.   pl = position inside the tile.
-__device__ __forceinline__ Window extract_window(const uint4 *__restrict__ rec, uint32_t pl, bool minus, uint32_t t,
-                                                 uint32_t L) {
-    const uint32_t ws = pl + 32u - (minus ? 2u : 25u);      // relative to the first halo position
+template <bool kMinus>
+__device__ __forceinline__ Window extract_window(const uint4 *__restrict__ rec, uint32_t pl, uint32_t t, uint32_t L) {
+    const uint32_t ws = pl + (kMinus ? 30u : 7u);           // relative to the first halo position
     const uint32_t wi = 1u + (ws >> 5), sh = ws & 31u;
     const uint4 lo = rec[wi], hi = rec[wi + 1];
     const uint32_t p0 = __funnelshift_r(lo.x, hi.x, sh), p1 = __funnelshift_r(lo.y, hi.y, sh);
     const uint32_t lw = __funnelshift_r(lo.z, hi.z, sh), ot = __funnelshift_r(lo.w, hi.w, sh);
     const uint32_t special = ot & p0;       // 'U' / 'Z': "other" bytes that still score
     const uint32_t valid = ~ot | special;
-    // '+': A<->T, C<->G of upper-case bases flips the low code bit; '-': U scores as A, Z as C
-    const uint32_t low = p0 ^ (minus ? special : (~lw & ~ot));
     Window w;
-    if (minus) {
-        w.s0 = low & 0x3FFFFFFFu;
+    if (kMinus) {
+        w.s0 = (p0 ^ special) & 0x3FFFFFFFu;                 // U scores as A, Z as C
         w.s1 = p1 & 0x3FFFFFFFu;
         w.valid = valid & 0x3FFFFFFFu;
     } else {
-        w.s0 = __brev(low) >> 2;
+        w.s0 = __brev(p0 ^ ~(lw | ot)) >> 2;                 // A<->T, C<->G of upper-case bases flips the low code bit
         w.s1 = __brev(p1) >> 2;
         w.valid = __brev(valid) >> 2;
     }
-    w.packed = (unsigned long long)w.s0 | ((unsigned long long)w.s1 << 32);
-    if ((lw | ot) & 0x3FFFFFFFu) w.packed |= CRP_PACKED_IRREGULAR;
-    if ((uint64_t)t + (minus ? 28u : 5u) > L) w.packed |= CRP_PACKED_TRUNCATED;
-    if (w.valid != 0x3FFFFFFFu) w.packed |= CRP_PACKED_UNSCORED;
+    uint32_t hi32 = w.s1;
+    if (w.valid != 0x3FFFFFFFu) hi32 |= (uint32_t)(CRP_PACKED_UNSCORED >> 32);
+    uint32_t lo32 = w.s0;
+    if ((lw | ot) & 0x3FFFFFFFu) lo32 |= (uint32_t)CRP_PACKED_IRREGULAR;
+    if (t + (kMinus ? 28u : 5u) > L) lo32 |= (uint32_t)CRP_PACKED_TRUNCATED;
+    w.packed = ((unsigned long long)hi32 << 32) | lo32;
     return w;
 }
 
@@ -258,33 +257,65 @@ __device__ __forceinline__ unsigned long long unpack_counts(uint32_t c) {   // (
     return ((unsigned long long)(c & 0xFFFFu) << 32) | (c >> 16);
 }
 
-// hits of one word into the compacted list: highest position first, ranks descending
-__device__ __forceinline__ void list_hits(uint16_t *__restrict__ list, uint32_t m, uint32_t rank_end, uint32_t pos0,
-                                          uint32_t lo, uint32_t slot0) {
-    // rank_end = rank of the word's last hit + 1; entries with lo <= rank < lo + kListCap land at slot0 + rank - lo
+// hits of one word into the compacted list, highest position first.  end = one past the
+// slot of the word's last hit.
+__device__ __forceinline__ void list_hits(uint16_t *__restrict__ end, uint32_t m, uint32_t pos0) {
+    while (m) {
+        const uint32_t b = 31u - (uint32_t)__clz(m);
+        m ^= 1u << b;
+        *--end = (uint16_t)(pos0 + b);
+    }
+}
+// same, for a tile with more than kListCap hits on a strand: only ranks [lo, lo + kListCap)
+__device__ __forceinline__ void list_hits_window(uint16_t *__restrict__ list, uint32_t m, uint32_t rank_end,
+                                                 uint32_t pos0, uint32_t lo) {
     uint32_t r = rank_end;
     while (m) {
-        const int b = 31 - __clz(m);
+        const uint32_t b = 31u - (uint32_t)__clz(m);
         m ^= 1u << b;
         --r;
-        if (r - lo < (uint32_t)kListCap) list[slot0 + r - lo] = (uint16_t)(pos0 + b);
+        if (r - lo < (uint32_t)kListCap) list[r - lo] = (uint16_t)(pos0 + b);
+    }
+}
+
+// one thread per listed hit of one strand: window, score, coalesced stores
+template <bool kScore, bool kMinus>
+__device__ __forceinline__ void emit_strand(const ScanArgs &a, const double *__restrict__ tab,
+                                            const uint4 *__restrict__ rec, const uint16_t *__restrict__ list,
+                                            uint32_t count, uint64_t out0, uint32_t t_start, uint32_t L, uint32_t slot) {
+    uint32_t *const pos = (kMinus ? a.pos_minus : a.pos_plus) + out0;
+    unsigned long long *const packed = (kMinus ? a.packed_minus : a.packed_plus) + out0;
+    double *const xs = (kMinus ? a.x_minus : a.x_plus) + out0;
+    if (out0 >= a.capacity) return;
+    if (count > a.capacity - out0) count = (uint32_t)(a.capacity - out0);
+    for (uint32_t i = slot; i < count; i += kThreads) {
+        const uint32_t pl = list[i], t = t_start + pl;
+        __stcs(pos + i, t);
+        if (kScore) {
+            const Window w = extract_window<kMinus>(rec, pl, t, L);
+            double x = rs1_canonical(tab, w.s0, w.s1, w.valid);
+            if (a.flags & CRP_SCAN_LOGISTIC) x = 1.0 / (1.0 + exp(x));
+            __stcs(packed + i, w.packed);
+            __stcs(xs + i, x);
+        }
     }
 }
 
 template <bool kScore>
 __global__ void __launch_bounds__(kThreads, CRP_CTAS_PER_SM)
 k_scan_score(const ScanArgs a) {
-    // dynamic shared memory: [stage 0][stage 1][RS1 lane tables][hit list][range prefixes]
+    // dynamic shared memory: [stage 0][stage 1][hit lists][range prefixes]
     extern __shared__ __align__(128) unsigned char s_dyn[];
     auto stage = [&](int b) { return reinterpret_cast<uint4 *>(s_dyn + (size_t)b * kRecBytes); };
-    double *const s_tab = reinterpret_cast<double *>(s_dyn + 2 * kRecBytes);
-    uint16_t *const s_list = reinterpret_cast<uint16_t *>(s_dyn + 2 * kRecBytes + kRs1TableBytes);
+    uint16_t *const s_list = reinterpret_cast<uint16_t *>(s_dyn + 2 * kRecBytes);
     unsigned long long *const s_rangepref =
-        reinterpret_cast<unsigned long long *>(s_dyn + 2 * kRecBytes + kRs1TableBytes + 2 * kListCap * sizeof(uint16_t));
+        reinterpret_cast<unsigned long long *>(s_dyn + 2 * kRecBytes + 2 * kListCap * sizeof(uint16_t));
+    __shared__ __align__(16) double s_tab[kScore ? RS1_TABLE_DOUBLES : 1];   // static: LDS takes the table offset as an immediate
     __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ uint32_t s_cnt[kMaxRange][kWarps];
     __shared__ uint2 s_wt[kWarps];
     __shared__ unsigned long long s_scan[kWarps];
+    __shared__ unsigned long long s_base[2];     // output offsets (plus << 32 | minus) of the tile staged in buffer b
     __shared__ uint32_t s_next;
 
     cg::grid_group grid = cg::this_grid();
@@ -392,7 +423,10 @@ k_scan_score(const ScanArgs a) {
         if (tid == 0) {
             const uint32_t t0 = w_lo + atomicAdd(ticket, 1u);
             s_next = t0;
-            if (t0 < w_hi) bulk_load(stage(0), record(t0), kRecBytes, &s_bar[0]);
+            if (t0 < w_hi) {
+                bulk_load(stage(0), record(t0), kRecBytes, &s_bar[0]);
+                s_base[0] = s_rangepref[(t0 - w_lo) / k] + a.tile_pref[t0];
+            }
         }
         __syncthreads();
         uint32_t tile = s_next;
@@ -400,12 +434,12 @@ k_scan_score(const ScanArgs a) {
             const int b = it & 1;
             // the next tile of this CTA: ticket now, its bulk copy lands while this tile is emitted
             uint32_t claimed = 0;
+            unsigned long long claimed_pref = 0;
             if (tid == 0) claimed = w_lo + atomicAdd(ticket, 1u);
             wait_stage(b);
             const uint4 *rec = stage(b);
             const uint4 d = rec[0];
             const TileDesc td = {d.x, d.y, d.z, d.w};
-            const unsigned long long tpref = __ldg(a.tile_pref + tile);
             const Hits h = tile_hits(rec, td, l, tid);
             // ---- block scan of the per-word counts: all A words precede all B words
             const uint32_t cA = __popc(h.pA) | (__popc(h.mA) << 16), cB = __popc(h.pB) | (__popc(h.mB) << 16);
@@ -420,50 +454,52 @@ k_scan_score(const ScanArgs a) {
             }
             if (lane == 31) s_wt[warp] = make_uint2(iA, iB);
             __syncthreads();
-            if (tid == 0) {                                    // ticket has arrived by now: start the prefetch
+            if (tid == 0) {                                    // the ticket has arrived by now: start the prefetch
                 s_next = claimed;
-                if (claimed < w_hi) bulk_load(stage(b ^ 1), record(claimed), kRecBytes, &s_bar[b ^ 1]);
+                if (claimed < w_hi) {
+                    bulk_load(stage(b ^ 1), record(claimed), kRecBytes, &s_bar[b ^ 1]);
+                    claimed_pref = __ldg(a.tile_pref + claimed);   // consumed after the list is built
+                }
             }
-            const uint2 wt = lane < kWarps ? s_wt[lane] : make_uint2(0u, 0u);
-            const uint32_t totA = __reduce_add_sync(0xFFFFFFFFu, wt.x), totB = __reduce_add_sync(0xFFFFFFFFu, wt.y);
+            const uint2 wt = s_wt[lane & (kWarps - 1)];
+            const uint32_t totA = __reduce_add_sync(0xFFFFFFFFu, lane < kWarps ? wt.x : 0u);
+            const uint32_t totB = __reduce_add_sync(0xFFFFFFFFu, lane < kWarps ? wt.y : 0u);
             const uint32_t preA = __reduce_add_sync(0xFFFFFFFFu, lane < warp ? wt.x : 0u);
             const uint32_t preB = __reduce_add_sync(0xFFFFFFFFu, lane < warp ? wt.y : 0u);
             const uint32_t np = (totA & 0xFFFFu) + (totB & 0xFFFFu), nm = (totA >> 16) + (totB >> 16);
             // rank (inside the tile, per strand) one past the last hit of my words
             const uint32_t endA = preA + iA, endB = totA + preB + iB;
             const uint32_t epA = endA & 0xFFFFu, emA = endA >> 16, epB = endB & 0xFFFFu, emB = endB >> 16;
-            const unsigned long long base = s_rangepref[(tile - w_lo) / k] + tpref;
+            const unsigned long long base = s_base[b];
             const uint64_t base_p = base >> 32, base_m = base & 0xFFFFFFFFull;
-            if (tid == 0)
-                a.tile_incl[tile] = base + (((unsigned long long)np << 32) | nm);
+            if (tid == 0) a.tile_incl[tile] = base + (((unsigned long long)np << 32) | nm);
 
-            for (uint32_t lo = 0; lo < np || lo < nm; lo += kListCap) {
-                const uint32_t cp = np > lo ? min(np - lo, (uint32_t)kListCap) : 0u;
-                const uint32_t cm = nm > lo ? min(nm - lo, (uint32_t)kListCap) : 0u;
-                if (lo) __syncthreads();                       // previous batch fully consumed
-                list_hits(s_list, h.pA, epA, 32u * tid, lo, 0u);
-                list_hits(s_list, h.pB, epB, 32u * (kThreads + tid), lo, 0u);
-                list_hits(s_list, h.mA, emA, 32u * tid, lo, cp);
-                list_hits(s_list, h.mB, emB, 32u * (kThreads + tid), lo, cp);
+            uint16_t *const list_p = s_list, *const list_m = s_list + kListCap;
+            if (np <= (uint32_t)kListCap && nm <= (uint32_t)kListCap) {
+                list_hits(list_p + epA, h.pA, 32u * tid);
+                list_hits(list_p + epB, h.pB, 32u * (kThreads + tid));
+                list_hits(list_m + emA, h.mA, 32u * tid);
+                list_hits(list_m + emB, h.mB, 32u * (kThreads + tid));
+                if (tid == 0 && claimed < w_hi) s_base[b ^ 1] = s_rangepref[(claimed - w_lo) / k] + claimed_pref;
                 __syncthreads();
-                for (uint32_t i = tid; i < cp + cm; i += kThreads) {
-                    const bool minus = i >= cp;
-                    const uint32_t pl = s_list[i], t = td.t_start + pl;
-                    const uint64_t o = minus ? base_m + lo + (i - cp) : base_p + lo + i;
-                    if (o < a.capacity) {
-                        uint32_t *const pos = minus ? a.pos_minus : a.pos_plus;
-                        __stcs(pos + o, t);
-                        if (kScore) {
-                            const Window w = extract_window(rec, pl, minus, t, td.L);
-                            double x = rs1_canonical(s_tab, w.s0, w.s1, w.valid);
-                            if (a.flags & CRP_SCAN_LOGISTIC) x = 1.0 / (1.0 + exp(x));
-                            __stcs((minus ? a.packed_minus : a.packed_plus) + o, w.packed);
-                            __stcs((minus ? a.x_minus : a.x_plus) + o, x);
-                        }
-                    }
+                emit_strand<kScore, false>(a, s_tab, rec, list_p, np, base_p, td.t_start, td.L, tid);
+                emit_strand<kScore, true>(a, s_tab, rec, list_m, nm, base_m, td.t_start, td.L, tid ^ (kThreads / 2));
+            } else {                                           // pathological density: batches of kListCap ranks
+                if (tid == 0 && claimed < w_hi) s_base[b ^ 1] = s_rangepref[(claimed - w_lo) / k] + claimed_pref;
+                for (uint32_t lo = 0; lo < np || lo < nm; lo += kListCap) {
+                    const uint32_t cp = np > lo ? min(np - lo, (uint32_t)kListCap) : 0u;
+                    const uint32_t cm = nm > lo ? min(nm - lo, (uint32_t)kListCap) : 0u;
+                    if (lo) __syncthreads();                   // previous batch fully consumed
+                    list_hits_window(list_p, h.pA, epA, 32u * tid, lo);
+                    list_hits_window(list_p, h.pB, epB, 32u * (kThreads + tid), lo);
+                    list_hits_window(list_m, h.mA, emA, 32u * tid, lo);
+                    list_hits_window(list_m, h.mB, emB, 32u * (kThreads + tid), lo);
+                    __syncthreads();
+                    emit_strand<kScore, false>(a, s_tab, rec, list_p, cp, base_p + lo, td.t_start, td.L, tid);
+                    emit_strand<kScore, true>(a, s_tab, rec, list_m, cm, base_m + lo, td.t_start, td.L, tid);
                 }
             }
-            __syncthreads();                                   // stage b, the list and s_next are settled
+            __syncthreads();                                   // stage b, the lists, s_next and s_base are settled
             tile = s_next;
         }
         wave_base += wave_total;
@@ -498,6 +534,7 @@ __global__ void k_rescore(const uint4 *__restrict__ records, const RescoreItem *
     if (i >= n) return;
     const RescoreItem it = items[i];
     const uint4 *rec = records + (size_t)it.tile * kRecWords;
-    const Window w = extract_window(rec, it.pl, it.strand == '-', 0u, 0xFFFFFFFFu);
+    const Window w = it.strand == '-' ? extract_window<true>(rec, it.pl, 0u, 0xFFFFFFFFu)
+                                      : extract_window<false>(rec, it.pl, 0u, 0xFFFFFFFFu);
     x_out[i] = rs1_dense(w.s0, w.s1, w.valid, (int)(it.cls & 15u), (int)(it.cls >> 4));
 }
