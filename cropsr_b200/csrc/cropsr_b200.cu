@@ -90,9 +90,35 @@ struct crp_result {
     float ms_scan = 0.f;
 };
 
+// CRP_TRACE=1: host-side wall time of every stage of the big calls, on stderr
+#include <chrono>
+struct Trace {
+    const char *what;
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    explicit Trace(const char *w) : what(w), on(getenv("CRP_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char *stage) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[crp] %s: %s %.3f ms\n", what, stage, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 static int need_ctx() {
     if (!g_ctx.ready) return fail(CRP_ERR_STATE, "crp_init has not been called");
     return 0;
+}
+
+// Device memory comes from the stream-ordered pool of the device, which crp_init tells to keep
+// freed blocks (cudaMalloc / cudaFree cost 10-70 ms per call on a 180 GB part; a genome commit
+// and a scan allocate ~1 GB between them).
+template <typename T>
+static cudaError_t dev_alloc(T **ptr, size_t bytes) {
+    return cudaMallocAsync(reinterpret_cast<void **>(ptr), bytes ? bytes : 16, g_ctx.stream);
+}
+static void dev_free(void *ptr) {
+    if (ptr) cudaFreeAsync(ptr, g_ctx.stream);
 }
 
 // ------------------------------------------------------------------ C ABI
@@ -123,6 +149,12 @@ int crp_init(int device) {
                     prop.major, prop.minor);
     CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
     {
+        cudaMemPool_t pool;
+        CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = UINT64_MAX;
+        CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    {
         std::vector<double> tab;
         char msg[128];
         if (build_rs1_tables(tab, msg, sizeof msg)) return fail(CRP_ERR_STATE, "%s", msg);
@@ -139,6 +171,10 @@ int crp_init(int device) {
 int crp_shutdown(void) {
     if (!g_ctx.ready) return 0;
     cudaStreamSynchronize(g_ctx.stream);
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, g_ctx.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
     cudaStreamDestroy(g_ctx.stream);
     cudaFree(g_ctx.d_tables);
     g_ctx = Context();
@@ -210,6 +246,7 @@ int crp_genome_commit(crp_genome *g) {
     if (int rc = need_ctx()) return rc;
     if (g->committed) return fail(CRP_ERR_STATE, "genome already committed");
     cudaStream_t st = g_ctx.stream;
+    Trace tr("commit");
 
     // ---- layout: every segment owns whole tile records; the bytes it needs (its positions
     // plus 32 of context each side) go to an ASCII staging buffer, 16-byte aligned per segment
@@ -247,20 +284,22 @@ int crp_genome_commit(crp_genome *g) {
                     (unsigned long long)g->n_positions);
     g->n_tiles = (uint32_t)descs.size();
 
+    tr.lap("layout");
     uint8_t *d_ascii = nullptr;
     PackDesc *d_descs = nullptr;
     auto cleanup = [&]() {
-        cudaFree(d_ascii);
-        cudaFree(d_descs);
+        dev_free(d_ascii);
+        dev_free(d_descs);
     };
     const size_t rec_bytes = (size_t)g->n_tiles * kRecBytes;
-    if (cudaMalloc(&d_ascii, ascii_bytes + 64) != cudaSuccess || cudaMalloc(&d_descs, (descs.size() + 1) * sizeof(PackDesc)) != cudaSuccess ||
-        cudaMalloc(&g->records, rec_bytes + 16) != cudaSuccess) {
+    if (dev_alloc(&d_ascii, ascii_bytes + 64) != cudaSuccess || dev_alloc(&d_descs, (descs.size() + 1) * sizeof(PackDesc)) != cudaSuccess ||
+        dev_alloc(&g->records, rec_bytes + 16) != cudaSuccess) {
         cudaGetLastError();
         cleanup();
         return fail(CRP_ERR_NOMEM, "cudaMalloc of %llu record bytes + %llu staging bytes failed",
                     (unsigned long long)rec_bytes, (unsigned long long)ascii_bytes);
     }
+    tr.lap("cudaMalloc");
     cudaEvent_t e0, e1, e2;
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
@@ -285,18 +324,21 @@ int crp_genome_commit(crp_genome *g) {
     CUDA_TRY(cudaEventRecord(e2, st));
     if (!g->segs.empty()) {
         const size_t nb = g->segs.size() * sizeof(uint32_t);
-        CUDA_TRY(cudaMalloc(&g->d_seg_first, nb));
-        CUDA_TRY(cudaMalloc(&g->d_seg_count, nb));
+        CUDA_TRY(dev_alloc(&g->d_seg_first, nb));
+        CUDA_TRY(dev_alloc(&g->d_seg_count, nb));
         CUDA_TRY(cudaMemcpyAsync(g->d_seg_first, seg_first.data(), nb, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(g->d_seg_count, seg_count.data(), nb, cudaMemcpyHostToDevice, st));
     }
+    tr.lap("enqueue");
     CUDA_TRY(cudaStreamSynchronize(st));
+    tr.lap("sync");
     CUDA_TRY(cudaEventElapsedTime(&g->ms_h2d, e0, e1));
     CUDA_TRY(cudaEventElapsedTime(&g->ms_pack, e1, e2));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaEventDestroy(e2);
     cleanup();
+    tr.lap("cudaFree");
     for (Segment &s : g->segs) s.token = nullptr;   // host tokens may be released now
     g->committed = true;
     return 0;
@@ -311,18 +353,18 @@ int crp_genome_timing(const crp_genome *g, float *ms_h2d, float *ms_pack) {
 
 int crp_genome_free(crp_genome *g) {
     if (!g) return 0;
-    cudaFree(g->records);
-    cudaFree(g->d_seg_first);
-    cudaFree(g->d_seg_count);
+    dev_free(g->records);
+    dev_free(g->d_seg_first);
+    dev_free(g->d_seg_count);
     delete g;
     return 0;
 }
 
 static void free_streams(crp_result *r) {
     for (int s = 0; s < 2; ++s) {
-        cudaFree(r->pos[s]);
-        cudaFree(r->packed[s]);
-        cudaFree(r->x[s]);
+        dev_free(r->pos[s]);
+        dev_free(r->packed[s]);
+        dev_free(r->x[s]);
         r->pos[s] = nullptr;
         r->packed[s] = nullptr;
         r->x[s] = nullptr;
@@ -333,10 +375,10 @@ static int alloc_streams(crp_result *r, uint64_t cap, bool scored) {
     r->capacity = cap;
     const uint64_t n = cap ? cap : 1;
     for (int s = 0; s < 2; ++s) {
-        if (cudaMalloc(&r->pos[s], n * sizeof(uint32_t)) != cudaSuccess) goto oom;
+        if (dev_alloc(&r->pos[s], n * sizeof(uint32_t)) != cudaSuccess) goto oom;
         if (scored) {
-            if (cudaMalloc(&r->packed[s], n * sizeof(unsigned long long)) != cudaSuccess) goto oom;
-            if (cudaMalloc(&r->x[s], n * sizeof(double)) != cudaSuccess) goto oom;
+            if (dev_alloc(&r->packed[s], n * sizeof(unsigned long long)) != cudaSuccess) goto oom;
+            if (dev_alloc(&r->x[s], n * sizeof(double)) != cudaSuccess) goto oom;
         }
     }
     return 0;
@@ -448,12 +490,14 @@ int crp_scan_score(crp_genome *g, int guide_len, uint32_t flags, crp_result **re
         crp_result_free(r);
         return code;
     };
+    Trace tr("scan");
     ScanPlan plan = {};
     if ((rc = plan_scan(g, r->scored, &plan))) return bail(rc);
+    tr.lap("plan");
     r->state_bytes = (2 * (size_t)g->n_tiles + 2 * (size_t)plan.grid) * sizeof(unsigned long long) +
                      ((size_t)plan.n_waves + 1) * sizeof(unsigned int);
-    if (cudaMalloc(&r->state, r->state_bytes) != cudaSuccess ||
-        cudaMalloc(&r->d_counts, (2 * (size_t)n_seg + 1) * sizeof(unsigned long long)) != cudaSuccess)
+    if (dev_alloc(&r->state, r->state_bytes) != cudaSuccess ||
+        dev_alloc(&r->d_counts, (2 * (size_t)n_seg + 1) * sizeof(unsigned long long)) != cudaSuccess)
         return bail(fail(CRP_ERR_NOMEM, "cudaMalloc of scan state failed"));
     if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)
         return bail(fail(CRP_ERR_CUDA, "cudaEventCreate failed"));
@@ -464,14 +508,17 @@ int crp_scan_score(crp_genome *g, int guide_len, uint32_t flags, crp_result **re
         uint64_t cap = g->n_positions / 8 + 4096;
         if ((rc = alloc_streams(r, cap, r->scored))) return bail(rc);
     }
+    tr.lap("cudaMalloc");
     for (int attempt = 0; attempt < 2; ++attempt) {
         if ((rc = launch_scan(g, r, plan, guide_len, flags, e0, e1))) return bail(rc);
+        tr.lap("launch");
         if (n_seg)
             if (cudaError_t e = cudaMemcpyAsync(counts.data(), r->d_counts, counts.size() * sizeof(unsigned long long),
                                                 cudaMemcpyDeviceToHost, st))
                 return bail(fail(CRP_ERR_CUDA, "D2H of segment counts failed: %s", cudaGetErrorString(e)));
         if (cudaError_t e = cudaStreamSynchronize(st))
             return bail(fail(CRP_ERR_CUDA, "scan kernels failed: %s", cudaGetErrorString(e)));
+        tr.lap("sync");
         r->n_plus = r->n_minus = 0;
         r->seg_plus.assign(n_seg, 0);
         r->seg_minus.assign(n_seg, 0);
@@ -548,8 +595,8 @@ int crp_result_timing(const crp_result *res, float *ms_scan) {
 int crp_result_free(crp_result *r) {
     if (!r) return 0;
     free_streams(r);
-    cudaFree(r->state);
-    cudaFree(r->d_counts);
+    dev_free(r->state);
+    dev_free(r->d_counts);
     delete r;
     return 0;
 }
@@ -578,9 +625,9 @@ int crp_rescore(const crp_genome *g, uint64_t n, const uint32_t *segment, const 
     cudaStream_t st = g_ctx.stream;
     RescoreItem *d_items = nullptr;
     double *d_x = nullptr;
-    CUDA_TRY(cudaMalloc(&d_items, n * sizeof(RescoreItem)));
-    if (cudaMalloc(&d_x, n * sizeof(double)) != cudaSuccess) {
-        cudaFree(d_items);
+    CUDA_TRY(dev_alloc(&d_items, n * sizeof(RescoreItem)));
+    if (dev_alloc(&d_x, n * sizeof(double)) != cudaSuccess) {
+        dev_free(d_items);
         return fail(CRP_ERR_NOMEM, "cudaMalloc failed");
     }
     int rc = 0;
@@ -597,8 +644,8 @@ int crp_rescore(const crp_genome *g, uint64_t n, const uint32_t *segment, const 
             break;
         }
     } while (0);
-    cudaFree(d_items);
-    cudaFree(d_x);
+    dev_free(d_items);
+    dev_free(d_x);
     return rc;
 }
 
