@@ -26,7 +26,7 @@
 
 #define CRP_ABI_VERSION 2
 
-static constexpr size_t kScanSmemFixed = 2 * (size_t)kRecBytes + 2 * (size_t)kListCap * sizeof(uint16_t);
+static constexpr size_t kScanSmemFixed = (size_t)kStages * kRecBytes + 2 * (size_t)kListCap * sizeof(uint16_t);
 
 // ------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -83,9 +83,9 @@ struct crp_result {
     uint32_t *pos[2] = {nullptr, nullptr};
     unsigned long long *packed[2] = {nullptr, nullptr};
     double *x[2] = {nullptr, nullptr};
-    unsigned char *state = nullptr;            // tile_pref | tile_incl | cta_tot | tickets, one allocation
-    size_t state_bytes = 0;
-    unsigned long long *d_counts = nullptr;    // [2*n_seg]
+    unsigned char *state = nullptr;            // warp_pref | cta_tot | segment counts | tickets, one allocation
+    size_t state_bytes = 0, zero_offset = 0;   // segment counts and tickets start at zero_offset
+    unsigned long long *d_counts = nullptr;    // [2*n_seg], inside state
     std::vector<uint64_t> seg_plus, seg_minus;
     float ms_scan = 0.f;
 };
@@ -129,6 +129,13 @@ int crp_abi_version(void) { return CRP_ABI_VERSION; }
 int crp_tile_size(void) { return kTile; }
 
 const char *crp_last_error(void) { return g_err; }
+
+/* debug only (not part of the public header): device buffer of 8 x u64 per CTA, or NULL */
+int crp_debug_set_times(void *dev_ptr) {
+    unsigned long long *p = (unsigned long long *)dev_ptr;
+    CUDA_TRY(cudaMemcpyToSymbol(g_dbg_times, &p, sizeof p));
+    return 0;
+}
 
 int crp_device_count(int *count) {
     if (!count) return fail(CRP_ERR_ARG, "count is NULL");
@@ -251,8 +258,8 @@ int crp_genome_commit(crp_genome *g) {
     // ---- layout: every segment owns whole tile records; the bytes it needs (its positions
     // plus 32 of context each side) go to an ASCII staging buffer, 16-byte aligned per segment
     std::vector<PackDesc> descs;
-    std::vector<uint32_t> seg_first, seg_count;
     std::vector<uint64_t> seg_ascii;
+    std::vector<uint32_t> seg_first, seg_count;
     uint64_t ascii_bytes = 0;
     g->n_positions = 0;
     for (size_t si = 0; si < g->segs.size(); ++si) {
@@ -442,29 +449,23 @@ static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p, in
     a.packed_minus = r->packed[1];
     a.x_plus = r->x[0];
     a.x_minus = r->x[1];
+    const uint32_t n_seg = (uint32_t)g->segs.size();
     unsigned long long *s64 = reinterpret_cast<unsigned long long *>(r->state);
-    a.tile_pref = s64;
-    a.tile_incl = s64 + g->n_tiles;
-    a.cta_tot = s64 + 2 * (size_t)g->n_tiles;
-    a.tickets = reinterpret_cast<unsigned int *>(s64 + 2 * (size_t)g->n_tiles + 2 * (size_t)p.grid);
+    a.warp_pref = s64;
+    a.cta_tot = s64 + (size_t)g->n_tiles * kPrefWords;
+    a.seg_counts = r->d_counts;
+    a.tickets = reinterpret_cast<unsigned int *>(r->d_counts + 2 * (size_t)n_seg);
+    a.n_seg = n_seg;
+    a.seg_first_tile = g->d_seg_first;
+    a.seg_tile_count = g->d_seg_count;
     CUDA_TRY(cudaEventRecord(e0, st));
     if (g->n_tiles) {
-        CUDA_TRY(cudaMemsetAsync(r->state, 0, r->state_bytes, st));
         void *params[] = {(void *)&a};
         CUDA_TRY(cudaLaunchCooperativeKernel(p.fn, dim3(p.grid), dim3(kThreads), params, p.smem, st));
         g_ctx.launches++;
         CUDA_TRY(cudaGetLastError());
-    }
-    const uint32_t n_seg = (uint32_t)g->segs.size();
-    if (n_seg) {
-        if (g->n_tiles) {
-            k_segment_counts<<<(n_seg + 127) / 128, 128, 0, st>>>(a.tile_incl, g->d_seg_first, g->d_seg_count, n_seg,
-                                                                 r->d_counts);
-            g_ctx.launches++;
-            CUDA_TRY(cudaGetLastError());
-        } else {
-            CUDA_TRY(cudaMemsetAsync(r->d_counts, 0, 2 * (size_t)n_seg * sizeof(unsigned long long), st));
-        }
+    } else if (n_seg) {
+        CUDA_TRY(cudaMemsetAsync(r->d_counts, 0, 2 * (size_t)n_seg * sizeof(unsigned long long), st));
     }
     CUDA_TRY(cudaEventRecord(e1, st));
     return 0;
@@ -494,11 +495,12 @@ int crp_scan_score(crp_genome *g, int guide_len, uint32_t flags, crp_result **re
     ScanPlan plan = {};
     if ((rc = plan_scan(g, r->scored, &plan))) return bail(rc);
     tr.lap("plan");
-    r->state_bytes = (2 * (size_t)g->n_tiles + 2 * (size_t)plan.grid) * sizeof(unsigned long long) +
-                     ((size_t)plan.n_waves + 1) * sizeof(unsigned int);
-    if (dev_alloc(&r->state, r->state_bytes) != cudaSuccess ||
-        dev_alloc(&r->d_counts, (2 * (size_t)n_seg + 1) * sizeof(unsigned long long)) != cudaSuccess)
+    r->zero_offset = ((size_t)g->n_tiles * kPrefWords + 2 * (size_t)plan.grid) * sizeof(unsigned long long);
+    r->state_bytes = r->zero_offset + 2 * (size_t)n_seg * sizeof(unsigned long long) +
+                     ((size_t)plan.n_waves + 2) * sizeof(unsigned int);
+    if (dev_alloc(&r->state, r->state_bytes) != cudaSuccess)
         return bail(fail(CRP_ERR_NOMEM, "cudaMalloc of scan state failed"));
+    r->d_counts = reinterpret_cast<unsigned long long *>(r->state + r->zero_offset);
     if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)
         return bail(fail(CRP_ERR_CUDA, "cudaEventCreate failed"));
     // First guess of the per-strand capacity: 1/8 candidate per position (GC 70 %
@@ -596,7 +598,6 @@ int crp_result_free(crp_result *r) {
     if (!r) return 0;
     free_streams(r);
     dev_free(r->state);
-    dev_free(r->d_counts);
     delete r;
     return 0;
 }

@@ -133,7 +133,7 @@ def main():
     emit("// table slot of a set of matching entries = ((sum over groups of umulhi(x_g, magic_hi) + x_g * magic_lo) >> 3) & (2^bits - 1)")
     emit("struct Rs1Lane { const char *name; int lane_base; int n_entries; int n_table; int bits; int offset; "
          "int n_groups; Rs1Group groups[4]; Rs1Entry entries[16]; };")
-    descs, code, offset = [], [], 0
+    descs, code, offset, consts = [], [], 0, []
     mask_name = {0: "mA", 1: "mT", 2: "mC", 3: "mG"}
     next_name = {0: "nA", 1: "nT", 2: "nC", 3: "nG"}
     for li, (name, base, entries) in enumerate(lanes()):
@@ -159,9 +159,15 @@ def main():
             assert p >= 20, "tail entry below bit 20: extend the generator with a shift"
             e = 1 << (p - 20)
             cond = f"{mask_name[c1]} & {next_name[base]} & 0x{1 << p:x}u" if second else f"{mask_name[base]} & 0x{1 << p:x}u"
-            code.append(f"    {name} = RS1_FMA_BIT({cond}, {hexf(v * 2.0 ** (1023 - e))}, {name});   // {v!r} * 2^{1023 - e}")
+            code.append(f"    {name} = RS1_FMA_BIT({cond}, RS1_K({len(consts)}), {name});   // {v!r} * 2^{1023 - e}")
+            consts.append(hexf(v * 2.0 ** (1023 - e)))
         offset += 1 << bits
     emit(f"#define RS1_TABLE_DOUBLES {offset}")
+    emit("// pre-scaled tail weights, then intercept and low_gc: kept in a __constant__ array so that DFMA / DADD")
+    emit("// read them as constant-bank operands (64-bit immediates would cost two UMOV each)")
+    emit(f"#define RS1_K_INTERCEPT {len(consts)}")
+    emit(f"#define RS1_K_LOW_GC {len(consts) + 1}")
+    emit("#define RS1_K_VALUES { " + ", ".join(consts + ["RS1_INTERCEPT", "RS1_LOW_GC"]) + " }")
     emit("static const Rs1Lane kRs1Lanes[8] = {")
     emit(",\n".join(descs))
     emit("};")

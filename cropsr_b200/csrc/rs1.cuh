@@ -25,6 +25,9 @@ static constexpr size_t kRs1TableBytes = (size_t)RS1_TABLE_DOUBLES * sizeof(doub
 // table of exact sequential fp64 sums (built on the host at crp_init, staged in shared
 // memory; rs1_weights.inc).  s0/s1: planar code bits of the scored 30-mer (bit q = base q),
 // valid: bases that score.
+__constant__ double c_rs1_k[] = RS1_K_VALUES;
+#define RS1_K(i) c_rs1_k[i]
+
 // lane table entry at a byte offset that is already a multiple of 8 (see gen_rs1_inc.py)
 #define RS1_LD(T, lane_off, byte_idx) (*reinterpret_cast<const double *>(reinterpret_cast<const char *>(T) + (lane_off) + (byte_idx)))
 // acc + w iff the match bit is set, as ONE DFMA: bit (a single bit p >= 20 of a class mask)
@@ -38,7 +41,7 @@ __device__ __forceinline__ double rs1_canonical(const double *__restrict__ T, ui
     const double first = __dadd_rn(__dadd_rn(fA, fC), __dadd_rn(fT, fG));
     const double second = __dadd_rn(__dadd_rn(dA, dC), __dadd_rn(dT, dG));
     // (score_first + score_second + intersect + low_gc) * -1, CROPSR.py:312
-    return -__dadd_rn(__dadd_rn(__dadd_rn(first, second), RS1_INTERCEPT), RS1_LOW_GC);
+    return -__dadd_rn(__dadd_rn(__dadd_rn(first, second), RS1_K(RS1_K_INTERCEPT)), RS1_K(RS1_K_LOW_GC));
 }
 
 // Host side: exact sequential sums of every valid subset of each lane's table entries.

@@ -37,7 +37,10 @@ static constexpr int kTileWords = 2 * kThreads;            // every thread owns 
 static constexpr int kTile = kTileWords * 32;              // 16384 positions
 static constexpr int kRecWords = kTileWords + 3;           // descriptor + halo + tile + halo
 static constexpr uint32_t kRecBytes = kRecWords * 16;      // 8240, one bulk copy
-static constexpr int kListCap = 1024;                      // hits per strand compacted per batch
+static constexpr int kStages = 2;                          // staged tiles per CTA
+static constexpr int kListCap = 1024;                      // hits per strand of a tile compacted in one go
+static constexpr int kPrefWords = 10;                      // per tile: 8 warp prefixes, tile total, pad (80 B, one bulk copy)
+static constexpr uint32_t kNoTile = 0xFFFFFFFFu;
 static constexpr int kMaxRange = 32;                       // tiles per CTA per wave in the count phase
 static constexpr uint32_t kAlign = 128;                    // positions; segment placement granularity
 
@@ -132,15 +135,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-// One bulk copy global -> shared, completion counted in bytes on the mbarrier (TMA).
-__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
-    const uint32_t b = smem_u32(bar);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(b)
-                 : "memory");
-}
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
     const uint32_t b = smem_u32(bar);
     asm volatile(
@@ -166,17 +160,18 @@ __device__ __forceinline__ uint32_t range_mask(int32_t t0, int32_t lo, int32_t h
 }
 
 struct Hits {
-    uint32_t pA, mA, pB, mB;   // '+' / '-' hit masks of word tid (A) and word tid + 256 (B)
+    uint32_t pA, mA, pB, mB;   // '+' / '-' hit masks of the lane's two words (A: first half of the warp chunk, B: second)
 };
 
-// PAM tests and bounds of one staged tile for this thread's two words.
+// PAM tests and bounds of this lane's two words of a staged tile.  Warp w owns the 64 words
+// [64w, 64w + 64) of the tile (2048 positions); lane l owns words 64w + l (A) and 64w + 32 + l (B).
 //   '+': (?=.GG) at t  <=>  tok[t+1]==tok[t+2]=='G'            (CROPSR.py:415)
 //   '-': (?=CC.) at t  <=>  tok[t]==tok[t+1]=='C' and t+2 < L  (CROPSR.py:426)
 //   bounds (CROPSR.py:419 / :430): '+' t >= l+5;  '-' 2 <= t <= L-l+7
 //   plus ownership: t inside the n positions of the tile that the segment owns.
 // All positions fit int32: L < 2^31 - 2^15 (crp_genome_add_segment), 1 <= l <= 10^6.
-__device__ __forceinline__ Hits tile_hits(const uint4 *__restrict__ rec, const TileDesc td, int l, int tid) {
-    const uint4 a = rec[2 + tid], an = rec[3 + tid], b = rec[2 + kThreads + tid], bn = rec[3 + kThreads + tid];
+__device__ __forceinline__ Hits tile_hits(const uint4 *__restrict__ rec, const TileDesc td, int l, int wordA) {
+    const uint4 a = rec[2 + wordA], an = rec[3 + wordA], b = rec[34 + wordA], bn = rec[35 + wordA];
     const uint32_t uA = ~(a.z | a.w), uAn = ~(an.z | an.w), uB = ~(b.z | b.w), uBn = ~(bn.z | bn.w);   // upper-case ACGT
     const uint32_t gA = a.x & a.y & uA, gAn = an.x & an.y & uAn, gB = b.x & b.y & uB, gBn = bn.x & bn.y & uBn;
     const uint32_t cA = ~a.x & a.y & uA, cAn = ~an.x & an.y & uAn, cB = ~b.x & b.y & uB, cBn = ~bn.x & bn.y & uBn;
@@ -190,7 +185,7 @@ __device__ __forceinline__ Hits tile_hits(const uint4 *__restrict__ rec, const T
     const int32_t hi_p = min(L - 3, last_owned);
     const int32_t hi_m = min(L - l + 7, hi_p);
     if (t0 < l + 5 || t0 + kTile - 1 > hi_m) {   // edge tiles only
-        const int32_t tA = t0 + 32 * tid, tB = tA + 32 * kThreads;
+        const int32_t tA = t0 + 32 * wordA, tB = tA + 32 * 32;
         h.pA &= range_mask(tA, l + 5, hi_p);
         h.pB &= range_mask(tB, l + 5, hi_p);
         h.mA &= range_mask(tA, 2, hi_m);
@@ -210,12 +205,25 @@ struct ScanArgs {
     uint32_t *pos_plus, *pos_minus;
     unsigned long long *packed_plus, *packed_minus;
     double *x_plus, *x_minus;
-    // scan state, zeroed before the launch.  Counts are (plus << 32) | minus.
-    unsigned long long *tile_pref;   // [n_tiles] exclusive prefix of a tile inside its count range
-    unsigned long long *tile_incl;   // [n_tiles] inclusive global prefix (written by the emit phase)
+    // scan state; nothing needs initialising before the launch.  Counts are (plus << 32) | minus.
+    unsigned long long *warp_pref;   // [n_tiles][kPrefWords] exclusive prefix of every warp chunk inside its count range, then the tile total
     unsigned long long *cta_tot;     // [2][gridDim.x] range totals, double-buffered by wave parity
-    unsigned int *tickets;           // [n_waves] emit-phase tile dispensers
+    unsigned int *tickets;           // [n_waves] emit-phase dispensers of the dynamic tiles
+    unsigned long long *seg_counts;  // [2 * n_seg] out: plus[0..n_seg) then minus[0..n_seg)
+    const uint32_t *seg_first_tile, *seg_tile_count;   // [n_seg]
+    uint32_t n_seg;
 };
+
+// optional phase timeline (tools/phase_timeline.py): 8 x u64 per CTA, or NULL
+__device__ unsigned long long *g_dbg_times = nullptr;
+__device__ __forceinline__ void dbg_stamp(int slot) {
+    unsigned long long *p = g_dbg_times;
+    if (p && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p[8ull * blockIdx.x + slot] = t;
+    }
+}
 
 struct Window {
     uint32_t s0, s1, valid;              // planar codes / scoring mask of the 30-mer, output order
@@ -257,7 +265,7 @@ __device__ __forceinline__ unsigned long long unpack_counts(uint32_t c) {   // (
     return ((unsigned long long)(c & 0xFFFFu) << 32) | (c >> 16);
 }
 
-// hits of one word into the compacted list, highest position first.  end = one past the
+// hits of one word into the warp's compacted list, highest position first.  end = one past the
 // slot of the word's last hit.
 __device__ __forceinline__ void list_hits(uint16_t *__restrict__ end, uint32_t m, uint32_t pos0) {
     while (m) {
@@ -278,16 +286,16 @@ __device__ __forceinline__ void list_hits_window(uint16_t *__restrict__ list, ui
     }
 }
 
-// one thread per listed hit of one strand: window, score, coalesced stores
+// one thread per listed hit of one strand of a tile: window, score, coalesced stores
 template <bool kScore, bool kMinus>
 __device__ __forceinline__ void emit_strand(const ScanArgs &a, const double *__restrict__ tab,
                                             const uint4 *__restrict__ rec, const uint16_t *__restrict__ list,
                                             uint32_t count, uint64_t out0, uint32_t t_start, uint32_t L, uint32_t slot) {
+    if (out0 >= a.capacity) return;
+    if (count > a.capacity - out0) count = (uint32_t)(a.capacity - out0);
     uint32_t *const pos = (kMinus ? a.pos_minus : a.pos_plus) + out0;
     unsigned long long *const packed = (kMinus ? a.packed_minus : a.packed_plus) + out0;
     double *const xs = (kMinus ? a.x_minus : a.x_plus) + out0;
-    if (out0 >= a.capacity) return;
-    if (count > a.capacity - out0) count = (uint32_t)(a.capacity - out0);
     for (uint32_t i = slot; i < count; i += kThreads) {
         const uint32_t pl = list[i], t = t_start + pl;
         __stcs(pos + i, t);
@@ -301,86 +309,159 @@ __device__ __forceinline__ void emit_strand(const ScanArgs &a, const double *__r
     }
 }
 
+// Ring of staged tiles of a CTA.  full[s] completes when the bulk copies of slot s (the tile
+// record and, in the emit phase, the tile's prefix block) have landed.
+struct __align__(16) Ring {
+    unsigned long long pref[kStages][kPrefWords];   // bulk-copy destination (emit phase)
+    unsigned long long full[kStages];               // mbarriers
+    unsigned long long rbase[kStages];              // global prefix of the count range of the staged tile (emit phase)
+    uint32_t tile[kStages];                         // staged tile, or kNoTile: the sequence has ended
+    uint32_t done[kStages];                         // warps finished with the slot (count phase)
+};
+
+__device__ __forceinline__ void mbar_inval(unsigned long long *bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// (re)arm the ring at the start of a phase; every thread of the CTA calls it
+__device__ __forceinline__ void ring_reset(Ring &ring, bool first) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            if (!first) mbar_inval(&ring.full[s]);
+            mbar_init(&ring.full[s], 1);
+            ring.done[s] = 0;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+
 template <bool kScore>
 __global__ void __launch_bounds__(kThreads, CRP_CTAS_PER_SM)
 k_scan_score(const ScanArgs a) {
-    // dynamic shared memory: [stage 0][stage 1][hit lists][range prefixes]
+    // dynamic shared memory: [stages][hit lists][range prefixes]
     extern __shared__ __align__(128) unsigned char s_dyn[];
-    auto stage = [&](int b) { return reinterpret_cast<uint4 *>(s_dyn + (size_t)b * kRecBytes); };
-    uint16_t *const s_list = reinterpret_cast<uint16_t *>(s_dyn + 2 * kRecBytes);
+    auto stage = [&](int s) { return reinterpret_cast<uint4 *>(s_dyn + (size_t)s * kRecBytes); };
+    uint16_t *const s_list = reinterpret_cast<uint16_t *>(s_dyn + kStages * kRecBytes);
     unsigned long long *const s_rangepref =
-        reinterpret_cast<unsigned long long *>(s_dyn + 2 * kRecBytes + 2 * kListCap * sizeof(uint16_t));
+        reinterpret_cast<unsigned long long *>(s_dyn + kStages * kRecBytes + 2 * (size_t)kListCap * sizeof(uint16_t));
     __shared__ __align__(16) double s_tab[kScore ? RS1_TABLE_DOUBLES : 1];   // static: LDS takes the table offset as an immediate
-    __shared__ __align__(8) unsigned long long s_bar[2];
+    __shared__ Ring ring;
     __shared__ uint32_t s_cnt[kMaxRange][kWarps];
-    __shared__ uint2 s_wt[kWarps];
     __shared__ unsigned long long s_scan[kWarps];
-    __shared__ unsigned long long s_base[2];     // output offsets (plus << 32 | minus) of the tile staged in buffer b
-    __shared__ uint32_t s_next;
 
     cg::grid_group grid = cg::this_grid();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int l = a.guide_len;
     const uint32_t G = gridDim.x, cta = blockIdx.x;
-    uint32_t phase = 0;     // bit b: parity of the next completion of stage b's mbarrier
 
+    dbg_stamp(0);
+    // the lane tables arrive by bulk copy while the first count phase runs
+    __shared__ __align__(8) unsigned long long s_tabbar;
     if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        mbar_init(&s_tabbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (kScore) {
+            mbar_expect(&s_tabbar, (uint32_t)kRs1TableBytes);
+            bulk_copy(s_tab, a.tables, (uint32_t)kRs1TableBytes, &s_tabbar);
+        }
     }
-    if (kScore)
-        for (int i = tid; i < RS1_TABLE_DOUBLES; i += kThreads) s_tab[i] = a.tables[i];
-    __syncthreads();
 
     auto record = [&](uint32_t tile) { return a.records + (size_t)tile * kRecWords; };
-    auto wait_stage = [&](int b) {
-        mbar_wait(&s_bar[b], (phase >> b) & 1u);
-        phase ^= 1u << b;
+    // warp-level: count this warp done with slot s; true on the lane that must refill the slot
+    auto release_slot = [&](int s) -> bool {
+        __syncwarp();
+        bool refill = false;
+        if (lane == 0) {
+            refill = atomicAdd(&ring.done[s], 1u) == (uint32_t)kWarps - 1u;
+            if (refill) ring.done[s] = 0;
+        }
+        return refill;
     };
 
     unsigned long long wave_base = 0;
     uint32_t wave = 0;
     for (uint32_t w_lo = 0; w_lo < a.n_tiles; w_lo += a.wave_tiles, ++wave) {
         const uint32_t w_hi = min(a.n_tiles, w_lo + a.wave_tiles);
-        const uint32_t k = (w_hi - w_lo + G - 1) / G;              // tiles per count range (<= kMaxRange)
+        const uint32_t nt = w_hi - w_lo;
+        const uint32_t k = (nt + G - 1) / G;                       // tiles per count range (<= kMaxRange)
 
-        // ================================================= count phase: tiles [r_lo, r_hi)
-        const uint32_t r_lo = min(w_hi, w_lo + cta * k), r_hi = min(w_hi, r_lo + k);
-        const uint32_t n_mine = r_hi - r_lo;
-        if (tid == 0) {
-            if (n_mine > 0) bulk_load(stage(0), record(r_lo), kRecBytes, &s_bar[0]);
-            if (n_mine > 1) bulk_load(stage(1), record(r_lo + 1), kRecBytes, &s_bar[1]);
-        }
-        for (uint32_t j = 0; j < n_mine; ++j) {
-            const int b = j & 1;
-            wait_stage(b);
-            const uint4 d = stage(b)[0];
+        // ================================================= count phase: tiles [r_lo, r_lo + n_mine)
+        const uint32_t r_lo = min(w_hi, w_lo + cta * k), n_mine = min(w_hi, r_lo + k) - r_lo;
+        auto produce_count = [&](uint32_t n, int s) {
+            if (n < n_mine) {
+                ring.tile[s] = r_lo + n;
+                mbar_expect(&ring.full[s], kRecBytes);
+                bulk_copy(stage(s), record(r_lo + n), kRecBytes, &ring.full[s]);
+            } else {
+                ring.tile[s] = kNoTile;
+                mbar_arrive(&ring.full[s]);
+            }
+        };
+        if (cta == 0 && tid == 0) a.tickets[wave] = 0;             // read after the grid barrier
+        ring_reset(ring, wave == 0);
+        dbg_stamp(1);
+        if (tid == 0)
+            for (int s = 0; s < kStages; ++s) produce_count(s, s);
+        for (uint32_t n = 0;; ++n) {
+            const int s = n % kStages;
+            mbar_wait(&ring.full[s], (n / kStages) & 1u);
+            if (ring.tile[s] == kNoTile) break;
+            const uint4 *rec = stage(s);
+            const uint4 d = rec[0];
             const TileDesc td = {d.x, d.y, d.z, d.w};
-            const Hits h = tile_hits(stage(b), td, l, tid);
+            const Hits h = tile_hits(rec, td, l, 64 * warp + lane);
             uint32_t c = (__popc(h.pA) + __popc(h.pB)) | ((__popc(h.mA) + __popc(h.mB)) << 16);
             c = __reduce_add_sync(0xFFFFFFFFu, c);
-            if (lane == 0) s_cnt[j][warp] = c;
-            __syncthreads();                                   // stage b is free again
-            if (tid == 0 && j + 2 < n_mine) bulk_load(stage(b), record(r_lo + j + 2), kRecBytes, &s_bar[b]);
+            if (lane == 0) {
+                s_cnt[n][warp] = c;
+            }
+            if (release_slot(s)) produce_count(n + kStages, s);
         }
         __syncthreads();
-        if (warp == 0) {
-            unsigned long long tot = 0;
-            if ((uint32_t)lane < n_mine) {
-#pragma unroll
-                for (int q = 0; q < kWarps; ++q) tot += unpack_counts(s_cnt[lane][q]);
-            }
-            unsigned long long incl = tot;
+        {   // exclusive scan over the (tile, warp) counts of the range: thread tid owns tile tid / 8, warp tid % 8
+            const uint32_t j = tid / kWarps, wq = tid % kWarps;
+            const unsigned long long mine = j < n_mine ? unpack_counts(s_cnt[j][wq]) : 0ull;
+            unsigned long long incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
                 if (lane >= o) incl += v;
             }
-            if ((uint32_t)lane < n_mine) a.tile_pref[r_lo + lane] = incl - tot;
-            if (lane == 31) a.cta_tot[(wave & 1u) * G + cta] = incl;
+            if (lane == 31) s_scan[warp] = incl;
+            __syncthreads();
+            unsigned long long before = 0, total = 0;
+#pragma unroll
+            for (int q = 0; q < kWarps; ++q) {
+                const unsigned long long x = s_scan[q];
+                if (q < warp) before += x;
+                total += x;
+            }
+            if (j < n_mine) {
+                unsigned long long *pf = a.warp_pref + (size_t)(r_lo + j) * kPrefWords;
+                pf[wq] = before + incl - mine;
+                if (wq == kWarps - 1) pf[kWarps] = before + incl;      // prefix at the end of the tile
+                asm volatile("fence.proxy.async.global;" ::: "memory");   // read back by bulk copies after the grid barrier
+            }
+            if (tid == 0) a.cta_tot[(wave & 1u) * G + cta] = total;
         }
+        dbg_stamp(2);
         grid.sync();
+        dbg_stamp(3);
 
         // ================================================= exclusive scan of the range totals
         unsigned long long wave_total;
@@ -415,33 +496,70 @@ k_scan_score(const ScanArgs a) {
                 run += v[q];
             }
             wave_total = total;
-            __syncthreads();
         }
 
-        // ================================================= emit phase: dynamic tiles of the wave
+        // ================================================= emit phase
+        // The first ns * G tiles of the wave are dealt round-robin (tile known without a
+        // round trip); the rest go through the ticket counter, which evens out what the
+        // data-dependent emit work left unbalanced.
+        const uint32_t ns = (uint32_t)((unsigned long long)nt * 3 / 4 / G);
+        const uint32_t dyn_lo = w_lo + ns * G, n_dyn = w_hi - dyn_lo;
         unsigned int *const ticket = a.tickets + wave;
-        if (tid == 0) {
-            const uint32_t t0 = w_lo + atomicAdd(ticket, 1u);
-            s_next = t0;
-            if (t0 < w_hi) {
-                bulk_load(stage(0), record(t0), kRecBytes, &s_bar[0]);
-                s_base[0] = s_rangepref[(t0 - w_lo) / k] + a.tile_pref[t0];
+        auto produce_emit = [&](uint32_t n, int s) {     // one thread: stage tile number n of this CTA into slot s
+            uint32_t t;
+            if (n < ns) {
+                t = w_lo + n * G + cta;
+            } else {
+                const uint32_t q = atomicAdd(ticket, 1u);
+                t = q < n_dyn ? dyn_lo + q : kNoTile;
             }
+            ring.tile[s] = t;
+            if (t != kNoTile) {
+                ring.rbase[s] = s_rangepref[(t - w_lo) / k];
+                mbar_expect(&ring.full[s], kRecBytes + kPrefWords * 8);
+                bulk_copy(stage(s), record(t), kRecBytes, &ring.full[s]);
+                bulk_copy(ring.pref[s], a.warp_pref + (size_t)t * kPrefWords, kPrefWords * 8, &ring.full[s]);
+            } else {
+                mbar_arrive(&ring.full[s]);
+            }
+        };
+        ring_reset(ring, false);                                   // also publishes s_rangepref
+        dbg_stamp(4);
+        if (kScore && wave == 0) mbar_wait(&s_tabbar, 0);
+        // per-segment candidate counts of this wave: prefix at the end of the segment's last
+        // tile minus prefix at the start of its first one (segments are dealt to threads)
+        for (uint32_t sg = cta * kThreads + tid; sg < a.n_seg; sg += G * kThreads) {
+            const uint32_t f = a.seg_first_tile[sg], c = a.seg_tile_count[sg];
+            const uint32_t lo_t = max(f, w_lo), hi_t = min(f + c, w_hi);       // tiles of the segment in this wave
+            unsigned long long cnt = 0;
+            if (lo_t < hi_t)
+                cnt = s_rangepref[(hi_t - 1 - w_lo) / k] + a.warp_pref[(size_t)(hi_t - 1) * kPrefWords + kWarps] -
+                      (s_rangepref[(lo_t - w_lo) / k] + a.warp_pref[(size_t)lo_t * kPrefWords]);
+            const unsigned long long plus = cnt >> 32, minus = cnt & 0xFFFFFFFFull;
+            a.seg_counts[sg] = (wave ? a.seg_counts[sg] : 0ull) + plus;
+            a.seg_counts[a.n_seg + sg] = (wave ? a.seg_counts[a.n_seg + sg] : 0ull) + minus;
         }
-        __syncthreads();
-        uint32_t tile = s_next;
-        for (uint32_t it = 0; tile < w_hi; ++it) {
-            const int b = it & 1;
-            // the next tile of this CTA: ticket now, its bulk copy lands while this tile is emitted
-            uint32_t claimed = 0;
-            unsigned long long claimed_pref = 0;
-            if (tid == 0) claimed = w_lo + atomicAdd(ticket, 1u);
-            wait_stage(b);
-            const uint4 *rec = stage(b);
+        if (tid == 0) produce_emit(0, 0);
+        uint16_t *const list_p = s_list, *const list_m = s_list + kListCap;
+        for (uint32_t n = 0;; ++n) {
+            const int s = n % kStages;
+            // next tile of this CTA: its copies land while this tile is emitted (slot s^1 was
+            // released by the barrier that ended tile n - 1)
+            if (tid == 0) produce_emit(n + 1, s ^ 1);
+            mbar_wait(&ring.full[s], (n / kStages) & 1u);
+            if (ring.tile[s] == kNoTile) break;
+            const uint4 *rec = stage(s);
             const uint4 d = rec[0];
             const TileDesc td = {d.x, d.y, d.z, d.w};
-            const Hits h = tile_hits(rec, td, l, tid);
-            // ---- block scan of the per-word counts: all A words precede all B words
+            const unsigned long long tile_pref = ring.pref[s][0];
+            const unsigned long long base = ring.rbase[s] + tile_pref;
+            const unsigned long long off = ring.pref[s][warp] - tile_pref;          // hits of the tile before my warp chunk
+            const unsigned long long tot = ring.pref[s][kWarps] - tile_pref;
+            const uint32_t np = (uint32_t)(tot >> 32), nm = (uint32_t)tot;
+            const uint64_t base_p = base >> 32, base_m = base & 0xFFFFFFFFull;
+            const uint32_t wordA = 64 * warp + lane;
+            const Hits h = tile_hits(rec, td, l, wordA);
+            // ---- warp scan of the per-word counts: the A words of the chunk precede its B words
             const uint32_t cA = __popc(h.pA) | (__popc(h.mA) << 16), cB = __popc(h.pB) | (__popc(h.mB) << 16);
             uint32_t iA = cA, iB = cB;
 #pragma unroll
@@ -452,73 +570,38 @@ k_scan_score(const ScanArgs a) {
                     iB += vB;
                 }
             }
-            if (lane == 31) s_wt[warp] = make_uint2(iA, iB);
-            __syncthreads();
-            if (tid == 0) {                                    // the ticket has arrived by now: start the prefetch
-                s_next = claimed;
-                if (claimed < w_hi) {
-                    bulk_load(stage(b ^ 1), record(claimed), kRecBytes, &s_bar[b ^ 1]);
-                    claimed_pref = __ldg(a.tile_pref + claimed);   // consumed after the list is built
-                }
-            }
-            const uint2 wt = s_wt[lane & (kWarps - 1)];
-            const uint32_t totA = __reduce_add_sync(0xFFFFFFFFu, lane < kWarps ? wt.x : 0u);
-            const uint32_t totB = __reduce_add_sync(0xFFFFFFFFu, lane < kWarps ? wt.y : 0u);
-            const uint32_t preA = __reduce_add_sync(0xFFFFFFFFu, lane < warp ? wt.x : 0u);
-            const uint32_t preB = __reduce_add_sync(0xFFFFFFFFu, lane < warp ? wt.y : 0u);
-            const uint32_t np = (totA & 0xFFFFu) + (totB & 0xFFFFu), nm = (totA >> 16) + (totB >> 16);
+            const uint32_t totA = __shfl_sync(0xFFFFFFFFu, iA, 31);
             // rank (inside the tile, per strand) one past the last hit of my words
-            const uint32_t endA = preA + iA, endB = totA + preB + iB;
-            const uint32_t epA = endA & 0xFFFFu, emA = endA >> 16, epB = endB & 0xFFFFu, emB = endB >> 16;
-            const unsigned long long base = s_base[b];
-            const uint64_t base_p = base >> 32, base_m = base & 0xFFFFFFFFull;
-            if (tid == 0) a.tile_incl[tile] = base + (((unsigned long long)np << 32) | nm);
-
-            uint16_t *const list_p = s_list, *const list_m = s_list + kListCap;
+            const uint32_t endB = totA + iB;
+            const uint32_t op = (uint32_t)(off >> 32), om = (uint32_t)off;
+            const uint32_t epA = op + (iA & 0xFFFFu), emA = om + (iA >> 16), epB = op + (endB & 0xFFFFu), emB = om + (endB >> 16);
             if (np <= (uint32_t)kListCap && nm <= (uint32_t)kListCap) {
-                list_hits(list_p + epA, h.pA, 32u * tid);
-                list_hits(list_p + epB, h.pB, 32u * (kThreads + tid));
-                list_hits(list_m + emA, h.mA, 32u * tid);
-                list_hits(list_m + emB, h.mB, 32u * (kThreads + tid));
-                if (tid == 0 && claimed < w_hi) s_base[b ^ 1] = s_rangepref[(claimed - w_lo) / k] + claimed_pref;
+                list_hits(list_p + epA, h.pA, 32u * wordA);
+                list_hits(list_p + epB, h.pB, 32u * (wordA + 32));
+                list_hits(list_m + emA, h.mA, 32u * wordA);
+                list_hits(list_m + emB, h.mB, 32u * (wordA + 32));
                 __syncthreads();
                 emit_strand<kScore, false>(a, s_tab, rec, list_p, np, base_p, td.t_start, td.L, tid);
                 emit_strand<kScore, true>(a, s_tab, rec, list_m, nm, base_m, td.t_start, td.L, tid ^ (kThreads / 2));
-            } else {                                           // pathological density: batches of kListCap ranks
-                if (tid == 0 && claimed < w_hi) s_base[b ^ 1] = s_rangepref[(claimed - w_lo) / k] + claimed_pref;
+            } else {                                               // dense tile: windows of kListCap ranks
                 for (uint32_t lo = 0; lo < np || lo < nm; lo += kListCap) {
                     const uint32_t cp = np > lo ? min(np - lo, (uint32_t)kListCap) : 0u;
                     const uint32_t cm = nm > lo ? min(nm - lo, (uint32_t)kListCap) : 0u;
-                    if (lo) __syncthreads();                   // previous batch fully consumed
-                    list_hits_window(list_p, h.pA, epA, 32u * tid, lo);
-                    list_hits_window(list_p, h.pB, epB, 32u * (kThreads + tid), lo);
-                    list_hits_window(list_m, h.mA, emA, 32u * tid, lo);
-                    list_hits_window(list_m, h.mB, emB, 32u * (kThreads + tid), lo);
+                    if (lo) __syncthreads();
+                    list_hits_window(list_p, h.pA, epA, 32u * wordA, lo);
+                    list_hits_window(list_p, h.pB, epB, 32u * (wordA + 32), lo);
+                    list_hits_window(list_m, h.mA, emA, 32u * wordA, lo);
+                    list_hits_window(list_m, h.mB, emB, 32u * (wordA + 32), lo);
                     __syncthreads();
                     emit_strand<kScore, false>(a, s_tab, rec, list_p, cp, base_p + lo, td.t_start, td.L, tid);
                     emit_strand<kScore, true>(a, s_tab, rec, list_m, cm, base_m + lo, td.t_start, td.L, tid);
                 }
             }
-            __syncthreads();                                   // stage b, the lists, s_next and s_base are settled
-            tile = s_next;
+            __syncthreads();                                       // slot s and the lists are free again
         }
+        dbg_stamp(5);
         wave_base += wave_total;
     }
-}
-
-// per-segment counts from the inclusive tile prefixes
-__global__ void k_segment_counts(const unsigned long long *__restrict__ tile_incl,
-                                 const uint32_t *__restrict__ seg_first_tile,
-                                 const uint32_t *__restrict__ seg_tile_count, uint32_t n_seg,
-                                 unsigned long long *__restrict__ counts /* [2*n_seg] */) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_seg) return;
-    const uint32_t f = seg_first_tile[s], c = seg_tile_count[s];
-    unsigned long long end = 0, begin = 0;
-    if (f > 0) begin = tile_incl[f - 1];
-    end = c > 0 ? tile_incl[f + c - 1] : begin;
-    counts[s] = (end >> 32) - (begin >> 32);
-    counts[n_seg + s] = (end & 0xFFFFFFFFull) - (begin & 0xFFFFFFFFull);
 }
 
 struct RescoreItem {
