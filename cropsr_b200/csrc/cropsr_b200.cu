@@ -439,6 +439,8 @@ static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p, in
     a.records = g->records;
     a.n_tiles = g->n_tiles;
     a.wave_tiles = p.wave_tiles;
+    a.static_eighths = 4;
+    if (const char *e = getenv("CRP_STATIC_EIGHTHS")) a.static_eighths = (uint32_t)atoi(e) > 8 ? 8 : (uint32_t)atoi(e);
     a.guide_len = guide_len;
     a.flags = flags;
     a.tables = g_ctx.d_tables;

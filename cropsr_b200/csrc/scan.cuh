@@ -198,6 +198,7 @@ struct ScanArgs {
     const uint4 *records;            // n_tiles records of kRecWords words
     uint32_t n_tiles;
     uint32_t wave_tiles;             // tiles per wave (<= gridDim.x * kMaxRange)
+    uint32_t static_eighths;         // share of a wave's tiles dealt round-robin, in 1/8 (the rest are ticketed)
     int guide_len;
     uint32_t flags;
     const double *tables;            // RS1 lane tables (RS1_TABLE_DOUBLES doubles)
@@ -502,7 +503,7 @@ k_scan_score(const ScanArgs a) {
         // The first ns * G tiles of the wave are dealt round-robin (tile known without a
         // round trip); the rest go through the ticket counter, which evens out what the
         // data-dependent emit work left unbalanced.
-        const uint32_t ns = (uint32_t)((unsigned long long)nt * 3 / 4 / G);
+        const uint32_t ns = (uint32_t)((unsigned long long)nt * a.static_eighths / 8 / G);
         const uint32_t dyn_lo = w_lo + ns * G, n_dyn = w_hi - dyn_lo;
         unsigned int *const ticket = a.tickets + wave;
         auto produce_emit = [&](uint32_t n, int s) {     // one thread: stage tile number n of this CTA into slot s
