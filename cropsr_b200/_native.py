@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcropsr_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 CRP_SCAN_DEFAULT = 0
 CRP_SCAN_NO_SCORE = 1
@@ -24,6 +24,12 @@ CRP_CLASS_SINGLE = 2
 PACKED_IRREGULAR = 1 << 30
 PACKED_TRUNCATED = 1 << 31
 PACKED_UNSCORED = 1 << 62
+
+
+class SegmentDesc(C.Structure):
+    """crp_segment_desc"""
+    _fields_ = [("token_id", C.c_uint32), ("token", C.c_void_p), ("token_len", C.c_uint64),
+                ("begin", C.c_uint64), ("end", C.c_uint64)]
 
 
 class CropsrError(RuntimeError):
@@ -68,6 +74,9 @@ SIGNATURES = {
     "crp_result_device_counts": (C.c_int, [C.c_void_p, _vpp]),
     "crp_result_fetch": (C.c_int, [C.c_void_p, C.c_char, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crp_result_free": (C.c_int, [C.c_void_p]),
+    "crp_scan_segments": (C.c_int, [C.c_uint32, C.c_void_p, C.c_int, C.c_uint32, C.c_uint64,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, _f32p]),
     "crp_rescore": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crp_genome_timing": (C.c_int, [C.c_void_p, _f32p, _f32p]),
     "crp_result_timing": (C.c_int, [C.c_void_p, _f32p]),

@@ -15,6 +15,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/cropsr_b200.h"
@@ -24,7 +25,7 @@
 #endif
 #include "scan.cuh"
 
-#define CRP_ABI_VERSION 2
+#define CRP_ABI_VERSION 3
 
 static constexpr size_t kScanSmemFixed = (size_t)kStages * kRecBytes + 2 * (size_t)kListCap * sizeof(uint16_t);
 
@@ -51,6 +52,7 @@ struct Context {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t lanes[3] = {nullptr, nullptr, nullptr};   // crp_scan_segments pipeline
     uint64_t launches = 0;
     double *d_tables = nullptr;        // RS1 lane tables in device memory
 };
@@ -67,6 +69,8 @@ struct Segment {
 
 struct crp_genome {
     std::vector<Segment> segs;
+    cudaStream_t st = nullptr;         // every operation on this genome and its results is ordered on this stream
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // commit timing: start, H2D done, pack done
     bool committed = false;
     uint64_t n_positions = 0;          // owned positions
     uint4 *records = nullptr;          // n_tiles tile records (scan.cuh)
@@ -77,6 +81,11 @@ struct crp_genome {
 
 struct crp_result {
     const crp_genome *g = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};    // scan timing
+    unsigned long long *h_counts = nullptr;    // pinned, [2*n_seg]: counts land here when the scan has run
+    int guide_len = 0;
+    uint32_t flags = 0;
     uint64_t capacity = 0;
     uint64_t n_plus = 0, n_minus = 0;
     bool scored = false;
@@ -114,11 +123,32 @@ static int need_ctx() {
 // freed blocks (cudaMalloc / cudaFree cost 10-70 ms per call on a 180 GB part; a genome commit
 // and a scan allocate ~1 GB between them).
 template <typename T>
-static cudaError_t dev_alloc(T **ptr, size_t bytes) {
-    return cudaMallocAsync(reinterpret_cast<void **>(ptr), bytes ? bytes : 16, g_ctx.stream);
+static cudaError_t dev_alloc(T **ptr, size_t bytes, cudaStream_t st) {
+    return cudaMallocAsync(reinterpret_cast<void **>(ptr), bytes ? bytes : 16, st);
 }
-static void dev_free(void *ptr) {
-    if (ptr) cudaFreeAsync(ptr, g_ctx.stream);
+static void dev_free(void *ptr, cudaStream_t st) {
+    if (ptr) cudaFreeAsync(ptr, st);
+}
+
+// Small pinned host blocks (the per-scan counts) are recycled: cudaHostAlloc takes ~0.1 ms.
+static std::vector<std::pair<size_t, void *>> g_pinned_free;
+static void *pinned_get(size_t bytes) {
+    for (size_t i = 0; i < g_pinned_free.size(); ++i)
+        if (g_pinned_free[i].first >= bytes) {
+            void *p = g_pinned_free[i].second;
+            g_pinned_free.erase(g_pinned_free.begin() + i);
+            return p;
+        }
+    const size_t want = bytes < 4096 ? 4096 : bytes;
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, want + sizeof(size_t) * 2, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    *reinterpret_cast<size_t *>(p) = want;
+    return reinterpret_cast<char *>(p) + sizeof(size_t) * 2;
+}
+static void pinned_put(void *p) {
+    if (!p) return;
+    const size_t cap = *reinterpret_cast<size_t *>(reinterpret_cast<char *>(p) - sizeof(size_t) * 2);
+    g_pinned_free.emplace_back(cap, p);
 }
 
 // ------------------------------------------------------------------ C ABI
@@ -182,7 +212,11 @@ int crp_shutdown(void) {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, g_ctx.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
     }
+    for (auto &pf : g_pinned_free) cudaFreeHost(reinterpret_cast<char *>(pf.second) - sizeof(size_t) * 2);
+    g_pinned_free.clear();
     cudaStreamDestroy(g_ctx.stream);
+    for (cudaStream_t l : g_ctx.lanes)
+        if (l) cudaStreamDestroy(l);
     cudaFree(g_ctx.d_tables);
     g_ctx = Context();
     return 0;
@@ -205,6 +239,8 @@ int crp_host_free(void *ptr) {
     if (ptr) CUDA_TRY(cudaFreeHost(ptr));
     return 0;
 }
+
+static cudaStream_t stream_of(const crp_genome *g) { return g->st ? g->st : g_ctx.stream; }
 
 int crp_genome_new(crp_genome **g) {
     if (!g) return fail(CRP_ERR_ARG, "g is NULL");
@@ -248,27 +284,29 @@ int crp_genome_num_positions(const crp_genome *g, uint64_t *n) {
     return 0;
 }
 
-int crp_genome_commit(crp_genome *g) {
-    if (!g) return fail(CRP_ERR_ARG, "g is NULL");
-    if (int rc = need_ctx()) return rc;
-    if (g->committed) return fail(CRP_ERR_STATE, "genome already committed");
-    cudaStream_t st = g_ctx.stream;
-    Trace tr("commit");
-
+// Enqueue the whole ingest of a genome on its stream: H2D of the token bytes the segments need,
+// the pack kernel, release of the staging buffer.  Nothing here waits for the device.
+static int commit_enqueue(crp_genome *g) {
+    cudaStream_t st = stream_of(g);
     // ---- layout: every segment owns whole tile records; the bytes it needs (its positions
     // plus 32 of context each side) go to an ASCII staging buffer, 16-byte aligned per segment
+    const bool one = g->segs.size() == 1;      // single segment: descriptors by arithmetic, no uploads
     std::vector<PackDesc> descs;
     std::vector<uint64_t> seg_ascii;
     std::vector<uint32_t> seg_first, seg_count;
-    uint64_t ascii_bytes = 0;
+    uint64_t ascii_bytes = 0, n_tiles = 0;
     g->n_positions = 0;
     for (size_t si = 0; si < g->segs.size(); ++si) {
         Segment &s = g->segs[si];
         s.stage_begin = s.begin >= 32 ? s.begin - 32 : 0;
         s.stage_end = s.end + 32 < s.token_len ? s.end + 32 : s.token_len;
         seg_ascii.push_back(ascii_bytes);
-        s.first_tile = (uint32_t)descs.size();
-        for (uint64_t t = s.begin; t < s.end; t += kTile) {
+        s.first_tile = (uint32_t)n_tiles;
+        s.n_tiles = (uint32_t)((s.end - s.begin + kTile - 1) / kTile);
+        n_tiles += s.n_tiles;
+        if (n_tiles >= (1ull << 31)) return fail(CRP_ERR_RANGE, "shard has too many tiles");
+        for (uint32_t j = 0; j < (one ? (s.n_tiles ? 1u : 0u) : s.n_tiles); ++j) {
+            const uint64_t t = s.begin + (uint64_t)j * kTile;
             PackDesc pd;
             pd.ascii_off = ascii_bytes;
             pd.stage_begin = (uint32_t)s.stage_begin;
@@ -278,9 +316,7 @@ int crp_genome_commit(crp_genome *g) {
             pd.td.n = (uint32_t)((s.end - t) < (uint64_t)kTile ? (s.end - t) : (uint64_t)kTile);
             pd.td.segment = (uint32_t)si;
             descs.push_back(pd);
-            if (descs.size() >= (1ull << 31)) return fail(CRP_ERR_RANGE, "shard has too many tiles");
         }
-        s.n_tiles = (uint32_t)descs.size() - s.first_tile;
         seg_first.push_back(s.first_tile);
         seg_count.push_back(s.n_tiles);
         g->n_positions += s.end - s.begin;
@@ -289,65 +325,67 @@ int crp_genome_commit(crp_genome *g) {
     if (g->n_positions >= (1ull << 32))
         return fail(CRP_ERR_RANGE, "shard of %llu positions exceeds the 32-bit candidate count range",
                     (unsigned long long)g->n_positions);
-    g->n_tiles = (uint32_t)descs.size();
+    g->n_tiles = (uint32_t)n_tiles;
 
-    tr.lap("layout");
     uint8_t *d_ascii = nullptr;
     PackDesc *d_descs = nullptr;
-    auto cleanup = [&]() {
-        dev_free(d_ascii);
-        dev_free(d_descs);
-    };
     const size_t rec_bytes = (size_t)g->n_tiles * kRecBytes;
-    if (dev_alloc(&d_ascii, ascii_bytes + 64) != cudaSuccess || dev_alloc(&d_descs, (descs.size() + 1) * sizeof(PackDesc)) != cudaSuccess ||
-        dev_alloc(&g->records, rec_bytes + 16) != cudaSuccess) {
+    if (dev_alloc(&d_ascii, ascii_bytes + 64, st) != cudaSuccess ||
+        (!one && dev_alloc(&d_descs, (descs.size() + 1) * sizeof(PackDesc), st) != cudaSuccess) ||
+        dev_alloc(&g->records, rec_bytes + 16, st) != cudaSuccess) {
         cudaGetLastError();
-        cleanup();
+        dev_free(d_ascii, st);
+        dev_free(d_descs, st);
         return fail(CRP_ERR_NOMEM, "cudaMalloc of %llu record bytes + %llu staging bytes failed",
                     (unsigned long long)rec_bytes, (unsigned long long)ascii_bytes);
     }
-    tr.lap("cudaMalloc");
-    cudaEvent_t e0, e1, e2;
-    CUDA_TRY(cudaEventCreate(&e0));
-    CUDA_TRY(cudaEventCreate(&e1));
-    CUDA_TRY(cudaEventCreate(&e2));
-    CUDA_TRY(cudaEventRecord(e0, st));
+    for (int i = 0; i < 3; ++i)
+        if (!g->ev[i]) CUDA_TRY(cudaEventCreate(&g->ev[i]));
+    CUDA_TRY(cudaEventRecord(g->ev[0], st));
     for (size_t si = 0; si < g->segs.size(); ++si) {
         const Segment &s = g->segs[si];
         if (s.stage_end > s.stage_begin && s.n_tiles)
             CUDA_TRY(cudaMemcpyAsync(d_ascii + seg_ascii[si], s.token + s.stage_begin, s.stage_end - s.stage_begin,
                                      cudaMemcpyHostToDevice, st));
     }
-    if (!descs.empty())
+    if (!one && !descs.empty())
         CUDA_TRY(cudaMemcpyAsync(d_descs, descs.data(), descs.size() * sizeof(PackDesc), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaEventRecord(g->ev[1], st));
     const uint64_t n_items = (uint64_t)g->n_tiles * kRecWords;
     if (n_items) {
+        PackDesc first = descs[0];
+        if (one) first.td.n = (uint32_t)(g->segs[0].end - g->segs[0].begin);     // positions of the whole segment
         const uint64_t want = (n_items + 255) / 256, cap = (uint64_t)g_ctx.sm_count * 16;
-        k_pack<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(d_ascii, d_descs, n_items, g->records);
+        k_pack<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(d_ascii, d_descs, first, n_items, g->records);
         g_ctx.launches++;
         CUDA_TRY(cudaGetLastError());
     }
-    CUDA_TRY(cudaEventRecord(e2, st));
-    if (!g->segs.empty()) {
+    CUDA_TRY(cudaEventRecord(g->ev[2], st));
+    if (!one && !g->segs.empty()) {
         const size_t nb = g->segs.size() * sizeof(uint32_t);
-        CUDA_TRY(dev_alloc(&g->d_seg_first, nb));
-        CUDA_TRY(dev_alloc(&g->d_seg_count, nb));
+        CUDA_TRY(dev_alloc(&g->d_seg_first, nb, st));
+        CUDA_TRY(dev_alloc(&g->d_seg_count, nb, st));
         CUDA_TRY(cudaMemcpyAsync(g->d_seg_first, seg_first.data(), nb, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(g->d_seg_count, seg_count.data(), nb, cudaMemcpyHostToDevice, st));
     }
-    tr.lap("enqueue");
-    CUDA_TRY(cudaStreamSynchronize(st));
-    tr.lap("sync");
-    CUDA_TRY(cudaEventElapsedTime(&g->ms_h2d, e0, e1));
-    CUDA_TRY(cudaEventElapsedTime(&g->ms_pack, e1, e2));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaEventDestroy(e2);
-    cleanup();
-    tr.lap("cudaFree");
-    for (Segment &s : g->segs) s.token = nullptr;   // host tokens may be released now
+    dev_free(d_ascii, st);       // stream ordered: after the pack kernel
+    dev_free(d_descs, st);
     g->committed = true;
+    return 0;
+}
+
+int crp_genome_commit(crp_genome *g) {
+    if (!g) return fail(CRP_ERR_ARG, "g is NULL");
+    if (int rc = need_ctx()) return rc;
+    if (g->committed) return fail(CRP_ERR_STATE, "genome already committed");
+    Trace tr("commit");
+    if (int rc = commit_enqueue(g)) return rc;
+    tr.lap("enqueue");
+    CUDA_TRY(cudaStreamSynchronize(stream_of(g)));
+    tr.lap("sync");
+    CUDA_TRY(cudaEventElapsedTime(&g->ms_h2d, g->ev[0], g->ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(&g->ms_pack, g->ev[1], g->ev[2]));
+    for (Segment &s : g->segs) s.token = nullptr;   // host tokens may be released now
     return 0;
 }
 
@@ -360,18 +398,21 @@ int crp_genome_timing(const crp_genome *g, float *ms_h2d, float *ms_pack) {
 
 int crp_genome_free(crp_genome *g) {
     if (!g) return 0;
-    dev_free(g->records);
-    dev_free(g->d_seg_first);
-    dev_free(g->d_seg_count);
+    cudaStream_t st = stream_of(g);
+    dev_free(g->records, st);
+    dev_free(g->d_seg_first, st);
+    dev_free(g->d_seg_count, st);
+    for (cudaEvent_t e : g->ev)
+        if (e) cudaEventDestroy(e);
     delete g;
     return 0;
 }
 
 static void free_streams(crp_result *r) {
     for (int s = 0; s < 2; ++s) {
-        dev_free(r->pos[s]);
-        dev_free(r->packed[s]);
-        dev_free(r->x[s]);
+        dev_free(r->pos[s], r->st);
+        dev_free(r->packed[s], r->st);
+        dev_free(r->x[s], r->st);
         r->pos[s] = nullptr;
         r->packed[s] = nullptr;
         r->x[s] = nullptr;
@@ -382,10 +423,10 @@ static int alloc_streams(crp_result *r, uint64_t cap, bool scored) {
     r->capacity = cap;
     const uint64_t n = cap ? cap : 1;
     for (int s = 0; s < 2; ++s) {
-        if (dev_alloc(&r->pos[s], n * sizeof(uint32_t)) != cudaSuccess) goto oom;
+        if (dev_alloc(&r->pos[s], n * sizeof(uint32_t), r->st) != cudaSuccess) goto oom;
         if (scored) {
-            if (dev_alloc(&r->packed[s], n * sizeof(unsigned long long)) != cudaSuccess) goto oom;
-            if (dev_alloc(&r->x[s], n * sizeof(double)) != cudaSuccess) goto oom;
+            if (dev_alloc(&r->packed[s], n * sizeof(unsigned long long), r->st) != cudaSuccess) goto oom;
+            if (dev_alloc(&r->x[s], n * sizeof(double), r->st) != cudaSuccess) goto oom;
         }
     }
     return 0;
@@ -408,41 +449,41 @@ static int plan_scan(const crp_genome *g, bool scored, ScanPlan *p) {
     p->fn = scored ? (const void *)k_scan_score<true> : (const void *)k_scan_score<false>;
     const unsigned grid_max = (unsigned)g_ctx.sm_count * CRP_CTAS_PER_SM;
     p->smem = kScanSmemFixed + (size_t)grid_max * sizeof(unsigned long long);
-    int per_sm = 0;
-    CUDA_TRY(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p->fn, kThreads, p->smem));
-    if (per_sm < 1) return fail(CRP_ERR_CUDA, "scan kernel does not fit on an SM");
-    if (per_sm > CRP_CTAS_PER_SM) per_sm = CRP_CTAS_PER_SM;
+    static int per_sm_cache[2] = {0, 0};       // occupancy of the two instantiations, queried once
+    int &per_sm = per_sm_cache[scored ? 1 : 0];
+    if (per_sm == 0) {
+        CUDA_TRY(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p->fn, kThreads, p->smem));
+        if (per_sm < 1) return fail(CRP_ERR_CUDA, "scan kernel does not fit on an SM");
+        if (per_sm > CRP_CTAS_PER_SM) per_sm = CRP_CTAS_PER_SM;
+    }
     // persistent grid, every CTA resident (grid barrier between the count and emit phases)
     uint64_t grid = (uint64_t)g_ctx.sm_count * per_sm;
     if (grid > g->n_tiles) grid = g->n_tiles;
     if (grid < 1) grid = 1;
     p->grid = (unsigned)grid;
-    // Wave = the tiles counted, then emitted, between two grid barriers.  One wave while the
-    // records fit in L2 next to the output stream; ~50 MB of records per wave beyond that.
-    uint64_t wave = g->n_tiles <= 12288 ? g->n_tiles : 6144;
+    // Wave = the tiles counted, then emitted, between two grid barriers: as many as the count
+    // ranges allow (measured: fewer, larger waves are faster even when the records outgrow L2).
+    uint64_t wave = grid * kMaxRange;
     if (const char *e = getenv("CRP_WAVE_TILES")) {
         const long v = atol(e);
-        if (v > 0) wave = (uint64_t)v;
+        if (v > 0 && (uint64_t)v < wave) wave = (uint64_t)v;
     }
-    if (wave > grid * kMaxRange) wave = grid * kMaxRange;
-    if (wave < 1) wave = 1;
     p->wave_tiles = (uint32_t)wave;
     p->n_waves = (uint32_t)((g->n_tiles + wave - 1) / wave);
     return 0;
 }
 
-static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p, int guide_len, uint32_t flags,
-                       cudaEvent_t e0, cudaEvent_t e1) {
-    cudaStream_t st = g_ctx.stream;
+static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p) {
+    cudaStream_t st = r->st;
     ScanArgs a;
     a.records = g->records;
     a.n_tiles = g->n_tiles;
     a.wave_tiles = p.wave_tiles;
     a.static_eighths = 4;
     if (const char *e = getenv("CRP_STATIC_EIGHTHS")) a.static_eighths = (uint32_t)atoi(e) > 8 ? 8 : (uint32_t)atoi(e);
-    a.guide_len = guide_len;
-    a.flags = flags;
+    a.guide_len = r->guide_len;
+    a.flags = r->flags;
     a.tables = g_ctx.d_tables;
     a.capacity = r->capacity;
     a.pos_plus = r->pos[0];
@@ -458,9 +499,9 @@ static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p, in
     a.seg_counts = r->d_counts;
     a.tickets = reinterpret_cast<unsigned int *>(r->d_counts + 2 * (size_t)n_seg);
     a.n_seg = n_seg;
-    a.seg_first_tile = g->d_seg_first;
+    a.seg_first_tile = g->d_seg_first;      // NULL for a single-segment genome
     a.seg_tile_count = g->d_seg_count;
-    CUDA_TRY(cudaEventRecord(e0, st));
+    CUDA_TRY(cudaEventRecord(r->ev[0], st));
     if (g->n_tiles) {
         void *params[] = {(void *)&a};
         CUDA_TRY(cudaLaunchCooperativeKernel(p.fn, dim3(p.grid), dim3(kThreads), params, p.smem, st));
@@ -469,7 +510,74 @@ static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p, in
     } else if (n_seg) {
         CUDA_TRY(cudaMemsetAsync(r->d_counts, 0, 2 * (size_t)n_seg * sizeof(unsigned long long), st));
     }
-    CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaEventRecord(r->ev[1], st));
+    if (n_seg)
+        CUDA_TRY(cudaMemcpyAsync(r->h_counts, r->d_counts, 2 * (size_t)n_seg * sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+// Allocate the result of a scan and enqueue the scan on the genome's stream (no waiting).
+static int scan_enqueue(crp_genome *g, int guide_len, uint32_t flags, crp_result **res) {
+    crp_result *r = new (std::nothrow) crp_result();
+    if (!r) return fail(CRP_ERR_NOMEM, "out of host memory");
+    r->g = g;
+    r->st = stream_of(g);
+    r->guide_len = guide_len;
+    r->flags = flags;
+    r->scored = guide_len == 20 && !(flags & CRP_SCAN_NO_SCORE);
+    const uint32_t n_seg = (uint32_t)g->segs.size();
+    int rc = 0;
+    auto bail = [&](int code) {
+        crp_result_free(r);
+        return code;
+    };
+    ScanPlan plan = {};
+    if ((rc = plan_scan(g, r->scored, &plan))) return bail(rc);
+    r->zero_offset = ((size_t)g->n_tiles * kPrefWords + 2 * (size_t)plan.grid) * sizeof(unsigned long long);
+    r->state_bytes = r->zero_offset + 2 * (size_t)n_seg * sizeof(unsigned long long) +
+                     ((size_t)plan.n_waves + 2) * sizeof(unsigned int);
+    if (dev_alloc(&r->state, r->state_bytes, r->st) != cudaSuccess)
+        return bail(fail(CRP_ERR_NOMEM, "cudaMalloc of scan state failed"));
+    r->d_counts = reinterpret_cast<unsigned long long *>(r->state + r->zero_offset);
+    r->h_counts = static_cast<unsigned long long *>(pinned_get((2 * (size_t)n_seg + 1) * sizeof(unsigned long long)));
+    if (!r->h_counts) return bail(fail(CRP_ERR_NOMEM, "cudaHostAlloc of the counts failed"));
+    if (cudaEventCreate(&r->ev[0]) != cudaSuccess || cudaEventCreate(&r->ev[1]) != cudaSuccess)
+        return bail(fail(CRP_ERR_CUDA, "cudaEventCreate failed"));
+    // First guess of the per-strand capacity: 1/8 candidate per position (GC 70 %
+    // upper-case sequence gives 0.1225); a second pass with the exact counts
+    // follows if it was too small.
+    if ((rc = alloc_streams(r, g->n_positions / 8 + 4096, r->scored))) return bail(rc);
+    if ((rc = launch_scan(g, r, plan))) return bail(rc);
+    *res = r;
+    return 0;
+}
+
+// Wait for the scan, read the counts; run it again with exact capacity if the guess was short.
+static int scan_finish(crp_genome *g, crp_result *r) {
+    const uint32_t n_seg = (uint32_t)g->segs.size();
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if (cudaError_t e = cudaStreamSynchronize(r->st))
+            return fail(CRP_ERR_CUDA, "scan kernels failed: %s", cudaGetErrorString(e));
+        r->n_plus = r->n_minus = 0;
+        r->seg_plus.assign(n_seg, 0);
+        r->seg_minus.assign(n_seg, 0);
+        for (uint32_t s = 0; s < n_seg; ++s) {
+            r->seg_plus[s] = r->h_counts[s];
+            r->seg_minus[s] = r->h_counts[n_seg + s];
+            r->n_plus += r->seg_plus[s];
+            r->n_minus += r->seg_minus[s];
+        }
+        const uint64_t need = r->n_plus > r->n_minus ? r->n_plus : r->n_minus;
+        if (need <= r->capacity) break;
+        if (attempt == 1) return fail(CRP_ERR_STATE, "candidate streams overflowed twice");
+        free_streams(r);
+        if (int rc = alloc_streams(r, need, r->scored)) return rc;
+        ScanPlan plan = {};
+        if (int rc = plan_scan(g, r->scored, &plan)) return rc;
+        if (int rc = launch_scan(g, r, plan)) return rc;
+    }
+    cudaEventElapsedTime(&r->ms_scan, r->ev[0], r->ev[1]);
     return 0;
 }
 
@@ -478,69 +586,15 @@ int crp_scan_score(crp_genome *g, int guide_len, uint32_t flags, crp_result **re
     if (int rc = need_ctx()) return rc;
     if (!g->committed) return fail(CRP_ERR_STATE, "genome not committed");
     if (guide_len < 1 || guide_len > 1000000) return fail(CRP_ERR_ARG, "guide_len %d out of range", guide_len);
-    crp_result *r = new (std::nothrow) crp_result();
-    if (!r) return fail(CRP_ERR_NOMEM, "out of host memory");
-    r->g = g;
-    r->scored = guide_len == 20 && !(flags & CRP_SCAN_NO_SCORE);
-    const uint32_t n_seg = (uint32_t)g->segs.size();
-    cudaStream_t st = g_ctx.stream;
-    int rc = 0;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    std::vector<unsigned long long> counts(2 * (size_t)n_seg);
-    auto bail = [&](int code) {
-        if (e0) cudaEventDestroy(e0);
-        if (e1) cudaEventDestroy(e1);
-        crp_result_free(r);
-        return code;
-    };
     Trace tr("scan");
-    ScanPlan plan = {};
-    if ((rc = plan_scan(g, r->scored, &plan))) return bail(rc);
-    tr.lap("plan");
-    r->zero_offset = ((size_t)g->n_tiles * kPrefWords + 2 * (size_t)plan.grid) * sizeof(unsigned long long);
-    r->state_bytes = r->zero_offset + 2 * (size_t)n_seg * sizeof(unsigned long long) +
-                     ((size_t)plan.n_waves + 2) * sizeof(unsigned int);
-    if (dev_alloc(&r->state, r->state_bytes) != cudaSuccess)
-        return bail(fail(CRP_ERR_NOMEM, "cudaMalloc of scan state failed"));
-    r->d_counts = reinterpret_cast<unsigned long long *>(r->state + r->zero_offset);
-    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)
-        return bail(fail(CRP_ERR_CUDA, "cudaEventCreate failed"));
-    // First guess of the per-strand capacity: 1/8 candidate per position (GC 70 %
-    // upper-case sequence gives 0.1225); a second pass with the exact counts
-    // follows if it was too small.
-    {
-        uint64_t cap = g->n_positions / 8 + 4096;
-        if ((rc = alloc_streams(r, cap, r->scored))) return bail(rc);
+    crp_result *r = nullptr;
+    if (int rc = scan_enqueue(g, guide_len, flags, &r)) return rc;
+    tr.lap("enqueue");
+    if (int rc = scan_finish(g, r)) {
+        crp_result_free(r);
+        return rc;
     }
-    tr.lap("cudaMalloc");
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        if ((rc = launch_scan(g, r, plan, guide_len, flags, e0, e1))) return bail(rc);
-        tr.lap("launch");
-        if (n_seg)
-            if (cudaError_t e = cudaMemcpyAsync(counts.data(), r->d_counts, counts.size() * sizeof(unsigned long long),
-                                                cudaMemcpyDeviceToHost, st))
-                return bail(fail(CRP_ERR_CUDA, "D2H of segment counts failed: %s", cudaGetErrorString(e)));
-        if (cudaError_t e = cudaStreamSynchronize(st))
-            return bail(fail(CRP_ERR_CUDA, "scan kernels failed: %s", cudaGetErrorString(e)));
-        tr.lap("sync");
-        r->n_plus = r->n_minus = 0;
-        r->seg_plus.assign(n_seg, 0);
-        r->seg_minus.assign(n_seg, 0);
-        for (uint32_t s = 0; s < n_seg; ++s) {
-            r->seg_plus[s] = counts[s];
-            r->seg_minus[s] = counts[n_seg + s];
-            r->n_plus += counts[s];
-            r->n_minus += counts[n_seg + s];
-        }
-        const uint64_t need = r->n_plus > r->n_minus ? r->n_plus : r->n_minus;
-        if (need <= r->capacity) break;
-        if (attempt == 1) return bail(fail(CRP_ERR_STATE, "candidate streams overflowed twice"));
-        free_streams(r);
-        if ((rc = alloc_streams(r, need, r->scored))) return bail(rc);
-    }
-    cudaEventElapsedTime(&r->ms_scan, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    tr.lap("finish");
     *res = r;
     return 0;
 }
@@ -567,6 +621,19 @@ int crp_result_device_counts(const crp_result *res, void **dev_ptr) {
     return 0;
 }
 
+// D2H of rows [first, first + count) of one strand stream, enqueued on the result's stream
+static int fetch_enqueue(const crp_result *res, int s, uint64_t first, uint64_t count, uint32_t *pos, uint64_t *packed,
+                         double *x) {
+    cudaStream_t st = res->st;
+    if (count) {
+        if (pos) CUDA_TRY(cudaMemcpyAsync(pos, res->pos[s] + first, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (packed)
+            CUDA_TRY(cudaMemcpyAsync(packed, res->packed[s] + first, count * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        if (x) CUDA_TRY(cudaMemcpyAsync(x, res->x[s] + first, count * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    return 0;
+}
+
 int crp_result_fetch(const crp_result *res, char strand, uint64_t first, uint64_t count, uint32_t *pos,
                      uint64_t *packed, double *x) {
     if (!res) return fail(CRP_ERR_ARG, "res is NULL");
@@ -579,14 +646,8 @@ int crp_result_fetch(const crp_result *res, char strand, uint64_t first, uint64_
                     (unsigned long long)count, (unsigned long long)total);
     if ((packed || x) && !res->scored && count)
         return fail(CRP_ERR_STATE, "this result carries positions only (guide_len != 20 or CRP_SCAN_NO_SCORE)");
-    cudaStream_t st = g_ctx.stream;
-    if (count) {
-        if (pos) CUDA_TRY(cudaMemcpyAsync(pos, res->pos[s] + first, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        if (packed)
-            CUDA_TRY(cudaMemcpyAsync(packed, res->packed[s] + first, count * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-        if (x) CUDA_TRY(cudaMemcpyAsync(x, res->x[s] + first, count * sizeof(double), cudaMemcpyDeviceToHost, st));
-    }
-    CUDA_TRY(cudaStreamSynchronize(st));
+    if (int rc = fetch_enqueue(res, s, first, count, pos, packed, x)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(res->st));
     return 0;
 }
 
@@ -599,8 +660,76 @@ int crp_result_timing(const crp_result *res, float *ms_scan) {
 int crp_result_free(crp_result *r) {
     if (!r) return 0;
     free_streams(r);
-    dev_free(r->state);
+    dev_free(r->state, r->st);
+    pinned_put(r->h_counts);
+    for (cudaEvent_t e : r->ev)
+        if (e) cudaEventDestroy(e);
     delete r;
+    return 0;
+}
+
+// ------------------------------------------------------------------ pipelined whole-call path
+// Segments in, candidate arrays out, host memory on both sides: segment k+1 is copied in and
+// packed while segment k is scanned and segment k-1 is copied out (three streams, PCIe both
+// ways at once).  Rows of a strand land in the caller's arena in segment order.
+int crp_scan_segments(uint32_t n_segments, const crp_segment_desc *segments, int guide_len, uint32_t flags,
+                      uint64_t capacity, uint32_t *pos_plus, uint64_t *packed_plus, double *x_plus,
+                      uint32_t *pos_minus, uint64_t *packed_minus, double *x_minus, uint64_t *n_plus,
+                      uint64_t *n_minus, float *ms_device) {
+    if (int rc = need_ctx()) return rc;
+    if (n_segments && (!segments || !n_plus || !n_minus)) return fail(CRP_ERR_ARG, "NULL argument");
+    if (guide_len < 1 || guide_len > 1000000) return fail(CRP_ERR_ARG, "guide_len %d out of range", guide_len);
+    const bool scored = guide_len == 20 && !(flags & CRP_SCAN_NO_SCORE);
+    constexpr int kLanes = 3;
+    if (!g_ctx.lanes[0])
+        for (int i = 0; i < kLanes; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.lanes[i], cudaStreamNonBlocking));
+    std::vector<crp_genome *> gs(n_segments, nullptr);
+    std::vector<crp_result *> rs(n_segments, nullptr);
+    int rc = 0;
+    uint64_t off[2] = {0, 0};
+    float ms = 0.f;
+    bool overflow = false;
+    // counts of segment k are needed on the host before its rows can be placed: finish k-1
+    // right after k has been enqueued, so that the copy engines and the SMs never wait for us
+    auto finish = [&](uint32_t k) -> int {
+        if (int e = scan_finish(gs[k], rs[k])) return e;
+        n_plus[k] = rs[k]->n_plus;
+        n_minus[k] = rs[k]->n_minus;
+        ms += rs[k]->ms_scan;
+        if (off[0] + rs[k]->n_plus > capacity || off[1] + rs[k]->n_minus > capacity) {
+            overflow = true;        // keep counting so that the caller learns the capacity it needs
+        } else {
+            if (int e = fetch_enqueue(rs[k], 0, 0, rs[k]->n_plus, pos_plus ? pos_plus + off[0] : nullptr,
+                                      scored && packed_plus ? packed_plus + off[0] : nullptr,
+                                      scored && x_plus ? x_plus + off[0] : nullptr)) return e;
+            if (int e = fetch_enqueue(rs[k], 1, 0, rs[k]->n_minus, pos_minus ? pos_minus + off[1] : nullptr,
+                                      scored && packed_minus ? packed_minus + off[1] : nullptr,
+                                      scored && x_minus ? x_minus + off[1] : nullptr)) return e;
+        }
+        off[0] += rs[k]->n_plus;
+        off[1] += rs[k]->n_minus;
+        return 0;
+    };
+    for (uint32_t k = 0; k < n_segments && !rc; ++k) {
+        const crp_segment_desc &sd = segments[k];
+        if ((rc = crp_genome_new(&gs[k]))) break;
+        gs[k]->st = g_ctx.lanes[k % kLanes];
+        if ((rc = crp_genome_add_segment(gs[k], sd.token_id, sd.token, sd.token_len, sd.begin, sd.end))) break;
+        if ((rc = commit_enqueue(gs[k]))) break;
+        if ((rc = scan_enqueue(gs[k], guide_len, flags, &rs[k]))) break;
+        if (k > 0) rc = finish(k - 1);
+    }
+    if (!rc && n_segments) rc = finish(n_segments - 1);
+    for (int i = 0; i < kLanes; ++i) cudaStreamSynchronize(g_ctx.lanes[i]);
+    for (uint32_t k = 0; k < n_segments; ++k) {
+        crp_result_free(rs[k]);
+        crp_genome_free(gs[k]);
+    }
+    if (ms_device) *ms_device = ms;
+    if (rc) return rc;
+    if (overflow)
+        return fail(CRP_ERR_RANGE, "arena capacity %llu rows per strand is too small: need %llu / %llu",
+                    (unsigned long long)capacity, (unsigned long long)off[0], (unsigned long long)off[1]);
     return 0;
 }
 
@@ -625,12 +754,12 @@ int crp_rescore(const crp_genome *g, uint64_t n, const uint32_t *segment, const 
         items[i].strand = (uint32_t)strand[i];
         items[i].cls = cls[i];
     }
-    cudaStream_t st = g_ctx.stream;
+    cudaStream_t st = stream_of(g);
     RescoreItem *d_items = nullptr;
     double *d_x = nullptr;
-    CUDA_TRY(dev_alloc(&d_items, n * sizeof(RescoreItem)));
-    if (dev_alloc(&d_x, n * sizeof(double)) != cudaSuccess) {
-        dev_free(d_items);
+    CUDA_TRY(dev_alloc(&d_items, n * sizeof(RescoreItem), st));
+    if (dev_alloc(&d_x, n * sizeof(double), st) != cudaSuccess) {
+        dev_free(d_items, st);
         return fail(CRP_ERR_NOMEM, "cudaMalloc failed");
     }
     int rc = 0;
@@ -647,8 +776,8 @@ int crp_rescore(const crp_genome *g, uint64_t n, const uint32_t *segment, const 
             break;
         }
     } while (0);
-    dev_free(d_items);
-    dev_free(d_x);
+    dev_free(d_items, st);
+    dev_free(d_x, st);
     return rc;
 }
 

@@ -80,8 +80,11 @@ __host__ __device__ inline uint32_t classify(uint32_t c) {
 
 // One thread per record word.  Positions outside the staged part of the token become
 // "other" bytes (they never match a PAM and never score).
+// descs == NULL: the shard is ONE segment, described by `one` (descriptor of its first tile,
+// td.n = positions of the whole segment); tile j then follows by arithmetic, so that a
+// pipelined ingest needs no descriptor upload.
 __global__ void __launch_bounds__(256)
-k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, uint64_t n_items,
+k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, const PackDesc one, uint64_t n_items,
        uint4 *__restrict__ records) {
     __shared__ uint8_t lut[256];
     lut[threadIdx.x] = (uint8_t)classify(threadIdx.x);
@@ -90,7 +93,15 @@ k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, ui
     for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += stride) {
         const uint64_t tile = it / kRecWords;
         const uint32_t k = (uint32_t)(it - tile * kRecWords);
-        const PackDesc &pd = descs[tile];
+        PackDesc pd;
+        if (descs) {
+            pd = descs[tile];
+        } else {
+            pd = one;
+            const uint32_t done = (uint32_t)tile * (uint32_t)kTile;
+            pd.td.t_start = one.td.t_start + done;
+            pd.td.n = one.td.n - done < (uint32_t)kTile ? one.td.n - done : (uint32_t)kTile;
+        }
         if (k == 0) {
             records[it] = make_uint4(pd.td.t_start, pd.td.L, pd.td.n, pd.td.segment);
             continue;
@@ -530,7 +541,8 @@ k_scan_score(const ScanArgs a) {
         // per-segment candidate counts of this wave: prefix at the end of the segment's last
         // tile minus prefix at the start of its first one (segments are dealt to threads)
         for (uint32_t sg = cta * kThreads + tid; sg < a.n_seg; sg += G * kThreads) {
-            const uint32_t f = a.seg_first_tile[sg], c = a.seg_tile_count[sg];
+            const uint32_t f = a.seg_first_tile ? a.seg_first_tile[sg] : 0u;            // NULL: one segment = all tiles
+            const uint32_t c = a.seg_tile_count ? a.seg_tile_count[sg] : a.n_tiles;
             const uint32_t lo_t = max(f, w_lo), hi_t = min(f + c, w_hi);       // tiles of the segment in this wave
             unsigned long long cnt = 0;
             if (lo_t < hi_t)

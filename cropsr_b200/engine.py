@@ -84,6 +84,69 @@ class PinnedBuffer:
             pass
 
 
+class Arena:
+    """Pinned host arrays for the candidate rows of both strands (crp_scan_segments)."""
+
+    def __init__(self, capacity, scored=True):
+        self.capacity = int(capacity)
+        self.scored = scored
+        self._bufs = []
+        self.arrays = {}
+        for strand in "+-":
+            row = {}
+            for name, dt in (("pos", np.uint32), ("packed", np.uint64), ("x", np.float64)):
+                if name != "pos" and not scored:
+                    row[name] = None
+                    continue
+                b = PinnedBuffer(self.capacity * np.dtype(dt).itemsize)
+                self._bufs.append(b)
+                row[name] = b.view(dt, self.capacity)
+            self.arrays[strand] = row
+
+    def free(self):
+        self.arrays = {}
+        for b in self._bufs:
+            b.free()
+        self._bufs = []
+
+
+def scan_segments(segments, guide_len=20, flags=N.CRP_SCAN_DEFAULT, arena=None):
+    """Pipelined whole call: `segments` = [(token_id, token uint8 array (pinned for full speed),
+    begin, end)].  Returns (arena, n_plus[], n_minus[], device_ms); rows of a strand are in
+    arena.arrays[strand][name][:sum(counts)] in segment order.  If the arena is too small a
+    larger one is allocated and the call repeated."""
+    if _device is None:
+        init(0)
+    scored = int(guide_len) == 20 and not (flags & N.CRP_SCAN_NO_SCORE)
+    n = len(segments)
+    descs = (N.SegmentDesc * max(n, 1))()
+    keep = []
+    for i, (tid, tok, a, b) in enumerate(segments):
+        arr = _as_u8(tok)
+        keep.append(arr)
+        descs[i] = N.SegmentDesc(int(tid), arr.ctypes.data, len(arr), int(a), len(arr) if b is None else int(b))
+    n_plus = np.zeros(max(n, 1), dtype=np.uint64)
+    n_minus = np.zeros(max(n, 1), dtype=np.uint64)
+    ms = C.c_float(0)
+    if arena is None:
+        total = sum((len(k) if b is None else b) - a for k, (_, _, a, b) in zip(keep, segments))
+        arena = Arena(total // 12 + 4096, scored)
+    for attempt in range(2):
+        ptr = lambda a: a.ctypes.data if a is not None else None
+        p, m = arena.arrays["+"], arena.arrays["-"]
+        rc = lib.crp_scan_segments(n, descs, int(guide_len), int(flags), arena.capacity,
+                                   ptr(p["pos"]), ptr(p["packed"]), ptr(p["x"]),
+                                   ptr(m["pos"]), ptr(m["packed"]), ptr(m["x"]),
+                                   n_plus.ctypes.data, n_minus.ctypes.data, C.byref(ms))
+        if rc == -5 and attempt == 0:          # CRP_ERR_RANGE: arena too small, counts are valid
+            arena.free()
+            arena = Arena(int(max(n_plus.sum(), n_minus.sum())) + 1024, scored)
+            continue
+        check(rc)
+        break
+    return arena, n_plus[:n], n_minus[:n], ms.value
+
+
 class Genome:
     """A genome shard: an ordered list of token segments packed into HBM."""
 

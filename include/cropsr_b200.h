@@ -128,6 +128,27 @@ int crp_result_fetch(const crp_result *res, char strand, uint64_t first, uint64_
                      uint32_t *pos, uint64_t *packed, double *x);
 int crp_result_free(crp_result *res);
 
+/* ---- whole call from host memory, pipelined -------------------------------
+ * The same work as add_segment/commit/scan_score/fetch, one segment after the
+ * other, but overlapped: segment k+1 is copied in and packed while segment k is
+ * scanned and segment k-1 is copied out (three streams; PCIe in both directions
+ * at once).  Tokens and arenas should be pinned (crp_host_alloc).  Rows of a
+ * strand land in its arena in segment order; n_plus / n_minus [n_segments]
+ * receive the per-segment counts.  Returns CRP_ERR_RANGE if an arena of
+ * `capacity` rows per strand is too small (the counts are still filled in).
+ * packed / x arenas may be NULL (and are ignored when guide_len != 20).
+ * ms_device (optional) receives the summed device time of the scan kernels. */
+typedef struct crp_segment_desc {
+    uint32_t token_id;
+    const uint8_t *token;       /* position 0 of the whole token */
+    uint64_t token_len;
+    uint64_t begin, end;        /* positions of the token this call owns (begin % 128 == 0) */
+} crp_segment_desc;
+int crp_scan_segments(uint32_t n_segments, const crp_segment_desc *segments, int guide_len, uint32_t flags,
+                      uint64_t capacity, uint32_t *pos_plus, uint64_t *packed_plus, double *x_plus,
+                      uint32_t *pos_minus, uint64_t *packed_minus, double *x_minus,
+                      uint64_t *n_plus, uint64_t *n_minus, float *ms_device);
+
 /* Re-evaluate x for selected candidates in a given BLAS summation class
  * (rows of an np.matmul call that OpenBLAS sums in a different lane order:
  * the tail rows of each emitted slice).  Items are identified by

@@ -231,3 +231,49 @@ def test_full_size_properties(eng):
                 assert f["x"][i] == want[0]
     res.free()
     g.free()
+
+
+def test_multi_wave_scan_matches_oracle(eng, monkeypatch):
+    """Several count/emit waves (grid barrier between them, per-wave tickets, segment counts
+    accumulated across waves): force 2-tile waves on inputs of 3-7 tiles."""
+    monkeypatch.setenv("CRP_WAVE_TILES", "2")
+    _check_against_oracle(eng, synthetic_fasta(21, [100000, 40000], gc=0.5, lower_frac=0.2), 20)
+    monkeypatch.setenv("CRP_WAVE_TILES", "1")
+    _check_against_oracle(eng, synthetic_fasta(22, [50000], gc=0.6, lower_frac=0.0), 20)
+    monkeypatch.setenv("CRP_STATIC_EIGHTHS", "8")
+    _check_against_oracle(eng, synthetic_fasta(23, [90000], gc=0.5), 20)
+    monkeypatch.setenv("CRP_STATIC_EIGHTHS", "0")
+    _check_against_oracle(eng, synthetic_fasta(23, [90000], gc=0.5), 20)
+
+
+def test_pipelined_call_equals_plain_scan(eng):
+    """crp_scan_segments (overlapped H2D / pack / scan / D2H, one segment at a time) returns
+    exactly the rows of the plain add_segment/commit/scan/fetch path, in segment order."""
+    from cropsr_b200 import engine, ingest
+    text = synthetic_fasta(31, [70000, 1500, 45000], gc=0.5)
+    toks = [v.encode() for v in ingest.fasta_text_to_tokens(text).values()]
+    cut = 2 * engine.TILE
+    segs = [(0, toks[0], 0, cut), (0, toks[0], cut, len(toks[0])), (1, toks[1], 0, None), (2, toks[2], 0, None)]
+    for guide_len in (20, 18):
+        g = engine.Genome()
+        for k, tok, a, b in segs:
+            g.add_segment(k, tok, a, b)
+        res = g.commit().scan(guide_len)
+        arena, n_plus, n_minus, ms = engine.scan_segments(segs, guide_len)
+        assert n_plus.tolist() == res.seg_plus.tolist() and n_minus.tolist() == res.seg_minus.tolist()
+        for strand, n in (("+", res.n_plus), ("-", res.n_minus)):
+            want = res.fetch(strand)
+            got = arena.arrays[strand]
+            assert np.array_equal(got["pos"][:n], want["pos"])
+            if guide_len == 20:
+                assert np.array_equal(got["packed"][:n], want["packed"])
+                assert np.array_equal(got["x"][:n], want["x"])
+        # an arena that is too small is replaced by one of the right size
+        small = engine.Arena(16, guide_len == 20)
+        arena2, p2, m2, _ = engine.scan_segments(segs, guide_len, arena=small)
+        assert p2.tolist() == n_plus.tolist() and arena2.capacity >= max(res.n_plus, res.n_minus)
+        assert np.array_equal(arena2.arrays["-"]["pos"][:res.n_minus], res.fetch("-")["pos"])
+        arena.free()
+        arena2.free()
+        res.free()
+        g.free()
