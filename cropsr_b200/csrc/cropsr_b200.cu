@@ -683,6 +683,7 @@ int crp_scan_segments(uint32_t n_segments, const crp_segment_desc *segments, int
     constexpr int kLanes = 3;
     if (!g_ctx.lanes[0])
         for (int i = 0; i < kLanes; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.lanes[i], cudaStreamNonBlocking));
+    Trace tr("scan_segments");
     std::vector<crp_genome *> gs(n_segments, nullptr);
     std::vector<crp_result *> rs(n_segments, nullptr);
     int rc = 0;
@@ -717,14 +718,19 @@ int crp_scan_segments(uint32_t n_segments, const crp_segment_desc *segments, int
         if ((rc = crp_genome_add_segment(gs[k], sd.token_id, sd.token, sd.token_len, sd.begin, sd.end))) break;
         if ((rc = commit_enqueue(gs[k]))) break;
         if ((rc = scan_enqueue(gs[k], guide_len, flags, &rs[k]))) break;
+        tr.lap("enqueue");
         if (k > 0) rc = finish(k - 1);
+        tr.lap("finish prev");
     }
     if (!rc && n_segments) rc = finish(n_segments - 1);
+    tr.lap("finish last");
     for (int i = 0; i < kLanes; ++i) cudaStreamSynchronize(g_ctx.lanes[i]);
+    tr.lap("drain");
     for (uint32_t k = 0; k < n_segments; ++k) {
         crp_result_free(rs[k]);
         crp_genome_free(gs[k]);
     }
+    tr.lap("free");
     if (ms_device) *ms_device = ms;
     if (rc) return rc;
     if (overflow)
