@@ -24,6 +24,9 @@ def build_parser():
                    help="prints visual indicators for each iteration")
     # additions (defaults reproduce the reference)
     p.add_argument("--device", type=int, default=0, help="CUDA device ordinal, default = 0")
+    p.add_argument("--side-output", metavar="", default=None,
+                   help="also write a tab-separated table of opt-in per-candidate side outputs (GC, poly-T, "
+                        "homopolymer, +-L flank window, GFF feature under the cut site); the CSV is unaffected")
     p.add_argument("--blas-threads", type=int, default=1,
                    help="emulate the float summation order of the reference running with this many "
                         "OpenBLAS threads (default 1 = OPENBLAS_NUM_THREADS=1)")
@@ -58,5 +61,6 @@ def main(argv=None):
         print(banner(args))
     from . import engine, pipeline
     engine.init(args.device)
-    pipeline.run_cas9(args.f, args.g, args.o, args.l, args.verbose, args.blas_threads)
+    pipeline.run_cas9(args.f, args.g, args.o, args.l, args.verbose, args.blas_threads,
+                      side_output=args.side_output, flank=args.L)
     return 0

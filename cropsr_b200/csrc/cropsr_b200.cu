@@ -24,6 +24,7 @@
 #define CRP_CTAS_PER_SM 4
 #endif
 #include "scan.cuh"
+#include "extras.cuh"
 
 #define CRP_ABI_VERSION 3
 
@@ -737,6 +738,115 @@ int crp_scan_segments(uint32_t n_segments, const crp_segment_desc *segments, int
         return fail(CRP_ERR_RANGE, "arena capacity %llu rows per strand is too small: need %llu / %llu",
                     (unsigned long long)capacity, (unsigned long long)off[0], (unsigned long long)off[1]);
     return 0;
+}
+
+// rows of one segment inside a strand stream
+static int segment_rows(const crp_result *res, uint32_t segment, char strand, uint64_t *first, uint64_t *count) {
+    if (strand != '+' && strand != '-') return fail(CRP_ERR_ARG, "strand must be '+' or '-'");
+    const std::vector<uint64_t> &c = strand == '+' ? res->seg_plus : res->seg_minus;
+    if (segment >= c.size()) return fail(CRP_ERR_ARG, "segment %u out of range", segment);
+    uint64_t f = 0;
+    for (uint32_t s = 0; s < segment; ++s) f += c[s];
+    *first = f;
+    *count = c[segment];
+    return 0;
+}
+
+int crp_result_extras(const crp_result *res, uint32_t segment, char strand, uint32_t flank, uint8_t *gc,
+                      uint8_t *flags, uint8_t *run, uint32_t *cut, uint32_t *flank_lo, uint32_t *flank_hi) {
+    if (!res) return fail(CRP_ERR_ARG, "res is NULL");
+    if (int rc = need_ctx()) return rc;
+    if (res->guide_len != 20) return fail(CRP_ERR_STATE, "extras are defined for guide_len 20 (30-base windows) only");
+    uint64_t first = 0, n = 0;
+    if (int rc = segment_rows(res, segment, strand, &first, &n)) return rc;
+    if (n == 0) return 0;
+    const crp_genome *g = res->g;
+    const Segment &sg = g->segs[segment];
+    cudaStream_t st = res->st;
+    const int s = strand == '+' ? 0 : 1;
+    uint8_t *d8 = nullptr;
+    uint32_t *d32 = nullptr;
+    CUDA_TRY(dev_alloc(&d8, 3 * n, st));
+    if (dev_alloc(&d32, 3 * n * sizeof(uint32_t), st) != cudaSuccess) {
+        dev_free(d8, st);
+        return fail(CRP_ERR_NOMEM, "cudaMalloc failed");
+    }
+    ExtrasArgs a;
+    a.records = g->records;
+    a.pos = res->pos[s] + first;
+    a.n = n;
+    a.first_tile = sg.first_tile;
+    a.seg_begin = (uint32_t)sg.begin;
+    a.L = (uint32_t)sg.token_len;
+    a.flank = flank;
+    a.minus = s;
+    a.gc = d8;
+    a.flags = d8 + n;
+    a.run = d8 + 2 * n;
+    a.cut = d32;
+    a.flank_lo = d32 + n;
+    a.flank_hi = d32 + 2 * n;
+    k_extras<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a);
+    g_ctx.launches++;
+    int rc = 0;
+    auto back = [&](void *dst, const void *src, size_t bytes) {
+        if (dst && !rc && cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            rc = fail(CRP_ERR_CUDA, "D2H of extras failed");
+    };
+    back(gc, a.gc, n);
+    back(flags, a.flags, n);
+    back(run, a.run, n);
+    back(cut, a.cut, n * 4);
+    back(flank_lo, a.flank_lo, n * 4);
+    back(flank_hi, a.flank_hi, n * 4);
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess)
+        rc = fail(CRP_ERR_CUDA, "extras kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    dev_free(d8, st);
+    dev_free(d32, st);
+    return rc;
+}
+
+int crp_result_annotate(const crp_result *res, uint32_t segment, char strand, uint32_t n_intervals,
+                        const uint32_t *start, const uint32_t *end, int32_t *feature) {
+    if (!res) return fail(CRP_ERR_ARG, "res is NULL");
+    if (int rc = need_ctx()) return rc;
+    uint64_t first = 0, n = 0;
+    if (int rc = segment_rows(res, segment, strand, &first, &n)) return rc;
+    if (n == 0) return 0;
+    if (!feature || (n_intervals && (!start || !end))) return fail(CRP_ERR_ARG, "NULL argument");
+    std::vector<uint32_t> host(3 * (size_t)n_intervals + 1);
+    uint32_t running = 0;
+    for (uint32_t j = 0; j < n_intervals; ++j) {
+        if (j && start[j] < start[j - 1]) return fail(CRP_ERR_ARG, "intervals must be sorted by start");
+        if (end[j] < start[j]) return fail(CRP_ERR_ARG, "interval %u has end < start", j);
+        running = end[j] > running ? end[j] : running;
+        host[j] = start[j];
+        host[n_intervals + j] = end[j];
+        host[2 * (size_t)n_intervals + j] = running;
+    }
+    cudaStream_t st = res->st;
+    uint32_t *d_iv = nullptr;
+    int32_t *d_f = nullptr;
+    CUDA_TRY(dev_alloc(&d_iv, host.size() * sizeof(uint32_t), st));
+    if (dev_alloc(&d_f, n * sizeof(int32_t), st) != cudaSuccess) {
+        dev_free(d_iv, st);
+        return fail(CRP_ERR_NOMEM, "cudaMalloc failed");
+    }
+    int rc = 0;
+    const int s = strand == '+' ? 0 : 1;
+    if (cudaMemcpyAsync(d_iv, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st) != cudaSuccess)
+        rc = fail(CRP_ERR_CUDA, "H2D of intervals failed");
+    if (!rc) {
+        k_annotate<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(res->pos[s] + first, n, s, d_iv, d_iv + n_intervals,
+                                                               d_iv + 2 * (size_t)n_intervals, n_intervals, d_f);
+        g_ctx.launches++;
+        if (cudaMemcpyAsync(feature, d_f, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess)
+            rc = fail(CRP_ERR_CUDA, "annotate failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    dev_free(d_iv, st);
+    dev_free(d_f, st);
+    return rc;
 }
 
 int crp_rescore(const crp_genome *g, uint64_t n, const uint32_t *segment, const uint32_t *t, const char *strand,

@@ -270,6 +270,30 @@ class ScanResult:
                                    ptr(res["pos"]), ptr(res["packed"]), ptr(res["x"])))
         return res
 
+    def extras(self, seg, strand, flank=200):
+        """Opt-in side outputs of one segment's candidates (never in the parity CSV):
+        dict(gc, flags, run: uint8[]; cut, flank_lo, flank_hi: uint32[])."""
+        n = int((self.seg_plus if strand == "+" else self.seg_minus)[seg])
+        out = {k: np.empty(n, np.uint8) for k in ("gc", "flags", "run")}
+        out.update({k: np.empty(n, np.uint32) for k in ("cut", "flank_lo", "flank_hi")})
+        ptr = lambda a: a.ctypes.data if len(a) else None
+        check(lib.crp_result_extras(self._h, int(seg), strand.encode(), int(flank), ptr(out["gc"]), ptr(out["flags"]),
+                                    ptr(out["run"]), ptr(out["cut"]), ptr(out["flank_lo"]), ptr(out["flank_hi"])))
+        return out
+
+    def annotate(self, seg, strand, start, end):
+        """Index of the innermost interval [start, end] (inclusive token coordinates,
+        sorted by start) containing each candidate's cut site, -1 if none."""
+        start = np.ascontiguousarray(start, dtype=np.uint32)
+        end = np.ascontiguousarray(end, dtype=np.uint32)
+        n = int((self.seg_plus if strand == "+" else self.seg_minus)[seg])
+        out = np.empty(n, np.int32)
+        if n:
+            check(lib.crp_result_annotate(self._h, int(seg), strand.encode(), len(start),
+                                          start.ctypes.data if len(start) else None,
+                                          end.ctypes.data if len(end) else None, out.ctypes.data))
+        return out
+
     def fetch_segment(self, seg, strand, **kw):
         off = self.off_plus if strand == "+" else self.off_minus
         return self.fetch(strand, int(off[seg]), int(off[seg + 1] - off[seg]), **kw)

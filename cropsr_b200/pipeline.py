@@ -26,12 +26,41 @@ def scan_tokens(tokens, guide_len=20, flags=0):
     return genome, result, token_bytes
 
 
+def write_side_output(path, tokens, result, gff_frame, flank, formatted_path):
+    """Opt-in table of the per-candidate side outputs (one row per unique candidate, reference
+    order).  NOT part of the reference's CSV: GC, poly-T / homopolymer flags, cut site, the
+    +-L flank window and the GFF feature under the cut site (device kernels k_extras /
+    k_annotate; semantics in oracle/extras_oracle.py)."""
+    import csv
+    from . import annotate
+    ivs = annotate.intervals_for_tokens(gff_frame, list(tokens.keys()), formatted_path)
+    with open(path, "w", newline="") as f:
+        w = csv.writer(f, delimiter="\t")
+        w.writerow(["chromosome", "strand", "pam_pos", "cutsite", "gc", "poly_t", "homopolymer", "low_gc",
+                    "unscored_base", "longest_run", "flank_start", "flank_end", "feature_type", "feature_attributes"])
+        for seg, key in enumerate(tokens.keys()):
+            iv = ivs[seg]
+            for strand in "+-":
+                pos = result.fetch_segment(seg, strand, want=("pos",))["pos"]
+                ex = result.extras(seg, strand, flank)
+                feat = result.annotate(seg, strand, iv["start"], iv["end"])
+                rows = np.where(feat >= 0, iv["row"][np.maximum(feat, 0)] if len(iv["row"]) else -1, -1)
+                for i in range(len(pos)):
+                    fl = int(ex["flags"][i])
+                    ft, fa = "", ""
+                    if rows[i] >= 0:
+                        ft, fa = gff_frame.at[rows[i], "feature"], gff_frame.at[rows[i], "attributes"]
+                    w.writerow([key[1:], strand, int(pos[i]), int(ex["cut"][i]), int(ex["gc"][i]), fl & 1, (fl >> 1) & 1,
+                                (fl >> 2) & 1, (fl >> 3) & 1, int(ex["run"][i]), int(ex["flank_lo"][i]),
+                                int(ex["flank_hi"][i]), ft, fa])
+
+
 def run_cas9(fasta, gff, output="data.csv", guide_len=20, verbose=False, blas_threads=1,
-             time_path="time.txt", out=print):
+             time_path="time.txt", out=print, side_output=None, flank=200):
     begin = time.time()
     timing = open(time_path, "w")                       # CROPSR.py:371
     tokens = ingest.import_fasta_file(fasta, verbose)   # :374
-    ingest.import_gff_file(gff, verbose)                # :375 (parsed, never used)
+    gff_frame = ingest.import_gff_file(gff, verbose)    # :375 (parsed, never used by the reference)
     if verbose:
         out("\n            Initiating PAM site detection.\n            \n"
             "            Please wait, this may take a while...\n            ")
@@ -52,6 +81,10 @@ def run_cas9(fasta, gff, output="data.csv", guide_len=20, verbose=False, blas_th
         rows_written += emit.emit_cumulative(output, table, genome, blas_threads)
         timing.write("Total runtime of the program is " + str(time.time() - begin))   # :476-477
     timing.close()
+    if side_output and guide_len == 20:
+        with open(fasta, "r") as f:
+            formatted_path = ingest.needs_formatting(f.read())
+        write_side_output(side_output, tokens, result, gff_frame, flank, formatted_path)
     stats = {"tokens": len(tokens), "candidates": len(table), "rows": rows_written,
              "scan_ms": result.scan_ms(), **genome.timing()}
     result.free()

@@ -158,6 +158,27 @@ int crp_scan_segments(uint32_t n_segments, const crp_segment_desc *segments, int
 int crp_rescore(const crp_genome *g, uint64_t n, const uint32_t *segment, const uint32_t *t,
                 const char *strand, const uint8_t *cls, double *x_out);
 
+/* ---- opt-in side outputs (never part of the reference CSV: the reference parses
+ * -L and -g and does not use them, CROPSR.py:41,375) -------------------------
+ * Per candidate of one segment and strand, in stream order; any pointer may be
+ * NULL.  guide_len 20 only.
+ *   gc        G+C count of the 20-base protospacer (scored 30-mer[5:25]; the
+ *             reference's only hint: cropsr_functions.py:174-179)
+ *   flags     bit0 TTTT in the protospacer, bit1 homopolymer run >= 5,
+ *             bit2 gc < 10, bit3 protospacer holds a base that does not score
+ *   run       longest homopolymer run in the protospacer
+ *   cut       cut site = end_pos - 3 of the CSV row (CROPSR.py:155-158)
+ *   flank_lo/hi  [cut - flank, cut + flank) clipped to the token (the -L window
+ *             meant for prmrdsgn2 primer design) */
+int crp_result_extras(const crp_result *res, uint32_t segment, char strand, uint32_t flank,
+                      uint8_t *gc, uint8_t *flags, uint8_t *run,
+                      uint32_t *cut, uint32_t *flank_lo, uint32_t *flank_hi);
+/* feature[i] = index of the innermost interval [start, end] (inclusive, token
+ * coordinates, sorted by start) that contains candidate i's cut site, or -1:
+ * a binary search per candidate in device memory. */
+int crp_result_annotate(const crp_result *res, uint32_t segment, char strand, uint32_t n_intervals,
+                        const uint32_t *start, const uint32_t *end, int32_t *feature);
+
 /* Kernel timings (CUDA events on the library stream) of the last commit /
  * scan: milliseconds. */
 int crp_genome_timing(const crp_genome *g, float *ms_h2d, float *ms_pack);

@@ -277,3 +277,57 @@ def test_pipelined_call_equals_plain_scan(eng):
         arena2.free()
         res.free()
         g.free()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_extras_and_annotation_match_oracle(eng, seed):
+    """Opt-in side outputs (GC / poly-T / homopolymer / cut / flank / feature index): device
+    kernels vs the independent string oracle, on FASTAs with lower-case, N and IUPAC."""
+    import extras_oracle
+    from cropsr_b200 import ingest, pipeline
+    rng = np.random.default_rng(500 + seed)
+    alphabet = np.frombuffer(b"ACGTacgtNRU", dtype=np.uint8)
+    p = np.array([20, 20, 20, 20, 3, 3, 3, 3, 1, .3, .2])
+    recs = [(f"r{k}", rng.choice(alphabet, size=int(rng.integers(100, 40000)), p=p / p.sum()).tobytes().decode())
+            for k in range(3)]
+    recs.append(("polyT", "ACGT" * 10 + "TTTTTTTTGG" * 30 + "CCAAAAAAAA" * 30))
+    text = "".join(f">{h}\n" + "\n".join(s[i:i + 60] for i in range(0, len(s), 60)) + "\n" for h, s in recs)
+    tokens = ingest.fasta_text_to_tokens(text)
+    genome, result, _ = pipeline.scan_tokens(tokens, 20)
+    try:
+        for seg, (key, tok) in enumerate(tokens.items()):
+            want = extras_oracle.extras_for_token(key, tok, flank=150)
+            n_iv = int(rng.integers(0, 40))
+            a = np.sort(rng.integers(0, max(len(tok), 1), size=n_iv)).astype(np.uint32)
+            b = (a + rng.integers(0, 3000, size=n_iv)).astype(np.uint32)
+            for strand in "+-":
+                rows = [r for r in want if r["strand"] == strand]
+                got = result.extras(seg, strand, flank=150)
+                assert got["cut"].tolist() == [r["cut"] for r in rows]
+                assert got["flank_lo"].tolist() == [r["flank_lo"] for r in rows]
+                assert got["flank_hi"].tolist() == [r["flank_hi"] for r in rows]
+                full = np.array([r["full"] for r in rows], dtype=bool)
+                for name in ("gc", "flags", "run"):
+                    assert got[name][full].tolist() == [r[name] for r in rows if r["full"]], (name, strand)
+                feat = result.annotate(seg, strand, a, b)
+                assert np.array_equal(feat, extras_oracle.annotate([r["cut"] for r in rows], a, b))
+    finally:
+        result.free()
+        genome.free()
+
+
+def test_cli_side_output_leaves_csv_untouched(manifest, eng, tmp_path):
+    """--side-output writes its own table; the parity CSV stays byte-identical to the reference's."""
+    from cropsr_b200 import pipeline
+    case = manifest["cases"]["sample"]
+    out, side = tmp_path / "out.csv", tmp_path / "side.tsv"
+    np.random.seed(case["seed"])
+    stats = pipeline.run_cas9(fixture_path(case["fasta"]), fixture_path("sample_genome.gff"), str(out), 20, False,
+                              case["blas_threads"], str(tmp_path / "time.txt"), out=lambda *a: None,
+                              side_output=str(side), flank=200)
+    assert out.read_bytes().decode() == golden_csv("sample")
+    rows = list(csv.reader(open(side), delimiter="\t"))
+    assert len(rows) == stats["candidates"] + 1
+    assert rows[0][:5] == ["chromosome", "strand", "pam_pos", "cutsite", "gc"]
+    assert any(r[12] == "CDS" for r in rows[1:]) and any(r[12] == "" for r in rows[1:])
+    assert all(0 <= int(r[4]) <= 20 for r in rows[1:])

@@ -128,3 +128,22 @@ def test_shard_plan_and_offsets(built_lib):
                 assert off == pos
                 pos += c
             assert [(k, st, a) for _, _, k, st, a in rows] == sorted((k, st, a) for _, _, k, st, a in rows)
+
+
+def test_gff_intervals_per_token(built_lib):
+    """GFF rows -> sorted inclusive token intervals, both ingest paths (annotate.py)."""
+    import os
+    from cropsr_b200 import annotate, ingest
+    gff = os.path.join(os.path.dirname(__file__), "golden", "fixtures", "sample_genome.gff")
+    frame = ingest.import_gff_file(gff)
+    chrom = frame.loc[frame["feature"] == "gene", "chromosome"].iloc[0]     # the #! header lines are junk rows
+    for formatted, key in ((True, f"('{chrom}',"), (False, f">{chrom}")):
+        iv, = annotate.intervals_for_tokens(frame, [key], formatted, features=("gene",))
+        genes = frame[(frame["feature"] == "gene") & (frame["chromosome"] == chrom)]
+        assert len(iv["start"]) == len(genes) > 0
+        assert np.all(np.diff(iv["start"].astype(np.int64)) >= 0)
+        shift = 0 if formatted else -1
+        assert iv["start"].min() == int(genes["start"].min()) + shift
+        assert set(frame.loc[iv["row"], "feature"]) == {"gene"}
+    none, = annotate.intervals_for_tokens(frame, [">not_there"], False)
+    assert len(none["start"]) == 0
