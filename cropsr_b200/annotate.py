@@ -17,15 +17,15 @@ DEFAULT_FEATURES = ("gene", "CDS")
 
 
 def token_chromosome(key, formatted_path):
-    """Sequence name of an ingest-dict key: '>chr1' (clean) or "('chr1'," / "'chr2'," (formatted)."""
+    """Sequence name of an ingest-dict key: '>chr1' (clean) or "[('chr1'," / "('chr2'," (formatted)."""
     if not formatted_path:
         return key[1:]
-    return key.strip("(),").strip("'\"")
+    return key.strip("[](),").strip("'\"")
 
 
 def intervals_for_tokens(frame, keys, formatted_path, features=DEFAULT_FEATURES):
     """frame: the DataFrame of ingest.import_gff_file.  Returns one dict per ingest key:
-    start, end (uint32, inclusive token coordinates, sorted by start then end), row (index of
+    start, end (uint32, inclusive token coordinates, sorted by start, longer feature first), row (index of
     the GFF row in `frame`), so that a feature index from the kernel maps back to its attributes."""
     shift = 0 if formatted_path else -1
     sel = frame[frame["feature"].isin(features)]
@@ -39,7 +39,7 @@ def intervals_for_tokens(frame, keys, formatted_path, features=DEFAULT_FEATURES)
             continue
         start = g["start"].to_numpy(dtype=np.int64) + shift
         end = g["end"].to_numpy(dtype=np.int64) + shift
-        order = np.lexsort((end, start))
+        order = np.lexsort((-end, start))      # equal starts: the shorter feature last, so that it wins
         out.append({"start": start[order].astype(np.uint32), "end": end[order].astype(np.uint32),
                     "row": g.index.to_numpy()[order]})
     return out

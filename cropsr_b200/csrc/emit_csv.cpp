@@ -1,0 +1,261 @@
+// Host-side CSV row formatter: byte-identical to what the reference writes with
+// csv.writer(...).writerows(rows) in /root/reference/CROPSR.py:463-474 -- excel dialect
+// (',' delimiter, QUOTE_MINIMAL with '"' doubled, "\r\n"), ints through str(), the score through
+// str(numpy.float64) == repr(float) (shortest digits that round-trip, Python's switch to
+// exponent notation below 1e-4 and from 1e16) -- but multi-threaded C++ instead of one Python
+// tuple + csv call per row.  Pure host code: no CUDA in this file.
+//
+// Row (CROPSR.py:463-469), len(long_sequence) == guide_len + 10:
+//     id,cas9,short,long,chrom,start,end,end-3,strand,score,,completed
+// otherwise the 11-field "error row":
+//     id,cas9,short,long,chrom,start,end,strand,-1,,completed
+// short / long are Python slices of the token (silently truncated at its end) pushed through the
+// reference's replace chains (CROPSR.py:116-129).
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/cropsr_b200.h"
+
+namespace {
+
+// '+' strand: gRNA(x) = A->U C->G G->C T->A (and Z->G through the chain), then reversed
+// '-' strand: gRNA(revcomp(x)) = forward order, T->U, U->A, Z->C
+struct Tables {
+    unsigned char plus[256], minus[256];
+    Tables() {
+        for (int i = 0; i < 256; ++i) plus[i] = minus[i] = (unsigned char)i;
+        plus['A'] = 'U'; plus['C'] = 'G'; plus['G'] = 'C'; plus['T'] = 'A'; plus['Z'] = 'G';
+        minus['T'] = 'U'; minus['U'] = 'A'; minus['Z'] = 'C';
+    }
+};
+const Tables kTab;
+
+inline void put_field(std::string &out, const char *s, size_t n) {   // QUOTE_MINIMAL
+    bool quote = false;
+    for (size_t i = 0; i < n; ++i) {
+        const char c = s[i];
+        if (c == ',' || c == '"' || c == '\r' || c == '\n') {
+            quote = true;
+            break;
+        }
+    }
+    if (!quote) {
+        out.append(s, n);
+        return;
+    }
+    out.push_back('"');
+    for (size_t i = 0; i < n; ++i) {
+        if (s[i] == '"') out.push_back('"');
+        out.push_back(s[i]);
+    }
+    out.push_back('"');
+}
+
+inline void put_int(std::string &out, long long v) {
+    char buf[24];
+    const int n = snprintf(buf, sizeof buf, "%lld", v);
+    out.append(buf, (size_t)n);
+}
+
+// repr(float): shortest decimal string that parses back to the same double, laid out the way
+// CPython's float_repr_style 'short' does (fixed notation for 1e-4 <= |x| < 1e16).
+void put_repr(std::string &out, double x) {
+    if (isnan(x)) { out += "nan"; return; }
+    if (isinf(x)) { out += x < 0 ? "-inf" : "inf"; return; }
+    if (x == 0.0) { out += signbit(x) ? "-0.0" : "0.0"; return; }
+    // Shortest precision whose correctly rounded decimal parses back to x.  Most doubles need
+    // 16-17 digits, so probe 15 first and walk from there.  At a power of two the interval of
+    // decimals that round to x is lopsided (half as wide below x): the nearest p-digit
+    // decimal can fall out on the narrow side while its upper neighbour still round-trips,
+    // and that neighbour is what repr() prints.
+    char buf[48];
+    int e2;
+    const bool pow2 = frexp(fabs(x), &e2) == 0.5;
+    auto fits = [&](int prec) -> bool {
+        snprintf(buf, sizeof buf, "%.*e", prec - 1, x);
+        if (strtod(buf, nullptr) == x) return true;
+        if (!pow2) return false;
+        // neighbour one unit in the last place further from zero
+        char *q = buf + (buf[0] == '-');
+        unsigned long long d = 0;
+        char *r = q;
+        for (; *r && *r != 'e'; ++r)
+            if (*r != '.') d = d * 10 + (unsigned long long)(*r - '0');
+        int ex = atoi(r + 1) - (prec - 1);            // value = d * 10^ex
+        ++d;
+        char alt[48];
+        snprintf(alt, sizeof alt, "%s%llue%d", buf[0] == '-' ? "-" : "", d, ex);
+        if (strtod(alt, nullptr) != x) return false;
+        // rewrite as d.ddde+XX with the same number of digits (d + 1 cannot carry into a new digit
+        // here: a carry would make it a shorter decimal, which an earlier precision would have found)
+        char dig[24];
+        const int nd = snprintf(dig, sizeof dig, "%llu", d);
+        int w = 0;
+        if (buf[0] == '-') buf[w++] = '-';
+        buf[w++] = dig[0];
+        if (nd > 1) {
+            buf[w++] = '.';
+            memcpy(buf + w, dig + 1, (size_t)(nd - 1));
+            w += nd - 1;
+        }
+        snprintf(buf + w, sizeof buf - (size_t)w, "e%+03d", ex + nd - 1);
+        return true;
+    };
+    int prec = 15;
+    if (fits(prec)) {
+        while (prec > 1 && fits(prec - 1)) --prec;
+        fits(prec);                                    // leave the winning string in buf
+    } else {
+        ++prec;
+        while (prec < 17 && !fits(prec)) ++prec;
+        if (prec == 17) fits(17);
+    }
+    // buf = [-]d[.ddd]e[+-]XX
+    const char *p = buf;
+    if (*p == '-') { out.push_back('-'); ++p; }
+    char digits[24];
+    int nd = 0;
+    for (; *p && *p != 'e'; ++p)
+        if (*p != '.') digits[nd++] = *p;
+    const int exp10 = atoi(p + 1);                 // value = d.ddd * 10^exp10
+    while (nd > 1 && digits[nd - 1] == '0') --nd;  // %.{p}e of a shorter-representable value never pads, but be safe
+    const int decpt = exp10 + 1;                   // digits before the decimal point
+    if (decpt > 16 || decpt < -3) {                // exponent notation
+        out.push_back(digits[0]);
+        if (nd > 1) {
+            out.push_back('.');
+            out.append(digits + 1, (size_t)(nd - 1));
+        }
+        char e[16];
+        snprintf(e, sizeof e, "e%c%02d", exp10 < 0 ? '-' : '+', abs(exp10));
+        out += e;
+    } else if (decpt <= 0) {                       // 0.000ddd
+        out += "0.";
+        out.append((size_t)(-decpt), '0');
+        out.append(digits, (size_t)nd);
+    } else if (decpt >= nd) {                      // ddd000.0
+        out.append(digits, (size_t)nd);
+        out.append((size_t)(decpt - nd), '0');
+        out += ".0";
+    } else {                                       // dd.ddd
+        out.append(digits, (size_t)decpt);
+        out.push_back('.');
+        out.append(digits + decpt, (size_t)(nd - decpt));
+    }
+}
+
+struct Job {
+    uint64_t n_rows;
+    const char *ids;                 // n_ids x 7 bytes
+    const uint64_t *id_index;        // per row
+    const uint32_t *token_of, *t;
+    const uint8_t *minus, *scored;
+    const double *score;
+    const uint8_t *const *tokens;
+    const uint64_t *token_len;
+    const char *const *chrom;
+    const uint32_t *chrom_len;
+    int guide_len;
+};
+
+void format_range(const Job &j, uint64_t lo, uint64_t hi, std::string &out) {
+    const int l = j.guide_len;
+    std::string seq;
+    out.reserve((size_t)(hi - lo) * (size_t)(96 + 2 * l));
+    for (uint64_t i = lo; i < hi; ++i) {
+        const uint32_t k = j.token_of[i];
+        const uint8_t *tok = j.tokens[k];
+        const int64_t L = (int64_t)j.token_len[k], t = j.t[i];
+        const bool minus = j.minus[i] != 0;
+        out.append(j.ids + 7 * j.id_index[i], 7);
+        out += ",cas9,";
+        // Python slices [a, b) clipped to the token
+        auto slice = [&](int64_t a, int64_t b) {
+            if (a < 0) a = 0;              // cannot happen for rows the scan emits (t >= l+5 resp. t >= 2)
+            if (b > L) b = L;
+            seq.clear();
+            if (minus)
+                for (int64_t q = a; q < b; ++q) seq.push_back((char)kTab.minus[tok[q]]);
+            else
+                for (int64_t q = b - 1; q >= a; --q) seq.push_back((char)kTab.plus[tok[q]]);
+            put_field(out, seq.data(), seq.size());
+        };
+        int64_t first, second;
+        if (minus) {
+            slice(t + 3, t + 3 + l);
+            out.push_back(',');
+            slice(t - 2, t + l + 8);
+            first = t + 3 + l;
+            second = t + 3;
+        } else {
+            slice(t - l, t);
+            out.push_back(',');
+            slice(t - l - 5, t + 5);
+            first = t - l;
+            second = t;
+        }
+        out.push_back(',');
+        put_field(out, j.chrom[k], j.chrom_len[k]);
+        out.push_back(',');
+        put_int(out, first);
+        out.push_back(',');
+        put_int(out, second);
+        out.push_back(',');
+        if (j.scored[i]) {
+            put_int(out, second - 3);                    // apply_cutsite, CROPSR.py:155-158
+            out.push_back(',');
+            out.push_back(minus ? '-' : '+');
+            out.push_back(',');
+            put_repr(out, j.score[i]);
+        } else {
+            out.push_back(minus ? '-' : '+');
+            out += ",-1";
+        }
+        out += ",,completed\r\n";
+    }
+}
+
+}  // namespace
+
+extern "C" int crp_format_rows(uint64_t n_rows, const char *ids, const uint64_t *id_index, const uint32_t *token_of,
+                               const uint32_t *t, const uint8_t *minus, const uint8_t *scored, const double *score,
+                               uint32_t n_tokens, const uint8_t *const *tokens, const uint64_t *token_len,
+                               const char *const *chrom, const uint32_t *chrom_len, int guide_len, int n_threads,
+                               char *out, uint64_t out_capacity, uint64_t *out_bytes) {
+    if (!out_bytes) return CRP_ERR_ARG;
+    *out_bytes = 0;
+    if (n_rows == 0) return 0;
+    if (!ids || !id_index || !token_of || !t || !minus || !scored || !score || !tokens || !token_len || !chrom ||
+        !chrom_len || guide_len < 1)
+        return CRP_ERR_ARG;
+    for (uint64_t i = 0; i < n_rows; ++i)
+        if (token_of[i] >= n_tokens) return CRP_ERR_ARG;
+    Job j = {n_rows, ids, id_index, token_of, t, minus, scored, score, tokens, token_len, chrom, chrom_len, guide_len};
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 1;
+    uint64_t nt = n_threads > 0 ? (uint64_t)n_threads : (hw > 16 ? 16 : hw);
+    if (nt > (n_rows + 4095) / 4096) nt = (n_rows + 4095) / 4096;     // >= 4096 rows per thread
+    std::vector<std::string> parts(nt);
+    std::vector<std::thread> pool;
+    for (uint64_t w = 1; w < nt; ++w)
+        pool.emplace_back([&, w] { format_range(j, n_rows * w / nt, n_rows * (w + 1) / nt, parts[w]); });
+    format_range(j, 0, n_rows / nt, parts[0]);
+    for (std::thread &th : pool) th.join();
+    uint64_t total = 0;
+    for (const std::string &p : parts) total += p.size();
+    *out_bytes = total;
+    if (total > out_capacity || !out) return CRP_ERR_RANGE;          // caller retries with *out_bytes
+    char *dst = out;
+    for (const std::string &p : parts) {
+        memcpy(dst, p.data(), p.size());
+        dst += p.size();
+    }
+    return 0;
+}

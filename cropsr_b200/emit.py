@@ -181,6 +181,44 @@ def slice_rows(table, ids, scores, scored, start, count):
     return rows
 
 
+def format_rows(table, ids, scores, scored, start, count, n_threads=0):
+    """CSV bytes of one emitted slice through the library's multi-threaded row formatter
+    (csrc/emit_csv.cpp) -- byte-identical to csv.writer().writerows(slice_rows(...))."""
+    import ctypes as C
+    from ._native import lib, check
+    if count == 0:
+        return b""
+    id_bytes = np.ascontiguousarray(ids).view(np.uint32).astype(np.uint8)   # '<U1' code points -> (size, 7) bytes
+    size = len(id_bytes)
+    id_index = ((start - 1 - np.arange(count, dtype=np.int64)) % size).astype(np.uint64)   # ids[start - k - 1]
+    tok = np.ascontiguousarray(table.tok[start:start + count], dtype=np.uint32)
+    t = np.ascontiguousarray(table.t[start:start + count], dtype=np.uint32)
+    minus = np.ascontiguousarray(table.minus[start:start + count], dtype=np.uint8)
+    ok = np.ascontiguousarray(scored, dtype=np.uint8)
+    sc = np.ascontiguousarray(scores, dtype=np.float64)
+    n_tok = len(table.tokens)
+    views = [np.frombuffer(b, dtype=np.uint8) for b in table.tokens]
+    tok_ptr = (C.c_void_p * n_tok)(*[v.ctypes.data if len(v) else None for v in views])
+    tok_len = np.array([len(b) for b in table.tokens], dtype=np.uint64)
+    chroms = [c.encode("utf-8") for c in table.chroms]
+    chrom_ptr = (C.c_char_p * n_tok)(*chroms)
+    chrom_len = np.array([len(c) for c in chroms], dtype=np.uint32)
+    cap = count * (96 + 4 * table.guide_len + 2 * int(chrom_len.max(initial=0)))
+    for _ in range(2):
+        out = np.empty(cap, dtype=np.uint8)
+        need = C.c_uint64(0)
+        rc = lib.crp_format_rows(count, id_bytes.ctypes.data, id_index.ctypes.data, tok.ctypes.data, t.ctypes.data,
+                                 minus.ctypes.data, ok.ctypes.data, sc.ctypes.data, n_tok, tok_ptr, tok_len.ctypes.data,
+                                 chrom_ptr, chrom_len.ctypes.data, int(table.guide_len), int(n_threads),
+                                 out.ctypes.data, cap, C.byref(need))
+        if rc == -5:
+            cap = need.value
+            continue
+        check(rc)
+        return out[:need.value].tobytes()
+    raise RuntimeError("crp_format_rows: capacity negotiation failed")
+
+
 def write_header(path):
     with open(path, "w", newline="") as f:
         csv.writer(f).writerow(HEADER)
@@ -192,11 +230,10 @@ def emit_cumulative(path, table, genome, blas_threads=1):
     chunk plan.  Returns the number of rows written."""
     size = len(table)
     written = 0
-    with open(path, "a", newline="") as f:
-        w = csv.writer(f)
-        ids = ids_to_strings(get_id(size))
+    with open(path, "ab") as f:
+        ids = get_id(size)
         for start, count in emission_slices(size):
             scores, scored = slice_scores(table, genome, start, count, blas_threads)
-            w.writerows(slice_rows(table, ids, scores, scored, start, count))
+            f.write(format_rows(table, ids, scores, scored, start, count))
             written += count
     return written

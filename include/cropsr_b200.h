@@ -179,6 +179,18 @@ int crp_result_extras(const crp_result *res, uint32_t segment, char strand, uint
 int crp_result_annotate(const crp_result *res, uint32_t segment, char strand, uint32_t n_intervals,
                         const uint32_t *start, const uint32_t *end, int32_t *feature);
 
+/* ---- host-side row formatter: replaces the per-row tuple + csv.writer path of
+ * CROPSR.py:463-474.  Writes n_rows CSV rows (excel dialect, "\r\n", repr() floats,
+ * the 11-field error-row variant where scored[i] == 0) into `out`, byte-identical
+ * to the reference's writer; multi-threaded, no GPU involved.  Row i is the
+ * candidate (token_of[i], t[i], minus[i]) with id ids[7 * id_index[i] .. +7).
+ * Returns CRP_ERR_RANGE (and the size needed in *out_bytes) if out is too small. */
+int crp_format_rows(uint64_t n_rows, const char *ids, const uint64_t *id_index, const uint32_t *token_of,
+                    const uint32_t *t, const uint8_t *minus, const uint8_t *scored, const double *score,
+                    uint32_t n_tokens, const uint8_t *const *tokens, const uint64_t *token_len,
+                    const char *const *chrom, const uint32_t *chrom_len, int guide_len, int n_threads,
+                    char *out, uint64_t out_capacity, uint64_t *out_bytes);
+
 /* Kernel timings (CUDA events on the library stream) of the last commit /
  * scan: milliseconds. */
 int crp_genome_timing(const crp_genome *g, float *ms_h2d, float *ms_pack);

@@ -137,7 +137,7 @@ def test_gff_intervals_per_token(built_lib):
     gff = os.path.join(os.path.dirname(__file__), "golden", "fixtures", "sample_genome.gff")
     frame = ingest.import_gff_file(gff)
     chrom = frame.loc[frame["feature"] == "gene", "chromosome"].iloc[0]     # the #! header lines are junk rows
-    for formatted, key in ((True, f"('{chrom}',"), (False, f">{chrom}")):
+    for formatted, key in ((True, f"[('{chrom}',"), (True, f"('{chrom}',"), (False, f">{chrom}")):     # first / later record
         iv, = annotate.intervals_for_tokens(frame, [key], formatted, features=("gene",))
         genes = frame[(frame["feature"] == "gene") & (frame["chromosome"] == chrom)]
         assert len(iv["start"]) == len(genes) > 0
@@ -147,3 +147,59 @@ def test_gff_intervals_per_token(built_lib):
         assert set(frame.loc[iv["row"], "feature"]) == {"gene"}
     none, = annotate.intervals_for_tokens(frame, [">not_there"], False)
     assert len(none["start"]) == 0
+
+
+def _table_from_oracle(text, guide_len):
+    import cropsr_oracle as oracle
+    from cropsr_b200 import emit, ingest
+    tokens = ingest.fasta_text_to_tokens(text)
+    table = emit.CandidateTable(guide_len)
+    for seg, (key, tok) in enumerate(tokens.items()):
+        plus, minus = oracle.pam_hits(tok, guide_len)
+        table.append_token(key, tok.encode(), seg, np.array(plus, np.uint32), None, np.array(minus, np.uint32), None)
+    return table
+
+
+@pytest.mark.parametrize("fasta,guide_len", [("edge_fmt.fa", 20), ("edge_clean.fa", 20), ("multi3.fa", 18),
+                                             ("mid50k.fa", 20), ("ws_header.fa", 20)])
+def test_c_row_formatter_equals_python_csv_writer(built_lib, fasta, guide_len):
+    """csrc/emit_csv.cpp vs the literal Python row tuples + csv.writer: quoting of decoration
+    bytes, truncated windows / 11-field error rows, repr() of the scores, id reverse indexing."""
+    import csv, io
+    from cropsr_b200 import emit
+    from helpers import fixture_text
+    table = _table_from_oracle(fixture_text(fasta), guide_len)
+    n = len(table)
+    assert n > 0
+    rng = np.random.default_rng(3)
+    np.random.seed(4)
+    ids = emit.get_id(n)
+    scored = emit.long_length(table, np.arange(n)) == 30
+    scores = 1 / (1 + np.exp(rng.uniform(-18, 9, n)))
+    scores[::7] = 10.0 ** rng.uniform(-300, 300, len(scores[::7]))         # exercise the exponent layouts too
+    scores[~scored] = np.nan
+    for start, count in ((0, n), (n // 3, n - n // 3), (n - 1, 1)):
+        want = io.StringIO(newline="")
+        csv.writer(want).writerows(emit.slice_rows(table, emit.ids_to_strings(ids), scores[start:start + count],
+                                                   scored[start:start + count], start, count))
+        for threads in (1, 3):
+            got = emit.format_rows(table, ids, scores[start:start + count], scored[start:start + count], start, count,
+                                   n_threads=threads)
+            assert got == want.getvalue().encode()
+
+
+def test_c_float_repr_matches_python(built_lib):
+    """repr(float) of the formatter on many values: shortest round-trip digits, fixed vs exponent."""
+    import ctypes as C
+    from cropsr_b200 import emit
+    rng = np.random.default_rng(5)
+    vals = np.concatenate([1 / (1 + np.exp(rng.uniform(-20, 10, 60000))), 10.0 ** rng.uniform(-320, 308, 30000),
+                           2.0 ** rng.integers(-1074, 1023, 4000).astype(np.float64), np.ldexp(rng.random(4000), -1070),
+                           np.array([0.5, 1.0, 1e16, 1e15, 9007199254740992.0, 0.0001, 0.00001, 5e-324, 1.7976931348623157e308,
+                                     123456789012345.0, 1e22, 1e23, 0.1, 0.2 + 0.1])])
+    table = emit.CandidateTable(20)
+    tok = b"A" * 40 + b"GG" + b"A" * 40
+    table.append_token(">c", tok, 0, np.full(len(vals), 39, np.uint32), None, np.empty(0, np.uint32), None)
+    ids = np.full((len(vals), 7), "A", dtype="<U1")
+    got = emit.format_rows(table, ids, vals, np.ones(len(vals), bool), 0, len(vals)).decode().split("\r\n")[:-1]
+    assert [row.split(",")[9] for row in got] == [repr(float(v)) for v in vals]
