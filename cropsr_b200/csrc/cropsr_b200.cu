@@ -24,6 +24,7 @@
 #define CRP_CTAS_PER_SM 4
 #endif
 #include "scan.cuh"
+#include "scan_sp.cuh"
 #include "extras.cuh"
 
 #define CRP_ABI_VERSION 3
@@ -78,6 +79,10 @@ struct crp_genome {
     uint32_t n_tiles = 0;
     uint32_t *d_seg_first = nullptr, *d_seg_count = nullptr;
     float ms_h2d = 0.f, ms_pack = 0.f;
+    // state of the single-pass scan kernel (scan_sp.cuh): zeroed once at commit, then only
+    // ever advanced by the launches, which are ordered on the genome's stream
+    unsigned char *sp_state = nullptr;         // agg[n_tiles] | incl[n_tiles] | ctl[2]
+    mutable uint32_t sp_epoch = 0, sp_ticket = 0, sp_done = 0;
 };
 
 struct crp_result {
@@ -340,6 +345,15 @@ static int commit_enqueue(crp_genome *g) {
         return fail(CRP_ERR_NOMEM, "cudaMalloc of %llu record bytes + %llu staging bytes failed",
                     (unsigned long long)rec_bytes, (unsigned long long)ascii_bytes);
     }
+    {
+        const size_t sp_bytes = (size_t)g->n_tiles * (sizeof(unsigned long long) + sizeof(ulonglong2)) + 48;
+        if (dev_alloc(&g->sp_state, sp_bytes, st) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(CRP_ERR_NOMEM, "cudaMalloc of %llu bytes of scan state failed", (unsigned long long)sp_bytes);
+        }
+        CUDA_TRY(cudaMemsetAsync(g->sp_state, 0, sp_bytes, st));
+        g->sp_epoch = g->sp_ticket = g->sp_done = 0;
+    }
     for (int i = 0; i < 3; ++i)
         if (!g->ev[i]) CUDA_TRY(cudaEventCreate(&g->ev[i]));
     CUDA_TRY(cudaEventRecord(g->ev[0], st));
@@ -401,6 +415,7 @@ int crp_genome_free(crp_genome *g) {
     if (!g) return 0;
     cudaStream_t st = stream_of(g);
     dev_free(g->records, st);
+    dev_free(g->sp_state, st);
     dev_free(g->d_seg_first, st);
     dev_free(g->d_seg_count, st);
     for (cudaEvent_t e : g->ev)
@@ -475,7 +490,77 @@ static int plan_scan(const crp_genome *g, bool scored, ScanPlan *p) {
     return 0;
 }
 
+// CRP_SCAN_KERNEL=sp selects the experimental single-pass kernel (scan_sp.cuh); the default
+// is the two-phase cooperative kernel (scan.cuh), which is faster
+static bool use_single_pass() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CRP_SCAN_KERNEL");
+        v = (e && !strcmp(e, "sp")) ? 1 : 0;
+    }
+    return v == 1;
+}
+
+// single-pass kernel (scan_sp.cuh): one CTA of 4 teams per SM, ordinary launch
+static int launch_scan_sp(const crp_genome *g, crp_result *r) {
+    cudaStream_t st = r->st;
+    const void *fn = r->scored ? (const void *)k_scan_sp<true> : (const void *)k_scan_sp<false>;
+    const size_t tab = r->scored ? (kRs1TableBytes + 127) / 128 * 128 : 0;
+    const size_t smem = tab + kTeams * kTeamBytes;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[r->scored ? 1 : 0]) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[r->scored ? 1 : 0] = true;
+    }
+    const uint32_t n_seg = (uint32_t)g->segs.size();
+    unsigned grid = (unsigned)g_ctx.sm_count;
+    const unsigned want = (g->n_tiles + kTeams - 1) / kTeams;
+    if (grid > want) grid = want;
+    SpArgs a;
+    a.records = g->records;
+    a.n_tiles = g->n_tiles;
+    a.guide_len = r->guide_len;
+    a.flags = r->flags;
+    if (const char *e = getenv("CRP_SP_DEBUG")) a.flags |= (uint32_t)strtoul(e, nullptr, 0);
+    g->sp_epoch = g->sp_epoch % 255u + 1u;
+    a.epoch = g->sp_epoch;
+    a.ticket_base = g->sp_ticket;
+    a.done_base = g->sp_done;
+    g->sp_ticket += g->n_tiles + 2u * grid * kTeams;      // every team draws (tiles it scans + 2) tickets
+    g->sp_done += g->n_tiles;
+    a.tables = g_ctx.d_tables;
+    a.capacity = r->capacity;
+    a.pos_plus = r->pos[0];
+    a.pos_minus = r->pos[1];
+    a.packed_plus = r->packed[0];
+    a.packed_minus = r->packed[1];
+    a.x_plus = r->x[0];
+    a.x_minus = r->x[1];
+    a.agg = reinterpret_cast<unsigned long long *>(g->sp_state);
+    a.incl = reinterpret_cast<ulonglong2 *>(g->sp_state + ((size_t)g->n_tiles * sizeof(unsigned long long) + 15) / 16 * 16);
+    a.ctl = reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned char *>(a.incl) + (size_t)g->n_tiles * sizeof(ulonglong2));
+    a.seg_counts = r->d_counts;
+    a.seg_first_tile = g->d_seg_first;
+    a.seg_tile_count = g->d_seg_count;
+    a.n_seg = n_seg;
+    CUDA_TRY(cudaEventRecord(r->ev[0], st));
+    if (g->n_tiles) {
+        void *params[] = {(void *)&a};
+        CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(kSpThreads), params, smem, st));
+        g_ctx.launches++;
+        CUDA_TRY(cudaGetLastError());
+    } else if (n_seg) {
+        CUDA_TRY(cudaMemsetAsync(r->d_counts, 0, 2 * (size_t)n_seg * sizeof(unsigned long long), st));
+    }
+    CUDA_TRY(cudaEventRecord(r->ev[1], st));
+    if (n_seg)
+        CUDA_TRY(cudaMemcpyAsync(r->h_counts, r->d_counts, 2 * (size_t)n_seg * sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
 static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p) {
+    if (use_single_pass()) return launch_scan_sp(g, r);
     cudaStream_t st = r->st;
     ScanArgs a;
     a.records = g->records;
