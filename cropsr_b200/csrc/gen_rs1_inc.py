@@ -17,10 +17,13 @@ This script emits
   * RS1_LANE_SUMS -- the device code that evaluates the 8 lanes.
 
 Hash of a lane (chosen for the instruction mix of the scan kernel, whose
-bottleneck is the integer ALU pipe): one IMAD.HI per group of match bits on the
-FMA pipe, one AND,
-    byte offset = (sum_g umulhi(bits_g, magic_g)) & (((1 << bits) - 1) << 3)
-i.e. bits [35, 35 + bits) of the 64-bit products, already scaled to doubles.
+bottleneck is the integer ALU pipe): one AND per group of match bits, then only
+multiplies, which run on the FMA pipe,
+    slot = (sum_g bits_g * magic_g  mod 2^32) >> (32 - bits)
+the shift written as a multiply-high by 2^bits.  Dinucleotide match bits are
+(first-base mask << 1) & second-base mask, so that the shift is a multiply too.
+Entries that can never match a scanned 30-mer (its bases 2 and 3 are the PAM's
+upper-case CC) are dropped; the two that always match are folded into the table.
 
 Tail entries cost one AND and one DFMA: the match bit p (>= 20) of the class
 mask, used as the HIGH word of a double, is the power of two 2^(2^(p-20) - 1023);
@@ -41,47 +44,71 @@ rs1 = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(rs1)
 
 BASES = rs1.BASES
-MAX_TABLE_ENTRIES = 10          # leading entries of a lane covered by its table
-TABLE_ENTRIES = {"fG": 9}       # per-lane override (keeps every table at <= 1024 doubles)
-FIELD_SHIFT = 3                 # index field sits at bits [3, 3 + bits) of the summed high words
+A, T, C, G = 0, 1, 2, 3
+MAX_TABLE_ENTRIES = 10          # leading free entries of a lane covered by its table
+TABLE_ENTRIES = {"fG": 9}       # per-lane override (keeps the tables of one CTA at ~25 KB)
+# Every 30-mer the scan scores carries the PAM the way the reference orients it: '+' windows
+# are reverse-complemented (.GG -> CC.), '-' windows are read forwards (CC.), so bases 2 and 3
+# are upper-case C on both strands (CROPSR.py:415-433; tests/test_oracle_golden.py pins it).
+KNOWN = {2: C, 3: C}
 
 
 def lanes():
+    """-> [(name, lane base, entries)], entries = (pos, first base or None, weight, forced) in
+    ascending column order; entries that cannot match a scanned 30-mer are dropped, entries
+    that always match are `forced` (always added, no hash bit)."""
     out = []
     for c, name in enumerate(BASES):
-        out.append(("f" + name, c, [(p, None, v) for (p, cc), v in sorted(rs1.FIRST.items()) if cc == c]))
+        ents = []
+        for (p, cc), v in sorted(rs1.FIRST.items()):
+            if cc != c:
+                continue
+            if p in KNOWN and KNOWN[p] != c:
+                continue
+            ents.append((p, None, v, p in KNOWN))
+        out.append(("f" + name, c, ents))
     for c, name in enumerate(BASES):
-        out.append(("d" + name, c, [(p, c1, v) for (p, c1, c2), v in sorted(rs1.SECOND.items()) if c2 == c]))
+        ents = []
+        for (p, c1, c2), v in sorted(rs1.SECOND.items()):
+            if c2 != c:
+                continue
+            if (p in KNOWN and KNOWN[p] != c1) or (p + 1 in KNOWN and KNOWN[p + 1] != c2):
+                continue
+            ents.append((p, c1, v, p in KNOWN and p + 1 in KNOWN))
+        out.append(("d" + name, c, ents))
     return out
+
+
+def bit_of(entry):
+    p, c1, _, _ = entry
+    return p if c1 is None else p + 1       # pair bits: first-base mask shifted left by one
 
 
 def valid_states(entries):
     by_pos = {}
-    for i, (p, c1, _) in enumerate(entries):
-        by_pos.setdefault(p, []).append(i)
+    for i, e in enumerate(entries):
+        by_pos.setdefault(e[0], []).append(i)
     opts = [[()] + [(i,) for i in idxs] for idxs in by_pos.values()]
     for combo in itertools.product(*opts):
         yield tuple(sorted(i for t in combo for i in t))
 
 
 def find_hash(entries, seed):
-    """Smallest index width with an injective hash
-        h = sum over first-base groups of (umulhi(x_g, hi_g) + x_g * lo_g)   (mod 2^32)
-    whose bits [3, 3 + bits) are the table slot.  lo_g is tried as 0 first (one multiply
-    per group); match bits below position 4 cannot reach the field through the high word,
-    so lanes that have them need the low product as well."""
+    """Smallest index width with an injective multiplicative hash
+        slot = (sum over first-base groups of x_g * magic_g  mod 2^32) >> (32 - bits)
+    over every state the free table entries can take."""
     groups = {}
-    for i, (p, c1, _) in enumerate(entries):
-        groups.setdefault(c1, []).append(i)
+    for i, e in enumerate(entries):
+        groups.setdefault(e[1], []).append(i)
     glist = list(groups.items())
     states = list(valid_states(entries))
     pat = np.zeros((len(glist), len(states)), dtype=np.uint64)
-    for si, s in enumerate(states):
+    for si, st in enumerate(states):
         for gi, (_, idxs) in enumerate(glist):
-            pat[gi, si] = sum(1 << entries[i][0] for i in s if i in idxs)
-    need = int(np.ceil(np.log2(len(states))))
+            pat[gi, si] = sum(1 << bit_of(entries[i]) for i in st if i in idxs)
+    need = max(int(np.ceil(np.log2(len(states)))), 1)
     rng = np.random.default_rng(seed)
-    batch = 1024
+    batch = 2048
     m32 = np.uint64(0xFFFFFFFF)
 
     def sparse():
@@ -91,25 +118,20 @@ def find_hash(entries, seed):
         return m
 
     for bits in (need, need + 1, need + 2):
-        field = np.uint64((1 << bits) - 1)
-        for with_lo in (False, True):
-            for t in range(1500 if bits == need else 400):
-                acc = np.zeros((batch, len(states)), dtype=np.uint64)
-                his, los = [], []
-                for gi in range(len(glist)):
-                    hi = sparse()
-                    lo = sparse() if with_lo else np.zeros(batch, dtype=np.uint64)
-                    his.append(hi)
-                    los.append(lo)
-                    acc += (pat[gi][None, :] * hi[:, None]) >> np.uint64(32)
-                    acc += (pat[gi][None, :] * lo[:, None]) & m32
-                h = (acc >> np.uint64(FIELD_SHIFT)) & field
-                h.sort(axis=1)
-                ok = (np.diff(h.astype(np.int64), axis=1) != 0).all(axis=1)
-                if ok.any():
-                    k = int(np.argmax(ok))
-                    return bits, [(c1, sum(1 << entries[i][0] for i in idxs), int(his[gi][k]), int(los[gi][k]))
-                                  for gi, (c1, idxs) in enumerate(glist)]
+        for t in range(4000 if bits == need else 500):
+            acc = np.zeros((batch, len(states)), dtype=np.uint64)
+            mags = []
+            for gi in range(len(glist)):
+                mg = sparse()
+                mags.append(mg)
+                acc += (pat[gi][None, :] * mg[:, None]) & m32
+            h = (acc & m32) >> np.uint64(32 - bits)
+            h.sort(axis=1)
+            ok = (np.diff(h.astype(np.int64), axis=1) != 0).all(axis=1) if len(states) > 1 else np.ones(batch, bool)
+            if ok.any():
+                k = int(np.argmax(ok))
+                return bits, [(c1, sum(1 << bit_of(entries[i]) for i in idxs), int(mags[gi][k]))
+                              for gi, (c1, idxs) in enumerate(glist)]
     raise SystemExit("no perfect hash found")
 
 
@@ -128,37 +150,44 @@ def main():
     emit("#define RS1_DENSE_SECOND { " + ", ".join(hexf(v) if v else "0.0" for v in w2) + " }")
 
     # ---- lane descriptors for the host-side table builder
-    emit("struct Rs1Entry { int pos; int first_base; double weight; };     // first_base < 0: first-order term")
-    emit("struct Rs1Group { int first_base; unsigned mask; unsigned magic_hi; unsigned magic_lo; };")
-    emit("// table slot of a set of matching entries = ((sum over groups of umulhi(x_g, magic_hi) + x_g * magic_lo) >> 3) & (2^bits - 1)")
+    emit("// bit: position of the entry's match bit (first order: p; dinucleotide: p + 1, the first-base mask is")
+    emit("// shifted left by one); forced: the entry matches every scanned 30-mer (PAM bases) and has no bit")
+    emit("struct Rs1Entry { int pos; int first_base; double weight; int bit; int forced; };     // first_base < 0: first-order term")
+    emit("struct Rs1Group { int first_base; unsigned mask; unsigned magic; };")
+    emit("// table slot of a set of matching entries = (sum over groups of x_g * magic  mod 2^32) >> (32 - bits)")
     emit("struct Rs1Lane { const char *name; int lane_base; int n_entries; int n_table; int bits; int offset; "
          "int n_groups; Rs1Group groups[4]; Rs1Entry entries[16]; };")
     descs, code, offset, consts = [], [], 0, []
     mask_name = {0: "mA", 1: "mT", 2: "mC", 3: "mG"}
-    next_name = {0: "nA", 1: "nT", 2: "nC", 3: "nG"}
+    shift_name = {0: "sA", 1: "sT", 2: "sC", 3: "sG"}
     for li, (name, base, entries) in enumerate(lanes()):
-        n_table = min(len(entries), TABLE_ENTRIES.get(name, MAX_TABLE_ENTRIES))
+        free = [e for e in entries if not e[3]]
+        n_free_table = min(len(free), TABLE_ENTRIES.get(name, MAX_TABLE_ENTRIES))
         # never split a group of mutually exclusive entries (same position) across table / tail
-        while n_table < len(entries) and n_table > 0 and entries[n_table][0] == entries[n_table - 1][0]:
-            n_table -= 1
-        bits, groups = find_hash(entries[:n_table], seed=100 + li)
-        ents = ", ".join(f"{{{p}, {-1 if c1 is None else c1}, {hexf(v)}}}" for p, c1, v in entries)
-        grps = ", ".join(f"{{{-1 if c1 is None else c1}, 0x{m:x}u, 0x{mh:x}u, 0x{ml:x}u}}" for c1, m, mh, ml in groups)
+        while 0 < n_free_table < len(free) and free[n_free_table][0] == free[n_free_table - 1][0]:
+            n_free_table -= 1
+        table_free = free[:n_free_table]
+        tail = free[n_free_table:]
+        assert all(e[0] < (tail[0][0] if tail else 99) for e in entries if e[3]), "forced entry after a tail entry"
+        bits, groups = find_hash(table_free, seed=100 + li)
+        n_table = len(entries) - len(tail)          # forced + tabulated entries come first
+        ents = ", ".join(f"{{{p}, {-1 if c1 is None else c1}, {hexf(v)}, {bit_of((p, c1, v, f))}, {int(f)}}}"
+                         for p, c1, v, f in entries)
+        grps = ", ".join(f"{{{-1 if c1 is None else c1}, 0x{m:x}u, 0x{mg:x}u}}" for c1, m, mg in groups)
         descs.append(f'    {{"{name}", {base}, {len(entries)}, {n_table}, {bits}, {offset}, {len(groups)}, {{{grps}}}, {{{ents}}}}}')
         # ---- device code of this lane
         second = name[0] == "d"
         terms = []
-        for c1, m, mh, ml in groups:
-            src = f"{mask_name[c1]} & {next_name[base]} & 0x{m:x}u" if second else f"{mask_name[base]} & 0x{m:x}u"
-            terms.append(f"__umulhi({src}, 0x{mh:x}u)")
-            if ml:
-                terms.append(f"({src}) * 0x{ml:x}u")
-        code.append(f"    double {name} = RS1_LD(T, {8 * offset}u, (" + " + ".join(terms) + f") & 0x{((1 << bits) - 1) << FIELD_SHIFT:x}u);")
-        for p, c1, v in entries[n_table:]:
+        for c1, m, mg in groups:
+            src = f"({shift_name[c1]} & {mask_name[base]} & 0x{m:x}u)" if second else f"({mask_name[base]} & 0x{m:x}u)"
+            terms.append(f"{src} * 0x{mg:x}u")
+        code.append(f"    double {name} = RS1_LD(T, {offset}u, RS1_TOP(" + " + ".join(terms) + f", {bits}));")
+        for p, c1, v, _ in tail:
             # entries at one position are mutually exclusive: at most one of the fma's adds a non-zero
-            assert p >= 20, "tail entry below bit 20: extend the generator with a shift"
-            e = 1 << (p - 20)
-            cond = f"{mask_name[c1]} & {next_name[base]} & 0x{1 << p:x}u" if second else f"{mask_name[base]} & 0x{1 << p:x}u"
+            b = bit_of((p, c1, v, False))
+            assert b >= 20, "tail entry below bit 20: extend the generator with a shift"
+            e = 1 << (b - 20)
+            cond = f"{shift_name[c1]} & {mask_name[base]} & 0x{1 << b:x}u" if second else f"{mask_name[base]} & 0x{1 << b:x}u"
             code.append(f"    {name} = RS1_FMA_BIT({cond}, RS1_K({len(consts)}), {name});   // {v!r} * 2^{1023 - e}")
             consts.append(hexf(v * 2.0 ** (1023 - e)))
         offset += 1 << bits
@@ -175,7 +204,7 @@ def main():
     emit("// and scores), T = the lane tables in shared memory.  Lane tables cover the leading")
     emit("// entries of each lane; the few remaining ones are added in order.")
     emit("#define RS1_LANE_SUMS(T, mA, mT, mC, mG) \\")
-    body = ["    const uint32_t nA = (mA) >> 1, nT = (mT) >> 1, nC = (mC) >> 1, nG = (mG) >> 1;"] + code
+    body = ["    const uint32_t sA = RS1_SHL1(mA), sT = RS1_SHL1(mT), sC = RS1_SHL1(mC), sG = RS1_SHL1(mG);"] + code
     emit(" \\\n".join(line.split("   // ")[0] for line in body))
     print("\n".join(out))
 

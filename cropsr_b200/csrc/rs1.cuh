@@ -28,8 +28,11 @@ static constexpr size_t kRs1TableBytes = (size_t)RS1_TABLE_DOUBLES * sizeof(doub
 __constant__ double c_rs1_k[] = RS1_K_VALUES;
 #define RS1_K(i) c_rs1_k[i]
 
-// lane table entry at a byte offset that is already a multiple of 8 (see gen_rs1_inc.py)
-#define RS1_LD(T, lane_off, byte_idx) (*reinterpret_cast<const double *>(reinterpret_cast<const char *>(T) + (lane_off) + (byte_idx)))
+// lane table entry: `off` doubles into the tables, slot idx
+#define RS1_LD(T, off, idx) (*reinterpret_cast<const double *>(reinterpret_cast<const char *>(T) + 8u * (off) + 8u * (idx)))
+// top `bits` bits of the hash as a multiply-high (FMA pipe; a shift would go to the ALU pipe)
+#define RS1_TOP(h, bits) __umulhi((h), 1u << (bits))
+#define RS1_SHL1(m) ((m) << 1)
 // acc + w iff the match bit is set, as ONE DFMA: bit (a single bit p >= 20 of a class mask)
 // read as the high word of a double is a power of two, w_scaled = w / that power.
 #define RS1_FMA_BIT(bit, w_scaled, acc) __fma_rn(__hiloint2double((int)(bit), 0), (w_scaled), (acc))
@@ -44,28 +47,41 @@ __device__ __forceinline__ double rs1_canonical(const double *__restrict__ T, ui
     return -__dadd_rn(__dadd_rn(__dadd_rn(first, second), RS1_K(RS1_K_INTERCEPT)), RS1_K(RS1_K_LOW_GC));
 }
 
-// Host side: exact sequential sums of every valid subset of each lane's table entries.
+// Host side: exact sequential sums of every valid subset of each lane's table entries
+// (forced entries -- the PAM bases -- are part of every sum).
 static int build_rs1_tables(std::vector<double> &tab, char *err, size_t errlen) {
     tab.assign(RS1_TABLE_DOUBLES, 0.0);
     std::vector<char> used(RS1_TABLE_DOUBLES, 0);
     for (const Rs1Lane &ln : kRs1Lanes) {
-        for (uint32_t sub = 0; sub < (1u << ln.n_table); ++sub) {
+        int free_idx[16], n_free = 0;
+        for (int i = 0; i < ln.n_table; ++i)
+            if (!ln.entries[i].forced) free_idx[n_free++] = i;
+        for (uint32_t sub = 0; sub < (1u << n_free); ++sub) {
             bool ok = true;                       // two entries at one position are mutually exclusive
-            for (int i = 0; i < ln.n_table && ok; ++i)
-                for (int j = i + 1; j < ln.n_table; ++j)
-                    if ((sub >> i & 1) && (sub >> j & 1) && ln.entries[i].pos == ln.entries[j].pos) ok = false;
+            for (int i = 0; i < n_free && ok; ++i)
+                for (int j = i + 1; j < n_free; ++j)
+                    if ((sub >> i & 1) && (sub >> j & 1) && ln.entries[free_idx[i]].pos == ln.entries[free_idx[j]].pos)
+                        ok = false;
             if (!ok) continue;
             uint32_t h = 0;
-            volatile double sum = 0.0;            // one IEEE add per entry, in ascending column order
             for (int g = 0; g < ln.n_groups; ++g) {
                 uint32_t x = 0;                   // match bits of this first-base group
-                for (int i = 0; i < ln.n_table; ++i)
-                    if ((sub >> i & 1) && ln.groups[g].first_base == ln.entries[i].first_base) x |= 1u << ln.entries[i].pos;
-                h += (uint32_t)(((unsigned long long)x * ln.groups[g].magic_hi) >> 32) + x * ln.groups[g].magic_lo;
+                for (int i = 0; i < n_free; ++i) {
+                    const Rs1Entry &e = ln.entries[free_idx[i]];
+                    if ((sub >> i & 1) && ln.groups[g].first_base == e.first_base) x |= 1u << e.bit;
+                }
+                if (x & ~ln.groups[g].mask) {
+                    snprintf(err, errlen, "rs1 lane %s: entry outside its group mask", ln.name);
+                    return -1;
+                }
+                h += x * ln.groups[g].magic;
             }
-            for (int i = 0; i < ln.n_table; ++i)
-                if (sub >> i & 1) sum = sum + ln.entries[i].weight;
-            const uint32_t slot = (h >> 3) & ((1u << ln.bits) - 1u);
+            volatile double sum = 0.0;            // one IEEE add per entry, in ascending column order
+            for (int i = 0, f = 0; i < ln.n_table; ++i) {
+                const bool on = ln.entries[i].forced ? true : ((sub >> f++) & 1);
+                if (on) sum = sum + ln.entries[i].weight;
+            }
+            const uint32_t slot = ln.bits ? h >> (32 - ln.bits) : 0u;
             const uint32_t idx = ln.offset + slot;
             if (idx >= RS1_TABLE_DOUBLES || used[idx]) {
                 snprintf(err, errlen, "rs1 table hash of lane %s is not injective", ln.name);

@@ -138,34 +138,6 @@ __device__ __forceinline__ void look_back(const SpArgs &a, uint32_t tile, int la
     }
 }
 
-// the first two hits of a word straight-line (a 32-position word holds more than two hits of a
-// strand in a few percent of the words), the rest in a loop; slots ascend with the position
-__device__ __forceinline__ void list_hits_sp(uint16_t *__restrict__ first, uint32_t m, uint32_t pos0) {
-    const uint32_t l0 = m & (0u - m);
-    if (m) first[0] = (uint16_t)(pos0 + 31u - (uint32_t)__clz(l0));
-    m ^= l0;
-    const uint32_t l1 = m & (0u - m);
-    if (m) first[1] = (uint16_t)(pos0 + 31u - (uint32_t)__clz(l1));
-    m ^= l1;
-    first += 2;
-    while (m) {
-        const uint32_t lb = m & (0u - m);
-        *first++ = (uint16_t)(pos0 + 31u - (uint32_t)__clz(lb));
-        m ^= lb;
-    }
-}
-// same, for a tile with more than kListCap hits on a strand: only ranks [lo, lo + kListCap)
-__device__ __forceinline__ void list_hits_window_sp(uint16_t *__restrict__ list, uint32_t m, uint32_t rank_first,
-                                                    uint32_t pos0, uint32_t lo) {
-    uint32_t r = rank_first;
-    while (m) {
-        const uint32_t lb = m & (0u - m);
-        if (r - lo < (uint32_t)kListCap) list[r - lo] = (uint16_t)(pos0 + 31u - (uint32_t)__clz(lb));
-        m ^= lb;
-        ++r;
-    }
-}
-
 // one thread per listed hit of one strand of a tile: window, score, coalesced stores
 template <bool kScore, bool kMinus>
 __device__ __forceinline__ void emit_strand_sp(const SpArgs &a, const double *__restrict__ tab,
@@ -274,10 +246,10 @@ k_scan_sp(const SpArgs a) {
         const uint32_t fA = off + iA - cA, fB = off + totA + iB - cB;
         const bool sparse = np <= (uint32_t)kListCap && nm <= (uint32_t)kListCap;
         if (sparse) {
-            list_hits_sp(list_p + (fA & 0xFFFFu), h.pA, 32u * wordA);
-            list_hits_sp(list_p + (fB & 0xFFFFu), h.pB, 32u * (wordA + 32));
-            list_hits_sp(list_m + (fA >> 16), h.mA, 32u * wordA);
-            list_hits_sp(list_m + (fB >> 16), h.mB, 32u * (wordA + 32));
+            list_hits(list_p + (fA & 0xFFFFu), h.pA, 32u * wordA);
+            list_hits(list_p + (fB & 0xFFFFu), h.pB, 32u * (wordA + 32));
+            list_hits(list_m + (fA >> 16), h.mA, 32u * wordA);
+            list_hits(list_m + (fB >> 16), h.mB, 32u * (wordA + 32));
         }
         if (warp == 0) {
             unsigned long long bp = 0, bm = 0;
@@ -315,10 +287,10 @@ k_scan_sp(const SpArgs a) {
                 const uint32_t cp = np > lo ? min(np - lo, (uint32_t)kListCap) : 0u;
                 const uint32_t cm = nm > lo ? min(nm - lo, (uint32_t)kListCap) : 0u;
                 if (lo) team_sync(team);
-                list_hits_window_sp(list_p, h.pA, fA & 0xFFFFu, 32u * wordA, lo);
-                list_hits_window_sp(list_p, h.pB, fB & 0xFFFFu, 32u * (wordA + 32), lo);
-                list_hits_window_sp(list_m, h.mA, fA >> 16, 32u * wordA, lo);
-                list_hits_window_sp(list_m, h.mB, fB >> 16, 32u * (wordA + 32), lo);
+                list_hits_window(list_p, h.pA, fA & 0xFFFFu, 32u * wordA, lo);
+                list_hits_window(list_p, h.pB, fB & 0xFFFFu, 32u * (wordA + 32), lo);
+                list_hits_window(list_m, h.mA, fA >> 16, 32u * wordA, lo);
+                list_hits_window(list_m, h.mB, fB >> 16, 32u * (wordA + 32), lo);
                 team_sync(team);
                 emit_strand_sp<kScore, false>(a, s_tab, rec, list_p, cp, base_p + lo, td.t_start, td.L, ttid);
                 emit_strand_sp<kScore, true>(a, s_tab, rec, list_m, cm, base_m + lo, td.t_start, td.L, ttid);
