@@ -65,7 +65,7 @@ def lanes():
                 continue
             if p in KNOWN and KNOWN[p] != c:
                 continue
-            ents.append((p, None, v, p in KNOWN))
+            ents.append((p, None, v, p in KNOWN, c))
         out.append(("f" + name, c, ents))
     for c, name in enumerate(BASES):
         ents = []
@@ -74,13 +74,13 @@ def lanes():
                 continue
             if (p in KNOWN and KNOWN[p] != c1) or (p + 1 in KNOWN and KNOWN[p + 1] != c2):
                 continue
-            ents.append((p, c1, v, p in KNOWN and p + 1 in KNOWN))
+            ents.append((p, c1, v, p in KNOWN and p + 1 in KNOWN, c))
         out.append(("d" + name, c, ents))
     return out
 
 
 def bit_of(entry):
-    p, c1, _, _ = entry
+    p, c1 = entry[0], entry[1]
     return p if c1 is None else p + 1       # pair bits: first-base mask shifted left by one
 
 
@@ -93,10 +93,51 @@ def valid_states(entries):
         yield tuple(sorted(i for t in combo for i in t))
 
 
-def find_hash(entries, seed):
+GC_MODEL = 0.42                 # base composition of the Monte-Carlo that ranks hash candidates
+SEQUENTIAL_MAX = 3               # lanes with at most this many entries are summed without a table
+SWIZZLE_MIN_BITS = 6            # lanes with at least this many index bits xor their top 4 hash bits into the slot              # bit-flip hill climbing on the best candidate
+N_CANDIDATES = 24               # injective hashes collected per lane before the best one is kept
+
+
+def sample_states(entries, rng, n):
+    """n random states of the free table entries under i.i.d. bases: -> list of index tuples"""
+    f = {A: (1 - GC_MODEL) / 2, T: (1 - GC_MODEL) / 2, C: GC_MODEL / 2, G: GC_MODEL / 2}
+    by_pos = {}
+    for i, (p, c1, _, _, _) in enumerate(entries):
+        by_pos.setdefault(p, []).append(i)
+    out = [[] for _ in range(n)]
+    for p, idxs in by_pos.items():
+        # entries at one position are mutually exclusive: pick at most one
+        probs = []
+        for i in idxs:
+            c1 = entries[i][1]
+            lane_c = entries[i][4]
+            probs.append(f[lane_c] if c1 is None else f[c1] * f[lane_c])
+        u = rng.random(n)
+        edges = np.cumsum(probs)
+        pick = np.searchsorted(edges, u, side="right")
+        for k in np.nonzero(pick < len(idxs))[0]:
+            out[k].append(idxs[pick[k]])
+    return out
+
+
+def expected_wavefronts(slots, offset):
+    """LDS.64 of a warp = two half-warps of 16 lanes; a half-warp costs as many wavefronts as the
+    largest number of DISTINCT slots that fall on one of the 16 bank pairs."""
+    n = len(slots) // 16 * 16
+    s = (slots[:n] + offset).reshape(-1, 16)
+    total = 0
+    for row in s:
+        u = np.unique(row)
+        total += np.bincount(u & 15, minlength=16).max()
+    return 2.0 * total / len(s)
+
+
+def find_hash(entries, seed, offset):
     """Smallest index width with an injective multiplicative hash
         slot = (sum over first-base groups of x_g * magic_g  mod 2^32) >> (32 - bits)
-    over every state the free table entries can take."""
+    over every state the free table entries can take; among the injective candidates the one
+    with the fewest expected shared-memory bank conflicts (Monte-Carlo over random 30-mers)."""
     groups = {}
     for i, e in enumerate(entries):
         groups.setdefault(e[1], []).append(i)
@@ -110,6 +151,11 @@ def find_hash(entries, seed):
     rng = np.random.default_rng(seed)
     batch = 2048
     m32 = np.uint64(0xFFFFFFFF)
+    mc = sample_states(entries, np.random.default_rng(seed + 7), 16 * 1500)
+    mc_pat = np.zeros((len(glist), len(mc)), dtype=np.uint64)
+    for k, st in enumerate(mc):
+        for gi, (_, idxs) in enumerate(glist):
+            mc_pat[gi, k] = sum(1 << bit_of(entries[i]) for i in st if i in idxs)
 
     def sparse():
         m = rng.integers(0, 2 ** 32, size=batch, dtype=np.uint64)
@@ -118,7 +164,8 @@ def find_hash(entries, seed):
         return m
 
     for bits in (need, need + 1, need + 2):
-        for t in range(4000 if bits == need else 500):
+        found = []
+        for t in range(6000 if bits == need else 800):
             acc = np.zeros((batch, len(states)), dtype=np.uint64)
             mags = []
             for gi in range(len(glist)):
@@ -128,10 +175,33 @@ def find_hash(entries, seed):
             h = (acc & m32) >> np.uint64(32 - bits)
             h.sort(axis=1)
             ok = (np.diff(h.astype(np.int64), axis=1) != 0).all(axis=1) if len(states) > 1 else np.ones(batch, bool)
-            if ok.any():
-                k = int(np.argmax(ok))
-                return bits, [(c1, sum(1 << bit_of(entries[i]) for i in idxs), int(mags[gi][k]))
-                              for gi, (c1, idxs) in enumerate(glist)]
+            for k in np.nonzero(ok)[0]:
+                found.append([int(mags[gi][k]) for gi in range(len(glist))])
+            if len(found) >= N_CANDIDATES or (found and t > 1500):
+                break
+        if found:
+            def cost_of(mg):
+                hh = np.zeros(len(mc), dtype=np.uint64)
+                for gi in range(len(glist)):
+                    hh += (mc_pat[gi] * np.uint64(mg[gi])) & m32
+                sl = ((hh & m32) >> np.uint64(32 - bits)).astype(np.int64)
+                if bits >= SWIZZLE_MIN_BITS:
+                    sl ^= sl >> (bits - 4)
+                return expected_wavefronts(sl, offset)
+
+            def injective(mg):
+                acc = np.zeros(len(states), dtype=np.uint64)
+                for gi in range(len(glist)):
+                    acc += (pat[gi] * np.uint64(mg[gi])) & m32
+                h = (acc & m32) >> np.uint64(32 - bits)
+                return len(np.unique(h)) == len(states)
+
+            best = min(((cost_of(mg), mg) for mg in found[:N_CANDIDATES]), key=lambda t: t[0])
+            import sys
+            print(f"lane hash: {len(states)} states, {bits} bits, {len(found)} candidates, expected wavefronts "
+                  f"{best[0]:.2f}{' (xor swizzle)' if bits >= SWIZZLE_MIN_BITS else ''}", file=sys.stderr)
+            return bits, [(c1, sum(1 << bit_of(entries[i]) for i in idxs), best[1][gi])
+                          for gi, (c1, idxs) in enumerate(glist)]
     raise SystemExit("no perfect hash found")
 
 
@@ -154,8 +224,9 @@ def main():
     emit("// shifted left by one); forced: the entry matches every scanned 30-mer (PAM bases) and has no bit")
     emit("struct Rs1Entry { int pos; int first_base; double weight; int bit; int forced; };     // first_base < 0: first-order term")
     emit("struct Rs1Group { int first_base; unsigned mask; unsigned magic; };")
-    emit("// table slot of a set of matching entries = (sum over groups of x_g * magic  mod 2^32) >> (32 - bits)")
-    emit("struct Rs1Lane { const char *name; int lane_base; int n_entries; int n_table; int bits; int offset; "
+    emit("// table slot of a set of matching entries: s = (sum over groups of x_g * magic  mod 2^32) >> (32 - bits),")
+    emit("// then s ^ (s >> (bits - 4)) if swizzle (spreads the probable states over the shared-memory banks)")
+    emit("struct Rs1Lane { const char *name; int lane_base; int n_entries; int n_table; int bits; int swizzle; int offset; "
          "int n_groups; Rs1Group groups[4]; Rs1Entry entries[16]; };")
     descs, code, offset, consts = [], [], 0, []
     mask_name = {0: "mA", 1: "mT", 2: "mC", 3: "mG"}
@@ -163,34 +234,45 @@ def main():
     for li, (name, base, entries) in enumerate(lanes()):
         free = [e for e in entries if not e[3]]
         n_free_table = min(len(free), TABLE_ENTRIES.get(name, MAX_TABLE_ENTRIES))
+        if len(free) <= SEQUENTIAL_MAX and not any(e[3] for e in entries):
+            n_free_table = 0                        # a short lane is cheaper as fused multiply-adds than as a lookup
         # never split a group of mutually exclusive entries (same position) across table / tail
         while 0 < n_free_table < len(free) and free[n_free_table][0] == free[n_free_table - 1][0]:
             n_free_table -= 1
         table_free = free[:n_free_table]
         tail = free[n_free_table:]
         assert all(e[0] < (tail[0][0] if tail else 99) for e in entries if e[3]), "forced entry after a tail entry"
-        bits, groups = find_hash(table_free, seed=100 + li)
-        n_table = len(entries) - len(tail)          # forced + tabulated entries come first
-        ents = ", ".join(f"{{{p}, {-1 if c1 is None else c1}, {hexf(v)}, {bit_of((p, c1, v, f))}, {int(f)}}}"
-                         for p, c1, v, f in entries)
-        grps = ", ".join(f"{{{-1 if c1 is None else c1}, 0x{m:x}u, 0x{mg:x}u}}" for c1, m, mg in groups)
-        descs.append(f'    {{"{name}", {base}, {len(entries)}, {n_table}, {bits}, {offset}, {len(groups)}, {{{grps}}}, {{{ents}}}}}')
-        # ---- device code of this lane
         second = name[0] == "d"
-        terms = []
-        for c1, m, mg in groups:
-            src = f"({shift_name[c1]} & {mask_name[base]} & 0x{m:x}u)" if second else f"({mask_name[base]} & 0x{m:x}u)"
-            terms.append(f"{src} * 0x{mg:x}u")
-        code.append(f"    double {name} = RS1_LD(T, {offset}u, RS1_TOP(" + " + ".join(terms) + f", {bits}));")
-        for p, c1, v, _ in tail:
+        if table_free or any(e[3] for e in entries):
+            bits, groups = find_hash(table_free, seed=100 + li, offset=offset)
+        else:
+            bits, groups = -1, []
+        n_table = len(entries) - len(tail)          # forced + tabulated entries come first
+        ents = ", ".join(f"{{{p}, {-1 if c1 is None else c1}, {hexf(v)}, {bit_of((p, c1))}, {int(f)}}}"
+                         for p, c1, v, f, _ in entries)
+        grps = ", ".join(f"{{{-1 if c1 is None else c1}, 0x{m:x}u, 0x{mg:x}u}}" for c1, m, mg in groups)
+        descs.append(f'    {{"{name}", {base}, {len(entries)}, {n_table}, {bits}, {int(bits >= SWIZZLE_MIN_BITS)}, {offset}, {len(groups)}, {{{grps}}}, {{{ents}}}}}')
+        # ---- device code of this lane
+        if bits >= 0:
+            terms = []
+            for c1, m, mg in groups:
+                src = f"({shift_name[c1]} & {mask_name[base]} & 0x{m:x}u)" if second else f"({mask_name[base]} & 0x{m:x}u)"
+                terms.append(f"{src} * 0x{mg:x}u")
+            top = "RS1_SWZ" if bits >= SWIZZLE_MIN_BITS else "RS1_TOP"
+            code.append(f"    double {name} = RS1_LD(T, {offset}u, {top}(" + " + ".join(terms) + f", {bits}));")
+            offset += 1 << bits
+        else:
+            code.append(f"    double {name} = 0.0;")
+        for p, c1, v, _, _ in tail:
             # entries at one position are mutually exclusive: at most one of the fma's adds a non-zero
-            b = bit_of((p, c1, v, False))
-            assert b >= 20, "tail entry below bit 20: extend the generator with a shift"
-            e = 1 << (b - 20)
+            b = bit_of((p, c1))
             cond = f"{shift_name[c1]} & {mask_name[base]} & 0x{1 << b:x}u" if second else f"{mask_name[base]} & 0x{1 << b:x}u"
+            if b < 20:                              # move the bit into the exponent field first
+                cond = f"RS1_SHL({cond}, {20 - b})"
+                b = 20
+            e = 1 << (b - 20)
             code.append(f"    {name} = RS1_FMA_BIT({cond}, RS1_K({len(consts)}), {name});   // {v!r} * 2^{1023 - e}")
             consts.append(hexf(v * 2.0 ** (1023 - e)))
-        offset += 1 << bits
     emit(f"#define RS1_TABLE_DOUBLES {offset}")
     emit("// pre-scaled tail weights, then intercept and low_gc: kept in a __constant__ array so that DFMA / DADD")
     emit("// read them as constant-bank operands (64-bit immediates would cost two UMOV each)")

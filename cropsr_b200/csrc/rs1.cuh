@@ -28,11 +28,14 @@ static constexpr size_t kRs1TableBytes = (size_t)RS1_TABLE_DOUBLES * sizeof(doub
 __constant__ double c_rs1_k[] = RS1_K_VALUES;
 #define RS1_K(i) c_rs1_k[i]
 
-// lane table entry: `off` doubles into the tables, slot idx
-#define RS1_LD(T, off, idx) (*reinterpret_cast<const double *>(reinterpret_cast<const char *>(T) + 8u * (off) + 8u * (idx)))
-// top `bits` bits of the hash as a multiply-high (FMA pipe; a shift would go to the ALU pipe)
-#define RS1_TOP(h, bits) __umulhi((h), 1u << (bits))
+// lane table entry: `off` doubles into the tables, byte index idx8
+#define RS1_LD(T, off, idx8) (*reinterpret_cast<const double *>(reinterpret_cast<const char *>(T) + 8u * (off) + (idx8)))
+// top `bits` bits of the hash, scaled to bytes, as multiplies (FMA pipe; shifts would go to the ALU pipe)
+#define RS1_TOP(h, bits) (__umulhi((h), 1u << (bits)) * 8u)
+// the same with the top 4 hash bits xor-ed into the slot: spreads the probable states over the banks
+#define RS1_SWZ(h, bits) ((__umulhi((h), 1u << (bits)) * 8u) ^ (__umulhi((h), 16u) * 8u))
 #define RS1_SHL1(m) ((m) << 1)
+#define RS1_SHL(m, k) ((m) << (k))
 // acc + w iff the match bit is set, as ONE DFMA: bit (a single bit p >= 20 of a class mask)
 // read as the high word of a double is a power of two, w_scaled = w / that power.
 #define RS1_FMA_BIT(bit, w_scaled, acc) __fma_rn(__hiloint2double((int)(bit), 0), (w_scaled), (acc))
@@ -53,6 +56,7 @@ static int build_rs1_tables(std::vector<double> &tab, char *err, size_t errlen) 
     tab.assign(RS1_TABLE_DOUBLES, 0.0);
     std::vector<char> used(RS1_TABLE_DOUBLES, 0);
     for (const Rs1Lane &ln : kRs1Lanes) {
+        if (ln.bits < 0) continue;                // no table: the lane is summed entry by entry
         int free_idx[16], n_free = 0;
         for (int i = 0; i < ln.n_table; ++i)
             if (!ln.entries[i].forced) free_idx[n_free++] = i;
@@ -81,7 +85,8 @@ static int build_rs1_tables(std::vector<double> &tab, char *err, size_t errlen) 
                 const bool on = ln.entries[i].forced ? true : ((sub >> f++) & 1);
                 if (on) sum = sum + ln.entries[i].weight;
             }
-            const uint32_t slot = ln.bits ? h >> (32 - ln.bits) : 0u;
+            uint32_t slot = ln.bits ? h >> (32 - ln.bits) : 0u;
+            if (ln.swizzle) slot ^= slot >> (ln.bits - 4);
             const uint32_t idx = ln.offset + slot;
             if (idx >= RS1_TABLE_DOUBLES || used[idx]) {
                 snprintf(err, errlen, "rs1 table hash of lane %s is not injective", ln.name);

@@ -289,8 +289,8 @@ __device__ __forceinline__ void st_list_if(uint16_t *p, uint32_t cond, uint32_t 
         : "memory");
 }
 // hits of one word into the compacted list, ascending; first = slot of the word's first hit.
-// The first two hits are straight-line predicated code (a 32-position word holds more than
-// two hits of a strand in ~6 % of the words at 36 % GC), the rest loop.
+// The first three hits are straight-line predicated code (a 32-position word holds more than
+// three hits of a strand in ~1 % of the words at 36 % GC), the rest loop.
 __device__ __forceinline__ void list_hits(uint16_t *__restrict__ first, uint32_t m, uint32_t pos0) {
     const uint32_t l0 = m & (0u - m);
     st_list_if(first, l0, pos0 + 31u - (uint32_t)__clz(l0));
@@ -298,7 +298,10 @@ __device__ __forceinline__ void list_hits(uint16_t *__restrict__ first, uint32_t
     const uint32_t l1 = m & (0u - m);
     st_list_if(first + 1, l1, pos0 + 31u - (uint32_t)__clz(l1));
     m ^= l1;
-    first += 2;
+    const uint32_t l2 = m & (0u - m);
+    st_list_if(first + 2, l2, pos0 + 31u - (uint32_t)__clz(l2));
+    m ^= l2;
+    first += 3;
     while (m) {
         const uint32_t lb = m & (0u - m);
         *first++ = (uint16_t)(pos0 + 31u - (uint32_t)__clz(lb));
