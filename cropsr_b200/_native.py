@@ -64,6 +64,10 @@ SIGNATURES = {
     "crp_host_free": (C.c_int, [C.c_void_p]),
     "crp_genome_new": (C.c_int, [_vpp]),
     "crp_genome_add_segment": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "crp_genome_add_fasta_record": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int]),
+    "crp_genome_token_length": (C.c_int, [C.c_void_p, C.c_uint32, _u64p]),
+    "crp_genome_fetch_token": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]),
+    "crp_genome_release_tokens": (C.c_int, [C.c_void_p]),
     "crp_genome_commit": (C.c_int, [C.c_void_p]),
     "crp_genome_num_segments": (C.c_int, [C.c_void_p, _u32p]),
     "crp_genome_num_positions": (C.c_int, [C.c_void_p, _u64p]),

@@ -67,6 +67,11 @@ struct Segment {
     uint64_t token_len, begin, end;
     uint64_t stage_begin, stage_end;   // token positions copied to the device
     uint32_t first_tile, n_tiles;
+    // FASTA record ingested on the device (crp_genome_add_fasta_record): token == NULL
+    const uint8_t *raw = nullptr;      // first sequence byte of the record, as in the file
+    uint64_t raw_bytes = 0;
+    uint32_t width = 0, last = 0;
+    uint64_t ascii_off = 0;            // token position stage_begin in the ASCII buffer kept on the device
 };
 
 struct crp_genome {
@@ -81,6 +86,9 @@ struct crp_genome {
     float ms_h2d = 0.f, ms_pack = 0.f;
     // state of the single-pass scan kernel (scan_sp.cuh): zeroed once at commit, then only
     // ever advanced by the launches, which are ordered on the genome's stream
+    uint8_t *d_ascii = nullptr;                // ASCII tokens, kept after the pack only for device-ingested FASTA records
+    bool fasta = false;
+    unsigned int *h_bad = nullptr;             // pinned: non-zero after the commit if a FASTA record was not plain
     unsigned char *sp_state = nullptr;         // agg[n_tiles] | incl[n_tiles] | ctl[2]
     mutable uint32_t sp_epoch = 0, sp_ticket = 0, sp_done = 0;
 };
@@ -278,6 +286,62 @@ int crp_genome_add_segment(crp_genome *g, uint32_t token_id, const uint8_t *toke
     return 0;
 }
 
+int crp_genome_add_fasta_record(crp_genome *g, uint32_t token_id, const uint8_t *seq_bytes, uint64_t n_bytes,
+                                uint32_t line_width, int last_record) {
+    if (!g) return fail(CRP_ERR_ARG, "g is NULL");
+    if (g->committed) return fail(CRP_ERR_STATE, "genome already committed");
+    if (!seq_bytes || !n_bytes || !line_width) return fail(CRP_ERR_FORMAT, "empty FASTA record");
+    // bytes = bases + one line end per full line, the last one optional
+    const uint64_t body = seq_bytes[n_bytes - 1] == '\n' ? n_bytes - 1 : n_bytes;
+    const uint64_t k = body / ((uint64_t)line_width + 1), r = body % ((uint64_t)line_width + 1);
+    if (r == 0) return fail(CRP_ERR_FORMAT, "FASTA record is not made of %u-base lines", line_width);
+    const uint64_t n_bases = k * line_width + r, token_len = n_bases + 4;
+    if (token_len >= (1ull << 31) - (1ull << 15))
+        return fail(CRP_ERR_RANGE, "token of %llu positions exceeds the 31-bit position range",
+                    (unsigned long long)token_len);
+    Segment s{};
+    s.token_id = token_id;
+    s.token = nullptr;
+    s.token_len = token_len;
+    s.begin = 0;
+    s.end = token_len;
+    s.raw = seq_bytes;
+    s.raw_bytes = n_bytes;
+    s.width = line_width;
+    s.last = last_record ? 1u : 0u;
+    g->segs.push_back(s);
+    g->fasta = true;
+    return 0;
+}
+
+int crp_genome_token_length(const crp_genome *g, uint32_t segment, uint64_t *token_len) {
+    if (!g || !token_len) return fail(CRP_ERR_ARG, "NULL argument");
+    if (segment >= g->segs.size()) return fail(CRP_ERR_ARG, "segment %u out of range", segment);
+    *token_len = g->segs[segment].token_len;
+    return 0;
+}
+
+int crp_genome_fetch_token(const crp_genome *g, uint32_t segment, uint8_t *dst, uint64_t capacity) {
+    if (!g || !dst) return fail(CRP_ERR_ARG, "NULL argument");
+    if (int rc = need_ctx()) return rc;
+    if (!g->committed || !g->d_ascii) return fail(CRP_ERR_STATE, "the genome keeps no tokens on the device");
+    if (segment >= g->segs.size()) return fail(CRP_ERR_ARG, "segment %u out of range", segment);
+    const Segment &s = g->segs[segment];
+    if (!s.raw) return fail(CRP_ERR_STATE, "segment %u was not ingested from FASTA bytes", segment);
+    if (capacity < s.token_len) return fail(CRP_ERR_RANGE, "token needs %llu bytes", (unsigned long long)s.token_len);
+    cudaStream_t st = g->st ? g->st : g_ctx.stream;
+    CUDA_TRY(cudaMemcpyAsync(dst, g->d_ascii + s.ascii_off, s.token_len, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int crp_genome_release_tokens(crp_genome *g) {
+    if (!g) return fail(CRP_ERR_ARG, "g is NULL");
+    dev_free(g->d_ascii, g->st ? g->st : g_ctx.stream);
+    g->d_ascii = nullptr;
+    return 0;
+}
+
 int crp_genome_num_segments(const crp_genome *g, uint32_t *n) {
     if (!g || !n) return fail(CRP_ERR_ARG, "NULL argument");
     *n = (uint32_t)g->segs.size();
@@ -357,11 +421,58 @@ static int commit_enqueue(crp_genome *g) {
     for (int i = 0; i < 3; ++i)
         if (!g->ev[i]) CUDA_TRY(cudaEventCreate(&g->ev[i]));
     CUDA_TRY(cudaEventRecord(g->ev[0], st));
+    uint8_t *d_raw = nullptr;
+    FastaRec *d_recs = nullptr;
+    unsigned int *d_bad = nullptr;
+    std::vector<FastaRec> frecs;
+    uint64_t raw_total = 0, strip_items = 0;
     for (size_t si = 0; si < g->segs.size(); ++si) {
+        Segment &s = g->segs[si];
+        s.ascii_off = seg_ascii[si];
+        if (!s.raw) continue;
+        FastaRec fr{};
+        fr.raw_off = raw_total;
+        fr.ascii_off = seg_ascii[si];
+        fr.first_item = strip_items;
+        fr.n_bases = (uint32_t)(s.token_len - 4);
+        fr.width = s.width;
+        fr.last = s.last;
+        frecs.push_back(fr);
+        raw_total += (s.raw_bytes + 15) / 16 * 16;
+        strip_items += (s.token_len + 15) / 16;
+    }
+    if (!frecs.empty()) {
+        if (dev_alloc(&d_raw, raw_total + 64, st) != cudaSuccess ||
+            dev_alloc(&d_recs, frecs.size() * sizeof(FastaRec), st) != cudaSuccess ||
+            dev_alloc(&d_bad, sizeof(unsigned int), st) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(CRP_ERR_NOMEM, "cudaMalloc of %llu FASTA bytes failed", (unsigned long long)raw_total);
+        }
+        CUDA_TRY(cudaMemsetAsync(d_bad, 0, sizeof(unsigned int), st));
+    }
+    for (size_t si = 0, fi = 0; si < g->segs.size(); ++si) {
         const Segment &s = g->segs[si];
-        if (s.stage_end > s.stage_begin && s.n_tiles)
+        if (s.raw) {
+            CUDA_TRY(cudaMemcpyAsync(d_raw + frecs[fi++].raw_off, s.raw, s.raw_bytes, cudaMemcpyHostToDevice, st));
+        } else if (s.stage_end > s.stage_begin && s.n_tiles) {
             CUDA_TRY(cudaMemcpyAsync(d_ascii + seg_ascii[si], s.token + s.stage_begin, s.stage_end - s.stage_begin,
                                      cudaMemcpyHostToDevice, st));
+        }
+    }
+    if (!frecs.empty()) {
+        CUDA_TRY(cudaMemcpyAsync(d_recs, frecs.data(), frecs.size() * sizeof(FastaRec), cudaMemcpyHostToDevice, st));
+        const uint64_t want = (strip_items + 255) / 256, cap = (uint64_t)g_ctx.sm_count * 16;
+        k_fasta_strip<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(d_raw, d_recs, (uint32_t)frecs.size(),
+                                                                           strip_items, d_ascii, d_bad);
+        g_ctx.launches++;
+        CUDA_TRY(cudaGetLastError());
+        if (!g->h_bad) g->h_bad = static_cast<unsigned int *>(pinned_get(sizeof(unsigned int)));
+        if (!g->h_bad) return fail(CRP_ERR_NOMEM, "cudaHostAlloc failed");
+        *g->h_bad = 0;
+        CUDA_TRY(cudaMemcpyAsync(g->h_bad, d_bad, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        dev_free(d_raw, st);
+        dev_free(d_recs, st);
+        dev_free(d_bad, st);
     }
     if (!one && !descs.empty())
         CUDA_TRY(cudaMemcpyAsync(d_descs, descs.data(), descs.size() * sizeof(PackDesc), cudaMemcpyHostToDevice, st));
@@ -383,7 +494,8 @@ static int commit_enqueue(crp_genome *g) {
         CUDA_TRY(cudaMemcpyAsync(g->d_seg_first, seg_first.data(), nb, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(g->d_seg_count, seg_count.data(), nb, cudaMemcpyHostToDevice, st));
     }
-    dev_free(d_ascii, st);       // stream ordered: after the pack kernel
+    if (g->fasta) g->d_ascii = d_ascii;   // kept: the host fetches the tokens it formats rows from
+    else dev_free(d_ascii, st);           // stream ordered: after the pack kernel
     dev_free(d_descs, st);
     g->committed = true;
     return 0;
@@ -401,6 +513,8 @@ int crp_genome_commit(crp_genome *g) {
     CUDA_TRY(cudaEventElapsedTime(&g->ms_h2d, g->ev[0], g->ev[1]));
     CUDA_TRY(cudaEventElapsedTime(&g->ms_pack, g->ev[1], g->ev[2]));
     for (Segment &s : g->segs) s.token = nullptr;   // host tokens may be released now
+    if (g->h_bad && *g->h_bad)
+        return fail(CRP_ERR_FORMAT, "a FASTA record is not plain fixed-width text; use the host ingest for this file");
     return 0;
 }
 
@@ -416,6 +530,8 @@ int crp_genome_free(crp_genome *g) {
     cudaStream_t st = stream_of(g);
     dev_free(g->records, st);
     dev_free(g->sp_state, st);
+    dev_free(g->d_ascii, st);
+    pinned_put(g->h_bad);
     dev_free(g->d_seg_first, st);
     dev_free(g->d_seg_count, st);
     for (cudaEvent_t e : g->ev)

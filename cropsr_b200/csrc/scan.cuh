@@ -140,6 +140,67 @@ k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, co
     }
 }
 
+// ------------------------------------------------------------------ k_fasta_strip
+// Device side of the formatted-path ingest (CROPSR.py:54-74 with cropsr_functions.py:221-229):
+// the sequence lines of one FASTA record, exactly as they sit in the file, become the token
+// the reference scans:  ' + bases + ') + (, or ] for the last record).  The record must be
+// "plain": every line `width` bases long except the last one, '\n' line ends, printable
+// non-blank ASCII without quotes or backslashes -- then str(list_of_tuples) changes nothing
+// but the decoration.  Anything else sets *bad (the host then falls back to the literal
+// Python ingest); so does a base where a line end is due or the other way round.  The host
+// derives n_bases from the byte count of the record and `width`, so every byte is accounted for.
+struct FastaRec {
+    uint64_t raw_off;     // first sequence byte of the record in the raw buffer
+    uint64_t ascii_off;   // token position 0 in the ASCII staging buffer (16-byte aligned)
+    uint64_t first_item;  // 16-byte output groups before this record
+    uint32_t n_bases, width;
+    uint32_t last, pad;   // last: last record of the file (its token ends in ')]', not '),')
+};
+
+__global__ void __launch_bounds__(256)
+k_fasta_strip(const uint8_t *__restrict__ raw, const FastaRec *__restrict__ recs, uint32_t n_recs, uint64_t n_items,
+              uint8_t *__restrict__ ascii, unsigned int *__restrict__ bad) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += stride) {
+        uint32_t lo = 0, hi = n_recs;                  // last record with first_item <= it
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (recs[mid].first_item <= it) lo = mid;
+            else hi = mid;
+        }
+        const FastaRec r = recs[lo];
+        const uint64_t p0 = (it - r.first_item) * 16;  // token position of output byte 0
+        const uint64_t n = r.n_bases, L = n + 4;
+        uint64_t b = p0 ? p0 - 1 : 0;                  // base index of the first base byte of the group
+        uint64_t line = b / r.width;
+        uint32_t col = (uint32_t)(b - line * r.width);
+        const uint8_t *src = raw + r.raw_off + b + line;
+        uint32_t w[4] = {0, 0, 0, 0};
+        unsigned int err = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint64_t p = p0 + i;
+            uint32_t c = 0;
+            if (p == 0 || p == n + 1) c = '\'';
+            else if (p == n + 2) c = ')';
+            else if (p == n + 3) c = r.last ? ']' : ',';
+            else if (p < L) {
+                if (col == r.width) {                  // a line end is due here
+                    if (__ldg(src) != '\n') err = 1;
+                    ++src;
+                    col = 0;
+                }
+                c = __ldg(src++);
+                ++col;
+                if (c <= 0x20 || c >= 0x7F || c == '\'' || c == '"' || c == '\\' || c == '>') err = 1;
+            }
+            w[i >> 2] |= c << (8 * (i & 3));
+        }
+        *reinterpret_cast<uint4 *>(ascii + r.ascii_off + p0) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (err) atomicOr(bad, 1u);
+    }
+}
+
 // ------------------------------------------------------------------ small device helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

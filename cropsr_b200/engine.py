@@ -167,6 +167,30 @@ class Genome:
         self.segments.append((int(token_id), len(arr), int(begin), end))
         return len(self.segments) - 1
 
+    def add_fasta_record(self, file_bytes, seq_off, seq_bytes, line_width, last, token_id=None):
+        """One record of a plain multi-line FASTA file, ingested on the device: file_bytes is a
+        uint8 array of the whole file, [seq_off, seq_off + seq_bytes) its sequence lines.
+        Raises CropsrError(code -6) if the record is not plain (see include/cropsr_b200.h)."""
+        arr = _as_u8(file_bytes)
+        tid = len(self.segments) if token_id is None else int(token_id)
+        check(lib.crp_genome_add_fasta_record(self._h, tid, arr.ctypes.data + int(seq_off), int(seq_bytes),
+                                              int(line_width), int(bool(last))))
+        self._keep.append(arr)
+        n = C.c_uint64(0)
+        check(lib.crp_genome_token_length(self._h, len(self.segments), C.byref(n)))
+        self.segments.append((tid, n.value, 0, n.value))
+        return len(self.segments) - 1
+
+    def fetch_token(self, segment):
+        """Token bytes of a device-ingested FASTA record (uint8 array, decoration included)."""
+        n = self.segments[segment][1]
+        out = np.empty(n, dtype=np.uint8)
+        check(lib.crp_genome_fetch_token(self._h, int(segment), out.ctypes.data, n))
+        return out
+
+    def release_tokens(self):
+        check(lib.crp_genome_release_tokens(self._h))
+
     def add_token(self, token, token_id=None):
         return self.add_segment(len(self.segments) if token_id is None else token_id, token)
 

@@ -57,6 +57,50 @@ def import_fasta_file(fasta, verbose=False):
     return fasta_text_to_tokens(text, verbose, fasta)
 
 
+def plain_fasta_layout(buf):
+    """Layout of a *plain* multi-line FASTA file for the device ingest
+    (engine.Genome.add_fasta_record), or None if the literal text path above is needed.
+
+    buf: bytes-like, the whole file.  Returns [(key, seq_off, seq_bytes, line_width, last)],
+    key being the ingest-dict key the reference derives for the record ("[('name'," for the
+    first record, "('name'," for the others -- CROPSR.py:66-70 via str(list_of_tuples).split()).
+    Plain means: the formatted path applies (CROPSR.py:62-63), the file starts with '>', every
+    '>' starts a line, header lines hold no blank, quote, backslash or non-ASCII byte, no two
+    records share a name, and every record has a sequence part; the sequence bytes themselves
+    are validated on the device (k_fasta_strip)."""
+    data = bytes(buf) if not isinstance(buf, (bytes, bytearray)) else buf
+    n = len(data)
+    if n == 0 or data[0:1] != b">":
+        return None
+    n_gt, n_nl = data.count(b">"), data.count(b"\n")
+    if 2 * n_gt == n_nl + 1:                     # the clean path: tokens come from text.split()
+        return None
+    if data.count(b"\n>") + 1 != n_gt or b"\r" in data:
+        return None
+    records, seen, pos = [], set(), 0
+    while pos < n:
+        eol = data.find(b"\n", pos)
+        if eol < 0:
+            return None                          # header without a sequence part
+        name = data[pos + 1:eol]
+        nxt = data.find(b">", eol + 1)
+        end = n if nxt < 0 else nxt
+        if end - (eol + 1) <= 0 or not name or name in seen:
+            return None
+        if any(c <= 0x20 or c >= 0x7F or c in b"'\"\\" for c in name):
+            return None
+        seen.add(name)
+        first_nl = data.find(b"\n", eol + 1, end)
+        width = (first_nl if first_nl >= 0 else end) - (eol + 1)
+        if width <= 0:
+            return None
+        text = name.decode("ascii")
+        key = ("[('" if not records else "('") + text + "',"
+        records.append((key, eol + 1, end - (eol + 1), width, nxt < 0))
+        pos = end
+    return records
+
+
 GFF_COLUMNS = ["chromosome", "source", "feature", "start", "end", "score", "strand", "phase", "attributes"]
 
 

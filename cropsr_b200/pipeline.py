@@ -26,6 +26,34 @@ def scan_tokens(tokens, guide_len=20, flags=0):
     return genome, result, token_bytes
 
 
+def scan_fasta_file(fasta, guide_len=20, flags=0):
+    """Device-side ingest of a plain multi-line FASTA file: the file's bytes go to the GPU as they
+    are, k_fasta_strip builds the tokens there, and the host gets them back for row formatting.
+    Returns (keys, genome, result, token_bytes), or None when the file needs the literal host
+    ingest (clean path, blanks in headers, duplicate names, ragged lines, ...)."""
+    from ._native import CropsrError
+    with open(fasta, "rb") as f:
+        data = f.read()
+    layout = ingest.plain_fasta_layout(data)
+    if layout is None:
+        return None
+    arr = np.frombuffer(data, dtype=np.uint8)
+    genome = engine.Genome()
+    try:
+        for key, off, nbytes, width, last in layout:
+            genome.add_fasta_record(arr, off, nbytes, width, last)
+        genome.commit()
+    except CropsrError as e:
+        genome.free()
+        if e.code == -6:            # CRP_ERR_FORMAT: not plain after all
+            return None
+        raise
+    result = genome.scan(guide_len, flags)
+    token_bytes = [genome.fetch_token(seg).tobytes() for seg in range(len(layout))]
+    genome.release_tokens()
+    return [rec[0] for rec in layout], genome, result, token_bytes
+
+
 def write_side_output(path, tokens, result, gff_frame, flank, formatted_path):
     """Opt-in table of the per-candidate side outputs (one row per unique candidate, reference
     order).  NOT part of the reference's CSV: GC, poly-T / homopolymer flags, cut site, the
@@ -56,17 +84,28 @@ def write_side_output(path, tokens, result, gff_frame, flank, formatted_path):
 
 
 def run_cas9(fasta, gff, output="data.csv", guide_len=20, verbose=False, blas_threads=1,
-             time_path="time.txt", out=print, side_output=None, flank=200):
+             time_path="time.txt", out=print, side_output=None, flank=200, device_ingest=True):
     begin = time.time()
     timing = open(time_path, "w")                       # CROPSR.py:371
-    tokens = ingest.import_fasta_file(fasta, verbose)   # :374
+    fast = scan_fasta_file(fasta, guide_len) if device_ingest else None
+    if fast is not None:                                # :374, on the device
+        keys, genome, result, token_bytes = fast
+        tokens = {k: b.decode("ascii") for k, b in zip(keys, (tb[:25] for tb in token_bytes))}   # stdout only
+        if verbose:
+            out(f"Genome file {fasta} successfully imported")
+            out("formatting genome")
+            out(f"Genome file {fasta} successfully formatted")
+            out("The genome was successfully converted to a dictionary")
+    else:
+        tokens = ingest.import_fasta_file(fasta, verbose)   # :374
     gff_frame = ingest.import_gff_file(gff, verbose)    # :375 (parsed, never used by the reference)
     if verbose:
         out("\n            Initiating PAM site detection.\n            \n"
             "            Please wait, this may take a while...\n            ")
     emit.write_header(output)                           # :402-405
 
-    genome, result, token_bytes = scan_tokens(tokens, guide_len)
+    if fast is None:
+        genome, result, token_bytes = scan_tokens(tokens, guide_len)
     table = emit.CandidateTable(guide_len)
     rows_written = 0
     for seg, (key, value) in enumerate(tokens.items()):

@@ -31,7 +31,8 @@ typedef enum crp_status {
     CRP_ERR_ARG = -2,       /* bad argument                                        */
     CRP_ERR_STATE = -3,     /* call out of order (e.g. scan before commit)         */
     CRP_ERR_NOMEM = -4,     /* host or device allocation failed                    */
-    CRP_ERR_RANGE = -5      /* token/segment too large for the 31-bit position     */
+    CRP_ERR_RANGE = -5,     /* token/segment too large for the 31-bit position     */
+    CRP_ERR_FORMAT = -6     /* FASTA bytes are not plain fixed-width records: use the host ingest */
 } crp_status;
 
 typedef struct crp_genome crp_genome;   /* packed genome shard resident in HBM     */
@@ -94,6 +95,27 @@ int crp_genome_new(crp_genome **g);
 int crp_genome_add_segment(crp_genome *g, uint32_t token_id,
                            const uint8_t *token_ascii, uint64_t token_len,
                            uint64_t seg_begin, uint64_t seg_end);
+/* Device-side ingest of one record of a multi-line FASTA file -- replaces, for that record,
+ * the text pipeline of CROPSR.py:54-74 (import_fasta_file) and cropsr_functions.py:221-229
+ * (formatted: split on '>', drop the line ends, str() of the list of tuples): the file's own
+ * bytes go to the device, a kernel drops the line ends and adds the decoration that the
+ * reference's repr round trip leaves around every sequence ("'" + bases + "')," -- "')]" for
+ * the last record of the file), and the pack kernel reads the result.  seq_bytes points at the
+ * first byte after the header line, n_bytes runs to the next '>' or the end of the file, and
+ * line_width is the length of the first sequence line.  Only "plain" records qualify: every
+ * line line_width bases long except the last, '\n' line ends, printable non-blank ASCII, no
+ * quotes, backslashes or '>' -- text that str()/split() leave untouched.  Anything else makes
+ * this call or crp_genome_commit return CRP_ERR_FORMAT, and the caller ingests the file the
+ * literal way (cropsr_b200/ingest.py).  The bytes must stay valid until crp_genome_commit
+ * returns.  The whole token is one segment. */
+int crp_genome_add_fasta_record(crp_genome *g, uint32_t token_id, const uint8_t *seq_bytes, uint64_t n_bytes,
+                                uint32_t line_width, int last_record);
+/* Length of the token of a segment, and -- for records ingested by the call above -- its
+ * bytes (the rows of the CSV are formatted from them on the host; CROPSR.py:463-469).  The
+ * device copy of the tokens is dropped by crp_genome_release_tokens / crp_genome_free. */
+int crp_genome_token_length(const crp_genome *g, uint32_t segment, uint64_t *token_len);
+int crp_genome_fetch_token(const crp_genome *g, uint32_t segment, uint8_t *dst, uint64_t capacity);
+int crp_genome_release_tokens(crp_genome *g);
 /* H2D copy + pack kernel: ASCII -> 2-bit code planes + lower-case plane +
  * other-byte plane (0.5 byte per base resident in HBM). */
 int crp_genome_commit(crp_genome *g);

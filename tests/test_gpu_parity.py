@@ -331,3 +331,55 @@ def test_cli_side_output_leaves_csv_untouched(manifest, eng, tmp_path):
     assert rows[0][:5] == ["chromosome", "strand", "pam_pos", "cutsite", "gc"]
     assert any(r[12] == "CDS" for r in rows[1:]) and any(r[12] == "" for r in rows[1:])
     assert all(0 <= int(r[4]) <= 20 for r in rows[1:])
+
+
+def test_device_fasta_ingest_equals_text_ingest(manifest, eng, tmp_path):
+    """crp_genome_add_fasta_record + k_fasta_strip: tokens rebuilt on the device from the file's own
+    bytes equal the tokens of the literal text pipeline, candidates and scores included."""
+    from cropsr_b200 import ingest, pipeline
+    texts = [open(fixture_path(n), "rb").read() for n in ("sample_genome.fa", "multi3.fa", "edge_fmt.fa", "mid50k.fa")]
+    texts.append(synthetic_fasta(11, [70000, 16385, 59, 60, 61, 1], gc=0.45, lower_frac=0.3).encode())
+    texts.append(b">one_line\n" + b"ACGGTCCA" * 40 + b"\n>no_final_newline\n" + b"GGCCAATT" * 9 + b"\nGGC")
+    for k, data in enumerate(texts):
+        path = tmp_path / f"in{k}.fa"
+        path.write_bytes(data)
+        fast = pipeline.scan_fasta_file(str(path), 20)
+        assert fast is not None, k
+        keys, genome, result, token_bytes = fast
+        tokens = ingest.fasta_text_to_tokens(data.decode())
+        g2, r2, tb2 = pipeline.scan_tokens(tokens, 20)
+        try:
+            assert keys == list(tokens.keys())
+            assert token_bytes == tb2
+            for seg in range(len(keys)):
+                for strand in "+-":
+                    a, b = result.fetch_segment(seg, strand), r2.fetch_segment(seg, strand)
+                    assert np.array_equal(a["pos"], b["pos"]) and np.array_equal(a["packed"], b["packed"])
+                    assert np.array_equal(a["x"], b["x"])
+        finally:
+            for h in (result, genome, r2, g2):
+                h.free()
+
+
+def test_device_fasta_ingest_refuses_text_that_is_not_plain(eng, tmp_path):
+    """Ragged lines, blanks or quotes inside the sequence: the device validation answers
+    CRP_ERR_FORMAT and the pipeline falls back to the literal host ingest."""
+    from cropsr_b200 import pipeline
+    for k, data in enumerate((b">a\nACGTACGT\nACGT\nACGTACGT\n", b">a\nACGTACGT\nAC GTACG\nAC\n", b">a\nACGTACGT\nAC'TACGT\nAC\n",
+                              b">a\nACGTACGT\nACGTACGT\n\n", b">a\nACGTACGT\n\nACGTACGT\n")):
+        path = tmp_path / f"bad{k}.fa"
+        path.write_bytes(data)
+        assert pipeline.scan_fasta_file(str(path), 20) is None, data
+
+
+def test_cli_csv_same_with_and_without_device_ingest(manifest, eng, tmp_path):
+    from cropsr_b200 import pipeline
+    case = manifest["cases"]["sample"]
+    outs = []
+    for dev in (True, False):
+        out = tmp_path / f"out{int(dev)}.csv"
+        np.random.seed(case["seed"])
+        pipeline.run_cas9(fixture_path(case["fasta"]), fixture_path("sample_genome.gff"), str(out), 20, False,
+                          case["blas_threads"], str(tmp_path / "time.txt"), out=lambda *a: None, device_ingest=dev)
+        outs.append(out.read_bytes())
+    assert outs[0] == outs[1] == golden_csv("sample").encode()

@@ -203,3 +203,32 @@ def test_c_float_repr_matches_python(built_lib):
     ids = np.full((len(vals), 7), "A", dtype="<U1")
     got = emit.format_rows(table, ids, vals, np.ones(len(vals), bool), 0, len(vals)).decode().split("\r\n")[:-1]
     assert [row.split(",")[9] for row in got] == [repr(float(v)) for v in vals]
+
+
+def test_plain_fasta_layout_matches_text_ingest():
+    """ingest.plain_fasta_layout (device ingest) derives the same keys and tokens as the literal
+    text pipeline on every plain fixture and refuses everything the text quirks would change."""
+    import glob, os
+    from cropsr_b200 import ingest
+    from helpers import synthetic_fasta
+    fixtures = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "fixtures", "*.fa")))
+    texts = {os.path.basename(f): open(f, "rb").read() for f in fixtures}
+    texts["synthetic"] = synthetic_fasta(5, [1000, 77, 80, 161], gc=0.5, lower_frac=0.2).encode()
+    plain = 0
+    for name, data in texts.items():
+        lay = ingest.plain_fasta_layout(data)
+        toks = ingest.fasta_text_to_tokens(data.decode())
+        if lay is None:
+            continue
+        plain += 1
+        assert [rec[0] for rec in lay] == list(toks.keys()), name
+        for (key, off, nbytes, width, last), value in zip(lay, toks.values()):
+            body = data[off:off + nbytes]
+            assert b"\n" not in body[:width] and (len(body) <= width or body[width:width + 1] == b"\n")
+            assert value.encode() == b"'" + body.replace(b"\n", b"") + (b"')]" if last else b"'),"), name
+    assert plain >= 5
+    for name in ("clean3.fa", "dup_keys.fa", "ws_header.fa", "empty_records.fa", "edge_clean.fa"):
+        assert ingest.plain_fasta_layout(texts[name]) is None, name
+    for bad in (b"", b"ACGT\n", b">a\nAC\r\nGT\n", b">a b\nACGT\nAC\n", b">a\nACGT\n>a\nAC\nA\n", b">a\n>b\nAC\nA\n",
+                b">a'\nACGT\nA\n", b">a\nAC>GT\nAA\n"):
+        assert ingest.plain_fasta_layout(bad) is None, bad
