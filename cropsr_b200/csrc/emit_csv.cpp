@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <charconv>
 #include <string>
 #include <thread>
 #include <vector>
@@ -60,63 +61,27 @@ inline void put_field(std::string &out, const char *s, size_t n) {   // QUOTE_MI
 
 inline void put_int(std::string &out, long long v) {
     char buf[24];
-    const int n = snprintf(buf, sizeof buf, "%lld", v);
-    out.append(buf, (size_t)n);
+    char *e = buf + sizeof buf, *p = e;
+    unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
+    do {
+        *--p = (char)('0' + u % 10);
+        u /= 10;
+    } while (u);
+    if (v < 0) *--p = '-';
+    out.append(p, (size_t)(e - p));
 }
 
-// repr(float): shortest decimal string that parses back to the same double, laid out the way
-// CPython's float_repr_style 'short' does (fixed notation for 1e-4 <= |x| < 1e16).
+// repr(float): shortest decimal string that parses back to the same double (std::to_chars
+// yields exactly those digits, the closest to x among the shortest -- what CPython's
+// float_repr_style 'short' prints), laid out the way CPython does: fixed notation for
+// 1e-4 <= |x| < 1e16, exponent notation otherwise.
 void put_repr(std::string &out, double x) {
     if (isnan(x)) { out += "nan"; return; }
     if (isinf(x)) { out += x < 0 ? "-inf" : "inf"; return; }
     if (x == 0.0) { out += signbit(x) ? "-0.0" : "0.0"; return; }
-    // Shortest precision whose correctly rounded decimal parses back to x.  Most doubles need
-    // 16-17 digits, so probe 15 first and walk from there.  At a power of two the interval of
-    // decimals that round to x is lopsided (half as wide below x): the nearest p-digit
-    // decimal can fall out on the narrow side while its upper neighbour still round-trips,
-    // and that neighbour is what repr() prints.
     char buf[48];
-    int e2;
-    const bool pow2 = frexp(fabs(x), &e2) == 0.5;
-    auto fits = [&](int prec) -> bool {
-        snprintf(buf, sizeof buf, "%.*e", prec - 1, x);
-        if (strtod(buf, nullptr) == x) return true;
-        if (!pow2) return false;
-        // neighbour one unit in the last place further from zero
-        char *q = buf + (buf[0] == '-');
-        unsigned long long d = 0;
-        char *r = q;
-        for (; *r && *r != 'e'; ++r)
-            if (*r != '.') d = d * 10 + (unsigned long long)(*r - '0');
-        int ex = atoi(r + 1) - (prec - 1);            // value = d * 10^ex
-        ++d;
-        char alt[48];
-        snprintf(alt, sizeof alt, "%s%llue%d", buf[0] == '-' ? "-" : "", d, ex);
-        if (strtod(alt, nullptr) != x) return false;
-        // rewrite as d.ddde+XX with the same number of digits (d + 1 cannot carry into a new digit
-        // here: a carry would make it a shorter decimal, which an earlier precision would have found)
-        char dig[24];
-        const int nd = snprintf(dig, sizeof dig, "%llu", d);
-        int w = 0;
-        if (buf[0] == '-') buf[w++] = '-';
-        buf[w++] = dig[0];
-        if (nd > 1) {
-            buf[w++] = '.';
-            memcpy(buf + w, dig + 1, (size_t)(nd - 1));
-            w += nd - 1;
-        }
-        snprintf(buf + w, sizeof buf - (size_t)w, "e%+03d", ex + nd - 1);
-        return true;
-    };
-    int prec = 15;
-    if (fits(prec)) {
-        while (prec > 1 && fits(prec - 1)) --prec;
-        fits(prec);                                    // leave the winning string in buf
-    } else {
-        ++prec;
-        while (prec < 17 && !fits(prec)) ++prec;
-        if (prec == 17) fits(17);
-    }
+    const std::to_chars_result res = std::to_chars(buf, buf + sizeof buf - 1, x, std::chars_format::scientific);
+    *res.ptr = 0;
     // buf = [-]d[.ddd]e[+-]XX
     const char *p = buf;
     if (*p == '-') { out.push_back('-'); ++p; }

@@ -181,6 +181,11 @@ def slice_rows(table, ids, scores, scored, start, count):
     return rows
 
 
+def id_bytes_of(ids):
+    """get_id()'s (size, 7) '<U1' array as (size, 7) ASCII bytes for the row formatter."""
+    return np.ascontiguousarray(ids).view(np.uint32).astype(np.uint8)
+
+
 def format_rows(table, ids, scores, scored, start, count, n_threads=0):
     """CSV bytes of one emitted slice through the library's multi-threaded row formatter
     (csrc/emit_csv.cpp) -- byte-identical to csv.writer().writerows(slice_rows(...))."""
@@ -188,7 +193,7 @@ def format_rows(table, ids, scores, scored, start, count, n_threads=0):
     from ._native import lib, check
     if count == 0:
         return b""
-    id_bytes = np.ascontiguousarray(ids).view(np.uint32).astype(np.uint8)   # '<U1' code points -> (size, 7) bytes
+    id_bytes = ids if ids.dtype == np.uint8 else id_bytes_of(ids)
     size = len(id_bytes)
     id_index = ((start - 1 - np.arange(count, dtype=np.int64)) % size).astype(np.uint64)   # ids[start - k - 1]
     tok = np.ascontiguousarray(table.tok[start:start + count], dtype=np.uint32)
@@ -215,7 +220,7 @@ def format_rows(table, ids, scores, scored, start, count, n_threads=0):
             cap = need.value
             continue
         check(rc)
-        return out[:need.value].tobytes()
+        return out[:need.value].data        # a memoryview: no copy on the way to f.write()
     raise RuntimeError("crp_format_rows: capacity negotiation failed")
 
 
@@ -231,7 +236,7 @@ def emit_cumulative(path, table, genome, blas_threads=1):
     size = len(table)
     written = 0
     with open(path, "ab") as f:
-        ids = get_id(size)
+        ids = id_bytes_of(get_id(size))
         for start, count in emission_slices(size):
             scores, scored = slice_scores(table, genome, start, count, blas_threads)
             f.write(format_rows(table, ids, scores, scored, start, count))

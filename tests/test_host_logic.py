@@ -201,7 +201,7 @@ def test_c_float_repr_matches_python(built_lib):
     tok = b"A" * 40 + b"GG" + b"A" * 40
     table.append_token(">c", tok, 0, np.full(len(vals), 39, np.uint32), None, np.empty(0, np.uint32), None)
     ids = np.full((len(vals), 7), "A", dtype="<U1")
-    got = emit.format_rows(table, ids, vals, np.ones(len(vals), bool), 0, len(vals)).decode().split("\r\n")[:-1]
+    got = bytes(emit.format_rows(table, ids, vals, np.ones(len(vals), bool), 0, len(vals))).decode().split("\r\n")[:-1]
     assert [row.split(",")[9] for row in got] == [repr(float(v)) for v in vals]
 
 
