@@ -95,7 +95,7 @@ def valid_states(entries):
 
 GC_MODEL = 0.42                 # base composition of the Monte-Carlo that ranks hash candidates
 SEQUENTIAL_MAX = 3               # lanes with at most this many entries are summed without a table
-SWIZZLE_MIN_BITS = 6            # lanes with at least this many index bits xor their top 4 hash bits into the slot              # bit-flip hill climbing on the best candidate
+SWIZZLE_MIN_BITS = 6            # lanes with at least this many index bits add their top 4 hash bits to the slot              # bit-flip hill climbing on the best candidate
 N_CANDIDATES = 24               # injective hashes collected per lane before the best one is kept
 
 
@@ -186,7 +186,7 @@ def find_hash(entries, seed, offset):
                     hh += (mc_pat[gi] * np.uint64(mg[gi])) & m32
                 sl = ((hh & m32) >> np.uint64(32 - bits)).astype(np.int64)
                 if bits >= SWIZZLE_MIN_BITS:
-                    sl ^= sl >> (bits - 4)
+                    sl += sl >> (bits - 4)
                 return expected_wavefronts(sl, offset)
 
             def injective(mg):
@@ -199,7 +199,7 @@ def find_hash(entries, seed, offset):
             best = min(((cost_of(mg), mg) for mg in found[:N_CANDIDATES]), key=lambda t: t[0])
             import sys
             print(f"lane hash: {len(states)} states, {bits} bits, {len(found)} candidates, expected wavefronts "
-                  f"{best[0]:.2f}{' (xor swizzle)' if bits >= SWIZZLE_MIN_BITS else ''}", file=sys.stderr)
+                  f"{best[0]:.2f}{' (additive swizzle)' if bits >= SWIZZLE_MIN_BITS else ''}", file=sys.stderr)
             return bits, [(c1, sum(1 << bit_of(entries[i]) for i in idxs), best[1][gi])
                           for gi, (c1, idxs) in enumerate(glist)]
     raise SystemExit("no perfect hash found")
@@ -225,7 +225,8 @@ def main():
     emit("struct Rs1Entry { int pos; int first_base; double weight; int bit; int forced; };     // first_base < 0: first-order term")
     emit("struct Rs1Group { int first_base; unsigned mask; unsigned magic; };")
     emit("// table slot of a set of matching entries: s = (sum over groups of x_g * magic  mod 2^32) >> (32 - bits),")
-    emit("// then s ^ (s >> (bits - 4)) if swizzle (spreads the probable states over the shared-memory banks)")
+    emit("// then s + (s >> (bits - 4)) if swizzle: injective (the table has 16 spare slots), costs no ALU instruction")
+    emit("// (the add rides on the multiply-high) and spreads the probable states over the shared-memory banks")
     emit("struct Rs1Lane { const char *name; int lane_base; int n_entries; int n_table; int bits; int swizzle; int offset; "
          "int n_groups; Rs1Group groups[4]; Rs1Entry entries[16]; };")
     descs, code, offset, consts = [], [], 0, []
@@ -260,7 +261,7 @@ def main():
                 terms.append(f"{src} * 0x{mg:x}u")
             top = "RS1_SWZ" if bits >= SWIZZLE_MIN_BITS else "RS1_TOP"
             code.append(f"    double {name} = RS1_LD(T, {offset}u, {top}(" + " + ".join(terms) + f", {bits}));")
-            offset += 1 << bits
+            offset += (1 << bits) + (16 if bits >= SWIZZLE_MIN_BITS else 0)
         else:
             code.append(f"    double {name} = 0.0;")
         for p, c1, v, _, _ in tail:

@@ -32,8 +32,9 @@ __constant__ double c_rs1_k[] = RS1_K_VALUES;
 #define RS1_LD(T, off, idx8) (*reinterpret_cast<const double *>(reinterpret_cast<const char *>(T) + 8u * (off) + (idx8)))
 // top `bits` bits of the hash, scaled to bytes, as multiplies (FMA pipe; shifts would go to the ALU pipe)
 #define RS1_TOP(h, bits) (__umulhi((h), 1u << (bits)) * 8u)
-// the same with the top 4 hash bits xor-ed into the slot: spreads the probable states over the banks
-#define RS1_SWZ(h, bits) ((__umulhi((h), 1u << (bits)) * 8u) ^ (__umulhi((h), 16u) * 8u))
+// the same with the top 4 hash bits added to the slot (spreads the probable states over the banks;
+// the add is the accumulate operand of the multiply-high)
+#define RS1_SWZ(h, bits) ((__umulhi((h), 1u << (bits)) + __umulhi((h), 16u)) * 8u)
 #define RS1_SHL1(m) ((m) << 1)
 #define RS1_SHL(m, k) ((m) << (k))
 // acc + w iff the match bit is set, as ONE DFMA: bit (a single bit p >= 20 of a class mask)
@@ -86,7 +87,7 @@ static int build_rs1_tables(std::vector<double> &tab, char *err, size_t errlen) 
                 if (on) sum = sum + ln.entries[i].weight;
             }
             uint32_t slot = ln.bits ? h >> (32 - ln.bits) : 0u;
-            if (ln.swizzle) slot ^= slot >> (ln.bits - 4);
+            if (ln.swizzle) slot += slot >> (ln.bits - 4);
             const uint32_t idx = ln.offset + slot;
             if (idx >= RS1_TABLE_DOUBLES || used[idx]) {
                 snprintf(err, errlen, "rs1 table hash of lane %s is not injective", ln.name);
