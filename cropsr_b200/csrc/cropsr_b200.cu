@@ -780,6 +780,16 @@ static int scan_finish(crp_genome *g, crp_result *r) {
         if (int rc = launch_scan(g, r, plan)) return rc;
     }
     cudaEventElapsedTime(&r->ms_scan, r->ev[0], r->ev[1]);
+    if (r->scored && (r->flags & CRP_SCAN_LOGISTIC)) {
+        const uint64_t n[2] = {r->n_plus, r->n_minus};
+        for (int s = 0; s < 2; ++s)
+            if (n[s]) {
+                const uint64_t want = (n[s] + 255) / 256, cap = (uint64_t)g_ctx.sm_count * 16;
+                k_logistic<<<(unsigned)(want < cap ? want : cap), 256, 0, r->st>>>(r->x[s], n[s]);
+                g_ctx.launches++;
+            }
+        CUDA_TRY(cudaGetLastError());
+    }
     return 0;
 }
 

@@ -396,8 +396,7 @@ __device__ __forceinline__ void emit_strand(const ScanArgs &a, const double *__r
         __stcs(pos + i, t);
         if (kScore) {
             const Window w = extract_window<kMinus>(rec, pl, t, L);
-            double x = rs1_canonical(tab, w.s0, w.s1, w.valid);
-            if (a.flags & CRP_SCAN_LOGISTIC) x = 1.0 / (1.0 + exp(x));
+            const double x = rs1_canonical(tab, w.s0, w.s1, w.valid);
             __stcs(packed + i, w.packed);
             __stcs(xs + i, x);
         }
@@ -698,6 +697,12 @@ k_scan_score(const ScanArgs a) {
         dbg_stamp(5);
         wave_base += wave_total;
     }
+}
+
+// CRP_SCAN_LOGISTIC: x -> 1 / (1 + exp(x)) over a finished stream (device exp: not numpy's digits)
+__global__ void k_logistic(double *__restrict__ x, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = 1.0 / (1.0 + exp(x[i]));
 }
 
 struct RescoreItem {

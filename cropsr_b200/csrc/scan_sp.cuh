@@ -153,8 +153,7 @@ __device__ __forceinline__ void emit_strand_sp(const SpArgs &a, const double *__
         __stcs(pos + i, t);
         if (kScore) {
             const Window w = extract_window<kMinus>(rec, pl, t, L);
-            double x = rs1_canonical(tab, w.s0, w.s1, w.valid);
-            if (a.flags & CRP_SCAN_LOGISTIC) x = 1.0 / (1.0 + exp(x));
+            const double x = rs1_canonical(tab, w.s0, w.s1, w.valid);
             __stcs(packed + i, w.packed);
             __stcs(xs + i, x);
         }

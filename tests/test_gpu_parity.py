@@ -383,3 +383,21 @@ def test_cli_csv_same_with_and_without_device_ingest(manifest, eng, tmp_path):
                           case["blas_threads"], str(tmp_path / "time.txt"), out=lambda *a: None, device_ingest=dev)
         outs.append(out.read_bytes())
     assert outs[0] == outs[1] == golden_csv("sample").encode()
+
+
+def test_logistic_flag_applies_the_device_exp(eng):
+    """CRP_SCAN_LOGISTIC: the stored value is 1/(1+exp(x)) by the device's exp -- not numpy's digits
+    (the CSV path keeps x and applies numpy's exp on the host), so only closeness is asserted."""
+    from cropsr_b200 import ingest, pipeline, _native as N
+    tokens = ingest.fasta_text_to_tokens(synthetic_fasta(31, [50000], gc=0.5, lower_frac=0.1))
+    g1, r1, _ = pipeline.scan_tokens(tokens, 20)
+    g2, r2, _ = pipeline.scan_tokens(tokens, 20, flags=N.CRP_SCAN_LOGISTIC)
+    try:
+        for strand in "+-":
+            x = r1.fetch_segment(0, strand)["x"]
+            y = r2.fetch_segment(0, strand)["x"]
+            assert len(x) > 100
+            np.testing.assert_allclose(y, 1.0 / (1.0 + np.exp(x)), rtol=4e-16, atol=0)
+    finally:
+        for h in (r1, g1, r2, g2):
+            h.free()
