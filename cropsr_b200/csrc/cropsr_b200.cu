@@ -811,6 +811,27 @@ int crp_scan_score(crp_genome *g, int guide_len, uint32_t flags, crp_result **re
     return 0;
 }
 
+int crp_logistic(uint64_t n, const double *x, double *score) {
+    if (n && (!x || !score)) return fail(CRP_ERR_ARG, "NULL argument");
+    if (int rc = need_ctx()) return rc;
+    if (!n) return 0;
+    cudaStream_t st = g_ctx.stream;
+    double *d = nullptr;
+    if (dev_alloc(&d, n * sizeof(double), st) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CRP_ERR_NOMEM, "cudaMalloc of %llu doubles failed", (unsigned long long)n);
+    }
+    CUDA_TRY(cudaMemcpyAsync(d, x, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    const uint64_t want = (n + 255) / 256, cap = (uint64_t)g_ctx.sm_count * 16;
+    k_logistic<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(d, n);
+    g_ctx.launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(score, d, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    dev_free(d, st);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int crp_result_totals(const crp_result *res, uint64_t *n_plus, uint64_t *n_minus) {
     if (!res) return fail(CRP_ERR_ARG, "res is NULL");
     if (n_plus) *n_plus = res->n_plus;

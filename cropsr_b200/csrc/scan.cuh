@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "npexp.cuh"
 #include "rs1.cuh"
 
 namespace cg = cooperative_groups;
@@ -699,10 +700,10 @@ k_scan_score(const ScanArgs a) {
     }
 }
 
-// CRP_SCAN_LOGISTIC: x -> 1 / (1 + exp(x)) over a finished stream (device exp: not numpy's digits)
+// CRP_SCAN_LOGISTIC: x -> 1 / (1 + np.exp(x)) over a finished stream, numpy's digits (npexp.cuh)
 __global__ void k_logistic(double *__restrict__ x, uint64_t n) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = 1.0 / (1.0 + exp(x[i]));
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = np_logistic_f64(x[i]);
 }
 
 struct RescoreItem {

@@ -44,6 +44,14 @@ def launch_count():
     return n.value
 
 
+def logistic(x):
+    """1 / (1 + np.exp(x)) on the device with numpy's own digits (CROPSR.py:313; csrc/npexp.cuh)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    check(lib.crp_logistic(x.size, x.ctypes.data, out.ctypes.data))
+    return out
+
+
 def _as_u8(token):
     """Token -> contiguous uint8 numpy view (str is encoded; must be ASCII)."""
     if isinstance(token, str):

@@ -41,7 +41,7 @@ typedef struct crp_result crp_result;   /* compacted candidate streams in HBM   
 /* ---- scan flags --------------------------------------------------------- */
 #define CRP_SCAN_DEFAULT     0u
 #define CRP_SCAN_NO_SCORE    1u   /* positions only (forced when guide_len != 20)  */
-#define CRP_SCAN_LOGISTIC    2u   /* store 1/(1+exp(x)) instead of x (see below)   */
+#define CRP_SCAN_LOGISTIC    2u   /* store 1/(1+np.exp(x)) instead of x (see below) */
 #define CRP_SCAN_EXTRAS      4u   /* also compute the opt-in per-candidate extras  */
 
 /* ---- summation classes for crp_rescore -------------------- */
@@ -132,8 +132,8 @@ int crp_genome_free(crp_genome *g);
  *   x       float64 pre-activation -(((A+B)+0.59763615)+(-0.2026259)) summed
  *                   in the canonical lane order; the reference's score is
  *                   1/(1+np.exp(x)) (CROPSR.py:312-313).  With
- *                   CRP_SCAN_LOGISTIC the stored value is 1/(1+exp(x)) using
- *                   the device's exp (<= 2 ulp from numpy's).
+ *                   CRP_SCAN_LOGISTIC the stored value is that score itself, with
+ *                   numpy's digits (see crp_logistic).
  * Reference order of a token's candidates = its '+' stream then its '-' stream
  * (CROPSR.py:417-434).
  */
@@ -212,6 +212,13 @@ int crp_format_rows(uint64_t n_rows, const char *ids, const uint64_t *id_index, 
                     uint32_t n_tokens, const uint8_t *const *tokens, const uint64_t *token_len,
                     const char *const *chrom, const uint32_t *chrom_len, int guide_len, int n_threads,
                     char *out, uint64_t out_capacity, uint64_t *out_bytes);
+
+/* ---- the reference's logistic, CROPSR.py:313: score = 1 / (1 + np.exp(x)).  numpy's float64
+ * exp on an AVX-512 host is the vendored SVML routine __svml_exp8_ha; the device evaluates a
+ * restatement of it (csrc/npexp.cuh), so for |x| < 707.7 the result has numpy's digits, not
+ * libm's.  Host arrays in and out.  The same function is applied in place to the x streams of a
+ * scan started with CRP_SCAN_LOGISTIC. */
+int crp_logistic(uint64_t n, const double *x, double *score);
 
 /* Kernel timings (CUDA events on the library stream) of the last commit /
  * scan: milliseconds. */

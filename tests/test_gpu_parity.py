@@ -385,10 +385,28 @@ def test_cli_csv_same_with_and_without_device_ingest(manifest, eng, tmp_path):
     assert outs[0] == outs[1] == golden_csv("sample").encode()
 
 
-def test_logistic_flag_applies_the_device_exp(eng):
-    """CRP_SCAN_LOGISTIC: the stored value is 1/(1+exp(x)) by the device's exp -- not numpy's digits
-    (the CSV path keeps x and applies numpy's exp on the host), so only closeness is asserted."""
+def test_device_logistic_has_numpys_digits(eng):
+    """csrc/npexp.cuh: 1 / (1 + np.exp(x)) on the device equals the golden vectors of the reference
+    environment's numpy and the CPU oracle bit for bit -- and np.exp on this host if it is an AVX-512 one."""
+    from test_oracle_golden import oracle_np_exp
+    v = np.load(os.path.join(os.path.dirname(__file__), "golden", "np_exp_vectors.npz"))
+    keep = np.abs(v["x"]) < 700
+    assert np.array_equal(eng.logistic(v["x"][keep]), v["score"][keep])
+    rng = np.random.default_rng(9)
+    x = np.concatenate([rng.uniform(-18, 9, 2_000_000), rng.uniform(-700, 700, 200_000), rng.normal(0, 1, 200_000)])
+    with np.errstate(all="ignore"):
+        want = 1.0 / (1.0 + oracle_np_exp(x))
+    got = eng.logistic(x)
+    assert np.array_equal(got, want)
+    feats = getattr(np._core._multiarray_umath, "__cpu_features__", {})
+    if feats.get("AVX512_SKX"):
+        assert np.array_equal(got, 1.0 / (1.0 + np.exp(x)))
+
+
+def test_logistic_flag_stores_the_reference_score(eng):
+    """CRP_SCAN_LOGISTIC: the x stream holds 1 / (1 + np.exp(x)) with numpy's digits."""
     from cropsr_b200 import ingest, pipeline, _native as N
+    from test_oracle_golden import oracle_np_exp
     tokens = ingest.fasta_text_to_tokens(synthetic_fasta(31, [50000], gc=0.5, lower_frac=0.1))
     g1, r1, _ = pipeline.scan_tokens(tokens, 20)
     g2, r2, _ = pipeline.scan_tokens(tokens, 20, flags=N.CRP_SCAN_LOGISTIC)
@@ -397,7 +415,7 @@ def test_logistic_flag_applies_the_device_exp(eng):
             x = r1.fetch_segment(0, strand)["x"]
             y = r2.fetch_segment(0, strand)["x"]
             assert len(x) > 100
-            np.testing.assert_allclose(y, 1.0 / (1.0 + np.exp(x)), rtol=4e-16, atol=0)
+            assert np.array_equal(y, 1.0 / (1.0 + oracle_np_exp(x)))
     finally:
         for h in (r1, g1, r2, g2):
             h.free()

@@ -2,6 +2,7 @@
 byte-for-byte against the golden CSVs made by tests/golden/make_golden.py and
 against the SURVEY section-4 digests of the reference's shipped output.csv."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -67,3 +68,43 @@ def test_emission_slices_closed_form():
     # 1,124,799 rows -> rows 0..999,999 then 124,799..249,597
     assert oracle.emission_slices(1124799) == [(0, 1000000), (124799, 124799)]
     assert oracle.emission_slices(1000000) == []
+
+
+def _np_exp_oracle():
+    import ctypes
+    lib_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle", "libnp_exp.so")
+    if not os.path.exists(lib_path):
+        import subprocess
+        subprocess.run(["make", "-C", os.path.dirname(lib_path)], check=True)
+    return ctypes.CDLL(lib_path)
+
+
+def oracle_np_exp(x):
+    import ctypes
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.empty_like(x)
+    _np_exp_oracle().np_exp_f64_array(x.ctypes.data_as(ctypes.c_void_p), y.ctypes.data_as(ctypes.c_void_p),
+                                       ctypes.c_long(x.size))
+    return y
+
+
+def test_np_exp_oracle_equals_the_golden_vectors():
+    """oracle/np_exp.c (numpy's SVML exp restated) against vectors produced by the reference
+    environment's own np.exp (tests/golden/make_np_exp_vectors.py): bit for bit."""
+    v = np.load(os.path.join(os.path.dirname(__file__), "golden", "np_exp_vectors.npz"))
+    got = oracle_np_exp(v["x"])
+    assert np.array_equal(got, v["exp"])
+    with np.errstate(all="ignore"):
+        assert np.array_equal(1.0 / (1.0 + got), v["score"])
+
+
+def test_np_exp_oracle_equals_numpy_on_avx512_hosts():
+    """...and against np.exp itself where numpy takes the AVX-512 SVML path (the golden host did)."""
+    feats = getattr(getattr(np, "_core", None), "_multiarray_umath", None)
+    feats = getattr(feats, "__cpu_features__", {}) if feats is not None else {}
+    if not feats.get("AVX512_SKX"):
+        pytest.skip("numpy does not dispatch exp to the AVX-512 SVML routine on this host")
+    rng = np.random.default_rng(8)
+    x = np.concatenate([rng.uniform(-18, 9, 400000), rng.uniform(-700, 700, 100000), rng.normal(0, 1, 100001)])
+    assert np.array_equal(oracle_np_exp(x), np.exp(x))
+    assert np.array_equal(oracle_np_exp(x[:13]), np.exp(x[:13]))        # numpy's tail loop is the same routine
