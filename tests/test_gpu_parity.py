@@ -419,3 +419,15 @@ def test_logistic_flag_stores_the_reference_score(eng):
     finally:
         for h in (r1, g1, r2, g2):
             h.free()
+
+
+def test_experimental_single_pass_kernel_is_exact_too(eng):
+    """CRP_SCAN_KERNEL=sp (csrc/scan_sp.cuh, decoupled look-back; slower, kept as a measured
+    alternative) must give the same candidates and the same fp64 x: smoke() in a subprocess."""
+    import subprocess, sys
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    env = dict(os.environ, CRP_SCAN_KERNEL="sp")
+    out = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "smoke ok" in out.stdout
