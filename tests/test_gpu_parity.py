@@ -431,3 +431,11 @@ def test_experimental_single_pass_kernel_is_exact_too(eng):
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "smoke ok" in out.stdout
+
+
+def test_many_scaffolds_match_oracle(eng):
+    """configs[4] shape in small: hundreds of scaffolds, some shorter than one window, some a
+    few tiles long -- per-segment counts, order and scores against the oracle."""
+    rng = np.random.default_rng(77)
+    lengths = [int(x) for x in rng.integers(1, 3000, size=300)] + [40000, 16384, 16385, 1, 29, 30, 31, 52, 53]
+    _check_against_oracle(eng, synthetic_fasta(78, lengths, gc=0.5, lower_frac=0.2, n_frac=0.002, width=60), 20)

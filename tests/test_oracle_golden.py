@@ -108,3 +108,19 @@ def test_np_exp_oracle_equals_numpy_on_avx512_hosts():
     x = np.concatenate([rng.uniform(-18, 9, 400000), rng.uniform(-700, 700, 100000), rng.normal(0, 1, 100001)])
     assert np.array_equal(oracle_np_exp(x), np.exp(x))
     assert np.array_equal(oracle_np_exp(x[:13]), np.exp(x[:13]))        # numpy's tail loop is the same routine
+
+
+def test_every_scored_window_carries_the_pam_as_cc():
+    """csrc/gen_rs1_inc.py folds the PAM into the Rule-Set-1 lane tables: every 30-mer the
+    reference scores has upper-case C at 0-based positions 2 and 3 on both strands
+    (CROPSR.py:415-433).  Pinned here on the oracle's candidates of every fixture."""
+    seen = 0
+    for name in ("sample_genome.fa", "multi3.fa", "edge_fmt.fa", "edge_clean.fa", "mid50k.fa", "clean3.fa"):
+        from cropsr_b200 import ingest
+        for key, tok in ingest.fasta_text_to_tokens(fixture_text(name)).items():
+            for cand in oracle.candidates_for_token(key, tok, 20):
+                long_ = cand[4]
+                if len(long_) == 30:
+                    assert long_[2:4] == "CC", (name, cand)
+                    seen += 1
+    assert seen > 20000
