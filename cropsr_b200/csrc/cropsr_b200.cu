@@ -81,6 +81,7 @@ struct crp_genome {
     bool committed = false;
     uint64_t n_positions = 0;          // owned positions
     uint4 *records = nullptr;          // n_tiles tile records (scan.cuh)
+    unsigned char *pam = nullptr;      // n_tiles PAM records (count phase of the scan)
     uint32_t n_tiles = 0;
     uint32_t *d_seg_first = nullptr, *d_seg_count = nullptr;
     float ms_h2d = 0.f, ms_pack = 0.f;
@@ -402,7 +403,8 @@ static int commit_enqueue(crp_genome *g) {
     const size_t rec_bytes = (size_t)g->n_tiles * kRecBytes;
     if (dev_alloc(&d_ascii, ascii_bytes + 64, st) != cudaSuccess ||
         (!one && dev_alloc(&d_descs, (descs.size() + 1) * sizeof(PackDesc), st) != cudaSuccess) ||
-        dev_alloc(&g->records, rec_bytes + 16, st) != cudaSuccess) {
+        dev_alloc(&g->records, rec_bytes + 16, st) != cudaSuccess ||
+        dev_alloc(&g->pam, (size_t)g->n_tiles * kPamBytes + 16, st) != cudaSuccess) {
         cudaGetLastError();
         dev_free(d_ascii, st);
         dev_free(d_descs, st);
@@ -482,7 +484,7 @@ static int commit_enqueue(crp_genome *g) {
         PackDesc first = descs[0];
         if (one) first.td.n = (uint32_t)(g->segs[0].end - g->segs[0].begin);     // positions of the whole segment
         const uint64_t want = (n_items + 255) / 256, cap = (uint64_t)g_ctx.sm_count * 16;
-        k_pack<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(d_ascii, d_descs, first, n_items, g->records);
+        k_pack<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(d_ascii, d_descs, first, n_items, g->records, g->pam);
         g_ctx.launches++;
         CUDA_TRY(cudaGetLastError());
     }
@@ -529,6 +531,7 @@ int crp_genome_free(crp_genome *g) {
     if (!g) return 0;
     cudaStream_t st = stream_of(g);
     dev_free(g->records, st);
+    dev_free(g->pam, st);
     dev_free(g->sp_state, st);
     dev_free(g->d_ascii, st);
     pinned_put(g->h_bad);
@@ -680,6 +683,7 @@ static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p) {
     cudaStream_t st = r->st;
     ScanArgs a;
     a.records = g->records;
+    a.pam = g->pam;
     a.n_tiles = g->n_tiles;
     a.wave_tiles = p.wave_tiles;
     a.static_eighths = 4;

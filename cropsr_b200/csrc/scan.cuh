@@ -45,6 +45,11 @@ static constexpr uint32_t kNoTile = 0xFFFFFFFFu;
 static constexpr int kMaxRange = 32;                       // tiles per CTA per wave in the count phase
 static constexpr uint32_t kAlign = 128;                    // positions; segment placement granularity
 
+// PAM record of a tile, read by the count phase instead of the full record: descriptor, then for
+// the 512 tile words and the right halo word the two planes the PAM tests need (upper-case G,
+// upper-case C) -- 0.25 byte per base
+static constexpr int kPamWords = kTileWords + 1;           // uint2 {upper G, upper C} each
+static constexpr uint32_t kPamBytes = (16 + kPamWords * 8 + 15) / 16 * 16;   // 4128, one bulk copy
 static_assert(kRecBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
 
 // record word 0
@@ -86,7 +91,7 @@ __host__ __device__ inline uint32_t classify(uint32_t c) {
 // pipelined ingest needs no descriptor upload.
 __global__ void __launch_bounds__(256)
 k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, const PackDesc one, uint64_t n_items,
-       uint4 *__restrict__ records) {
+       uint4 *__restrict__ records, unsigned char *__restrict__ pam) {
     __shared__ uint8_t lut[256];
     lut[threadIdx.x] = (uint8_t)classify(threadIdx.x);
     __syncthreads();
@@ -104,7 +109,9 @@ k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, co
             pd.td.n = one.td.n - done < (uint32_t)kTile ? one.td.n - done : (uint32_t)kTile;
         }
         if (k == 0) {
-            records[it] = make_uint4(pd.td.t_start, pd.td.L, pd.td.n, pd.td.segment);
+            const uint4 d = make_uint4(pd.td.t_start, pd.td.L, pd.td.n, pd.td.segment);
+            records[it] = d;
+            *reinterpret_cast<uint4 *>(pam + tile * kPamBytes) = d;
             continue;
         }
         const int64_t p0 = (int64_t)pd.td.t_start + ((int64_t)k - 2) * 32;   // token position of bit 0
@@ -138,6 +145,10 @@ k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, co
             }
         }
         records[it] = make_uint4(o0, o1, ol, oo);
+        if (k >= 2) {                       // tile words and the right halo: the planes of the PAM tests
+            const uint32_t up = ~(ol | oo);
+            reinterpret_cast<uint2 *>(pam + tile * kPamBytes + 16)[k - 2] = make_uint2(o0 & o1 & up, ~o0 & o1 & up);
+        }
     }
 }
 
@@ -243,11 +254,9 @@ struct Hits {
 //   bounds (CROPSR.py:419 / :430): '+' t >= l+5;  '-' 2 <= t <= L-l+7
 //   plus ownership: t inside the n positions of the tile that the segment owns.
 // All positions fit int32: L < 2^31 - 2^15 (crp_genome_add_segment), 1 <= l <= 10^6.
-__device__ __forceinline__ Hits tile_hits(const uint4 *__restrict__ rec, const TileDesc td, int l, int wordA) {
-    const uint4 a = rec[2 + wordA], an = rec[3 + wordA], b = rec[34 + wordA], bn = rec[35 + wordA];
-    const uint32_t uA = ~(a.z | a.w), uAn = ~(an.z | an.w), uB = ~(b.z | b.w), uBn = ~(bn.z | bn.w);   // upper-case ACGT
-    const uint32_t gA = a.x & a.y & uA, gAn = an.x & an.y & uAn, gB = b.x & b.y & uB, gBn = bn.x & bn.y & uBn;
-    const uint32_t cA = ~a.x & a.y & uA, cAn = ~an.x & an.y & uAn, cB = ~b.x & b.y & uB, cBn = ~bn.x & bn.y & uBn;
+__device__ __forceinline__ Hits hits_from_planes(uint32_t gA, uint32_t gAn, uint32_t cA, uint32_t cAn, uint32_t gB,
+                                                 uint32_t gBn, uint32_t cB, uint32_t cBn, const TileDesc td, int l,
+                                                 int wordA) {
     Hits h;
     h.pA = __funnelshift_r(gA, gAn, 1) & __funnelshift_r(gA, gAn, 2);
     h.pB = __funnelshift_r(gB, gBn, 1) & __funnelshift_r(gB, gBn, 2);
@@ -267,8 +276,23 @@ __device__ __forceinline__ Hits tile_hits(const uint4 *__restrict__ rec, const T
     return h;
 }
 
+__device__ __forceinline__ Hits tile_hits(const uint4 *__restrict__ rec, const TileDesc td, int l, int wordA) {
+    const uint4 a = rec[2 + wordA], an = rec[3 + wordA], b = rec[34 + wordA], bn = rec[35 + wordA];
+    const uint32_t uA = ~(a.z | a.w), uAn = ~(an.z | an.w), uB = ~(b.z | b.w), uBn = ~(bn.z | bn.w);   // upper-case ACGT
+    return hits_from_planes(a.x & a.y & uA, an.x & an.y & uAn, ~a.x & a.y & uA, ~an.x & an.y & uAn, b.x & b.y & uB,
+                            bn.x & bn.y & uBn, ~b.x & b.y & uB, ~bn.x & bn.y & uBn, td, l, wordA);
+}
+
+// the same from a staged PAM record (count phase)
+__device__ __forceinline__ Hits tile_hits_pam(const unsigned char *__restrict__ rec, const TileDesc td, int l, int wordA) {
+    const uint2 *w = reinterpret_cast<const uint2 *>(rec + 16);
+    const uint2 a = w[wordA], an = w[wordA + 1], b = w[wordA + 32], bn = w[wordA + 33];
+    return hits_from_planes(a.x, an.x, a.y, an.y, b.x, bn.x, b.y, bn.y, td, l, wordA);
+}
+
 struct ScanArgs {
     const uint4 *records;            // n_tiles records of kRecWords words
+    const unsigned char *pam;        // n_tiles PAM records of kPamBytes bytes (count phase)
     uint32_t n_tiles;
     uint32_t wave_tiles;             // tiles per wave (<= gridDim.x * kMaxRange)
     uint32_t static_eighths;         // share of a wave's tiles dealt round-robin, in 1/8 (the rest are ticketed)
@@ -500,8 +524,8 @@ k_scan_score(const ScanArgs a) {
         auto produce_count = [&](uint32_t n, int s) {
             if (n < n_mine) {
                 ring.tile[s] = r_lo + n;
-                mbar_expect(&ring.full[s], kRecBytes);
-                bulk_copy(stage(s), record(r_lo + n), kRecBytes, &ring.full[s]);
+                mbar_expect(&ring.full[s], kPamBytes);
+                bulk_copy(stage(s), a.pam + (size_t)(r_lo + n) * kPamBytes, kPamBytes, &ring.full[s]);
             } else {
                 ring.tile[s] = kNoTile;
                 mbar_arrive(&ring.full[s]);
@@ -516,10 +540,9 @@ k_scan_score(const ScanArgs a) {
             const int s = n % kStages;
             mbar_wait(&ring.full[s], (n / kStages) & 1u);
             if (ring.tile[s] == kNoTile) break;
-            const uint4 *rec = stage(s);
-            const uint4 d = rec[0];
+            const uint4 d = stage(s)[0];
             const TileDesc td = {d.x, d.y, d.z, d.w};
-            const Hits h = tile_hits(rec, td, l, 64 * warp + lane);
+            const Hits h = tile_hits_pam(reinterpret_cast<const unsigned char *>(stage(s)), td, l, 64 * warp + lane);
             uint32_t c = (__popc(h.pA) + __popc(h.pB)) | ((__popc(h.mA) + __popc(h.mB)) << 16);
             c = __reduce_add_sync(0xFFFFFFFFu, c);
             if (lane == 0) {
