@@ -584,6 +584,7 @@ static int plan_scan(const crp_genome *g, bool scored, ScanPlan *p) {
     p->fn = scored ? (const void *)k_scan_score<true> : (const void *)k_scan_score<false>;
     const unsigned grid_max = (unsigned)g_ctx.sm_count * CRP_CTAS_PER_SM;
     p->smem = kScanSmemFixed + (size_t)grid_max * sizeof(unsigned long long);
+    if (p->smem < (size_t)kCountStages * kPamBytes) p->smem = (size_t)kCountStages * kPamBytes;   // the count ring reuses all of it
     static int per_sm_cache[2] = {0, 0};       // occupancy of the two instantiations, queried once
     int &per_sm = per_sm_cache[scored ? 1 : 0];
     if (per_sm == 0) {

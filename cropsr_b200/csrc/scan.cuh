@@ -50,6 +50,8 @@ static constexpr uint32_t kAlign = 128;                    // positions; segment
 // upper-case C) -- 0.25 byte per base
 static constexpr int kPamWords = kTileWords + 1;           // uint2 {upper G, upper C} each
 static constexpr uint32_t kPamBytes = (16 + kPamWords * 8 + 15) / 16 * 16;   // 4128, one bulk copy
+static constexpr int kCountStages = 6;                     // staged PAM records per CTA in the count phase: the tile
+                                                           // slots, the hit lists and the range prefixes are all idle then
 static_assert(kRecBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
 
 // record word 0
@@ -432,11 +434,12 @@ __device__ __forceinline__ void emit_strand(const ScanArgs &a, const double *__r
 // record and, in the emit phase, the tile's prefix block) have landed.
 struct __align__(16) Ring {
     unsigned long long pref[kStages][kPrefWords];   // bulk-copy destination (emit phase)
-    unsigned long long full[kStages];               // mbarriers
+    unsigned long long full[kCountStages];          // mbarriers (the emit phase uses the first kStages)
     unsigned long long rbase[kStages];              // global prefix of the count range of the staged tile (emit phase)
-    uint32_t tile[kStages];                         // staged tile, or kNoTile: the sequence has ended
-    uint32_t done[kStages];                         // warps finished with the slot (count phase)
+    uint32_t tile[kCountStages];                    // staged tile, or kNoTile: the sequence has ended
+    uint32_t done[kCountStages];                    // warps finished with the slot (count phase)
 };
+static_assert(kCountStages >= kStages, "the ring control block is sized by the count phase");
 
 __device__ __forceinline__ void mbar_inval(unsigned long long *bar) {
     asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -459,7 +462,7 @@ __device__ __forceinline__ void ring_reset(Ring &ring, bool first) {
     __syncthreads();
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < kCountStages; ++s) {
             if (!first) mbar_inval(&ring.full[s]);
             mbar_init(&ring.full[s], 1);
             ring.done[s] = 0;
@@ -521,11 +524,12 @@ k_scan_score(const ScanArgs a) {
 
         // ================================================= count phase: tiles [r_lo, r_lo + n_mine)
         const uint32_t r_lo = min(w_hi, w_lo + cta * k), n_mine = min(w_hi, r_lo + k) - r_lo;
+        auto pam_stage = [&](int s) { return s_dyn + (size_t)s * kPamBytes; };
         auto produce_count = [&](uint32_t n, int s) {
             if (n < n_mine) {
                 ring.tile[s] = r_lo + n;
                 mbar_expect(&ring.full[s], kPamBytes);
-                bulk_copy(stage(s), a.pam + (size_t)(r_lo + n) * kPamBytes, kPamBytes, &ring.full[s]);
+                bulk_copy(pam_stage(s), a.pam + (size_t)(r_lo + n) * kPamBytes, kPamBytes, &ring.full[s]);
             } else {
                 ring.tile[s] = kNoTile;
                 mbar_arrive(&ring.full[s]);
@@ -535,20 +539,20 @@ k_scan_score(const ScanArgs a) {
         ring_reset(ring, wave == 0);
         dbg_stamp(1);
         if (tid == 0)
-            for (int s = 0; s < kStages; ++s) produce_count(s, s);
+            for (int s = 0; s < kCountStages; ++s) produce_count(s, s);
         for (uint32_t n = 0;; ++n) {
-            const int s = n % kStages;
-            mbar_wait(&ring.full[s], (n / kStages) & 1u);
+            const int s = n % kCountStages;
+            mbar_wait(&ring.full[s], (n / kCountStages) & 1u);
             if (ring.tile[s] == kNoTile) break;
-            const uint4 d = stage(s)[0];
+            const uint4 d = *reinterpret_cast<const uint4 *>(pam_stage(s));
             const TileDesc td = {d.x, d.y, d.z, d.w};
-            const Hits h = tile_hits_pam(reinterpret_cast<const unsigned char *>(stage(s)), td, l, 64 * warp + lane);
+            const Hits h = tile_hits_pam(pam_stage(s), td, l, 64 * warp + lane);
             uint32_t c = (__popc(h.pA) + __popc(h.pB)) | ((__popc(h.mA) + __popc(h.mB)) << 16);
             c = __reduce_add_sync(0xFFFFFFFFu, c);
             if (lane == 0) {
                 s_cnt[n][warp] = c;
             }
-            if (release_slot(s)) produce_count(n + kStages, s);
+            if (release_slot(s)) produce_count(n + kCountStages, s);
         }
         __syncthreads();
         {   // exclusive scan over the (tile, warp) counts of the range: thread tid owns tile tid / 8, warp tid % 8
