@@ -88,6 +88,7 @@ SIGNATURES = {
                                   C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_int, C.c_void_p, C.c_uint64, _u64p]),
     "crp_logistic": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p]),
+    "crp_rs1_score": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crp_rescore": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crp_genome_timing": (C.c_int, [C.c_void_p, _f32p, _f32p]),
     "crp_result_timing": (C.c_int, [C.c_void_p, _f32p]),

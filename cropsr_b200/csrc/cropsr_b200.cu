@@ -816,6 +816,30 @@ int crp_scan_score(crp_genome *g, int guide_len, uint32_t flags, crp_result **re
     return 0;
 }
 
+int crp_rs1_score(uint64_t n, const uint8_t *rows, const uint8_t *cls, double *score) {
+    if (n && (!rows || !cls || !score)) return fail(CRP_ERR_ARG, "NULL argument");
+    if (int rc = need_ctx()) return rc;
+    if (!n) return 0;
+    cudaStream_t st = g_ctx.stream;
+    uint8_t *d_rows = nullptr;
+    double *d_out = nullptr;
+    if (dev_alloc(&d_rows, 31 * n, st) != cudaSuccess || dev_alloc(&d_out, n * sizeof(double), st) != cudaSuccess) {
+        cudaGetLastError();
+        dev_free(d_rows, st);
+        return fail(CRP_ERR_NOMEM, "cudaMalloc for %llu rows failed", (unsigned long long)n);
+    }
+    CUDA_TRY(cudaMemcpyAsync(d_rows, rows, 30 * n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_rows + 30 * n, cls, n, cudaMemcpyHostToDevice, st));
+    k_rs1_rows<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_rows, d_rows + 30 * n, n, d_out);
+    g_ctx.launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(score, d_out, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    dev_free(d_rows, st);
+    dev_free(d_out, st);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int crp_logistic(uint64_t n, const double *x, double *score) {
     if (n && (!x || !score)) return fail(CRP_ERR_ARG, "NULL argument");
     if (int rc = need_ctx()) return rc;

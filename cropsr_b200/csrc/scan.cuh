@@ -733,6 +733,27 @@ __global__ void k_logistic(double *__restrict__ x, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = np_logistic_f64(x[i]);
 }
 
+// rs1_score(sequences) of the reference (CROPSR.py:285-313) on its own input: n rows of 30
+// ASCII bytes (only 'A' 'T' 'C' 'G' score, CROPSR.py:300-302), row i summed in the BLAS class
+// cls[i] (first-order matmul | second-order matmul << 4), then the reference's logistic.
+__global__ void k_rs1_rows(const uint8_t *__restrict__ rows, const uint8_t *__restrict__ cls, uint64_t n,
+                           double *__restrict__ score) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *r = rows + 30 * i;
+    uint32_t s0 = 0, s1 = 0, valid = 0;
+    for (int q = 0; q < 30; ++q) {
+        const uint32_t c = r[q];
+        const uint32_t code = c == 'A' ? 0u : c == 'T' ? 1u : c == 'C' ? 2u : c == 'G' ? 3u : 4u;
+        if (code < 4u) {
+            valid |= 1u << q;
+            s0 |= (code & 1u) << q;
+            s1 |= (code >> 1) << q;
+        }
+    }
+    score[i] = np_logistic_f64(rs1_dense(s0, s1, valid, (int)(cls[i] & 15u), (int)(cls[i] >> 4)));
+}
+
 struct RescoreItem {
     uint32_t tile;     // record holding token position t
     uint32_t pl;       // position of t inside the tile

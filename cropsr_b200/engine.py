@@ -52,6 +52,15 @@ def logistic(x):
     return out
 
 
+def rs1_score(rows, cls):
+    """crp_rs1_score: rows (n, 30) uint8 ASCII, cls (n,) uint8 BLAS classes -> float64 scores."""
+    rows = np.ascontiguousarray(rows, dtype=np.uint8)
+    cls = np.ascontiguousarray(cls, dtype=np.uint8)
+    out = np.empty(len(rows), dtype=np.float64)
+    check(lib.crp_rs1_score(len(rows), rows.ctypes.data, cls.ctypes.data, out.ctypes.data))
+    return out
+
+
 def _as_u8(token):
     """Token -> contiguous uint8 numpy view (str is encoded; must be ASCII)."""
     if isinstance(token, str):

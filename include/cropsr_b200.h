@@ -220,6 +220,14 @@ int crp_format_rows(uint64_t n_rows, const char *ids, const uint64_t *id_index, 
  * scan started with CRP_SCAN_LOGISTIC. */
 int crp_logistic(uint64_t n, const double *x, double *score);
 
+/* rs1_score(sequences) itself (CROPSR.py:285-313) on the reference's own argument: n rows of 30
+ * ASCII bytes, row-major (only 'A' 'T' 'C' 'G' score, everything else contributes 0,
+ * CROPSR.py:300-302).  cls[i] = BLAS lane class of row i in the two np.matmul calls
+ * (CRP_CLASS_* of the first-order call | class of the second-order call << 4; which rows of an
+ * n-row call are not canonical is index logic, cropsr_b200/blas_order.py).  score[i] is the
+ * reference's return value, logistic included. */
+int crp_rs1_score(uint64_t n, const uint8_t *rows, const uint8_t *cls, double *score);
+
 /* Kernel timings (CUDA events on the library stream) of the last commit /
  * scan: milliseconds. */
 int crp_genome_timing(const crp_genome *g, float *ms_h2d, float *ms_pack);

@@ -439,3 +439,31 @@ def test_many_scaffolds_match_oracle(eng):
     rng = np.random.default_rng(77)
     lengths = [int(x) for x in rng.integers(1, 3000, size=300)] + [40000, 16384, 16385, 1, 29, 30, 31, 52, 53]
     _check_against_oracle(eng, synthetic_fasta(78, lengths, gc=0.5, lower_frac=0.2, n_frac=0.002, width=60), 20)
+
+
+def test_reference_callables_on_the_device(eng):
+    """CROPSR.find_PAM_site and CROPSR.rs1_score against the regex and against the
+    oracle's np.matmul / np.exp port of the reference function, for every row-count class."""
+    import re
+    import CROPSR
+    rng = np.random.default_rng(21)
+    for n in (0, 1, 2, 3, 5, 7, 40, 3000, 70001):
+        tok = "".join(rng.choice(list("ACGTacgtN"), size=n, p=[.2, .2, .22, .22, .04, .04, .03, .03, .02]))
+        for pat in ("(?=.GG)", "(?=CC.)"):
+            assert CROPSR.find_PAM_site(pat, tok) == [m.span() for m in re.finditer(pat, tok)], (n, pat)
+    tok = "GGGGGGGGCCCCCCCC" + "'),"
+    for pat in ("(?=.GG)", "(?=CC.)"):
+        assert CROPSR.find_PAM_site(pat, tok) == [m.span() for m in re.finditer(pat, tok)]
+    alphabet = np.frombuffer(b"ATCGNatcg'", dtype=np.uint8)
+    for n in (1, 2, 3, 4, 5, 6, 7, 8, 9, 4098, 4099):
+        seqs = rng.choice(alphabet, size=(n, 30), p=[.23, .23, .23, .23, .02, .01, .01, .01, .01, .02])
+        got = CROPSR.rs1_score(seqs)
+        assert np.array_equal(got, oracle.score_model(seqs, threads=1)), n
+        feats = getattr(np._core._multiarray_umath, "__cpu_features__", {})
+        if feats.get("AVX512_SKX") and os.environ.get("OPENBLAS_NUM_THREADS") == "1":
+            assert np.array_equal(got, oracle.score_blas(seqs)), n       # the reference function itself
+    # a placeholder row (CROPSR.py:459, np.empty(30,)) turns the reference's matrix into float64
+    ph = np.array([np.frombuffer(b"ACGT" * 7 + b"AC", np.uint8), np.full(30, 1e-310)])
+    conv = np.array([np.frombuffer(b"ACGT" * 7 + b"AC", np.uint8), np.zeros(30, np.uint8)])
+    assert ph.dtype == np.float64
+    assert np.array_equal(CROPSR.rs1_score(ph), oracle.score_model(conv, threads=1))

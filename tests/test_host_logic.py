@@ -232,3 +232,24 @@ def test_plain_fasta_layout_matches_text_ingest():
     for bad in (b"", b"ACGT\n", b">a\nAC\r\nGT\n", b">a b\nACGT\nAC\n", b">a\nACGT\n>a\nAC\nA\n", b">a\n>b\nAC\nA\n",
                 b">a'\nACGT\nA\n", b">a\nAC>GT\nAA\n"):
         assert ingest.plain_fasta_layout(bad) is None, bad
+
+
+def test_cropsr_module_keeps_the_reference_callables(built_lib):
+    """`import CROPSR` offers the callables of the reference's module that sit on the Cas9 path
+    (SURVEY 8b), and the host-side ones behave like the reference's (literal replace chains)."""
+    import CROPSR
+    for name in ("import_fasta_file", "import_gff_file", "find_PAM_site", "get_reverse_complement",
+                 "get_gRNA_sequence", "apply_cutsite", "rs1_score", "get_id", "main"):
+        assert callable(getattr(CROPSR, name)), name
+    rng = np.random.default_rng(12)
+    for _ in range(200):
+        s = "".join(rng.choice(list("ACGTacgtNUZ'),"), size=int(rng.integers(0, 40))))
+        assert CROPSR.get_gRNA_sequence(s) == oracle.grna(s)
+        assert CROPSR.get_reverse_complement(s) == oracle.reverse_complement(s)
+    assert CROPSR.apply_cutsite(5, 25, "cas9") == 22
+    np.random.seed(3)
+    a = CROPSR.get_id(5)
+    np.random.seed(3)
+    assert np.array_equal(a, np.random.choice(CROPSR.alphanum, [5, 7]))
+    with pytest.raises(NotImplementedError):
+        CROPSR.find_PAM_site("(?=TTT)", "ACGT")
