@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcropsr_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 CRP_SCAN_DEFAULT = 0
 CRP_SCAN_NO_SCORE = 1

@@ -27,7 +27,7 @@
 #include "scan_sp.cuh"
 #include "extras.cuh"
 
-#define CRP_ABI_VERSION 3
+#define CRP_ABI_VERSION 4
 
 static constexpr size_t kScanSmemFixed = (size_t)kStages * kRecBytes + 2 * (size_t)kListCap * sizeof(uint16_t);
 
