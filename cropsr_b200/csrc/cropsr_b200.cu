@@ -692,7 +692,7 @@ static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p) {
     a.guide_len = r->guide_len;
     a.flags = r->flags;
     a.tables = g_ctx.d_tables;
-    a.capacity = r->capacity;
+    a.capacity = r->capacity < 0xFFFFFFFFull ? r->capacity : 0xFFFFFFFFull;   // rows are 32-bit in the kernel (counts are packed 32 | 32)
     a.pos_plus = r->pos[0];
     a.pos_minus = r->pos[1];
     a.packed_plus = r->packed[0];

@@ -31,7 +31,8 @@ __global__ void k_extras(const ExtrasArgs a) {
     if (i >= a.n) return;
     const uint32_t t = a.pos[i], rel = t - a.seg_begin;
     const uint4 *rec = a.records + (size_t)(a.first_tile + rel / kTile) * kRecWords;
-    const Window w = a.minus ? extract_window<true>(rec, rel % kTile, t, a.L) : extract_window<false>(rec, rel % kTile, t, a.L);
+    const Window w = a.minus ? extract_window<true>(rec, rel % kTile + kWinBiasMinus, t, a.L)
+                             : extract_window<false>(rec, rel % kTile + kWinBiasPlus, t, a.L);
     const uint32_t v = w.valid & kProto, s0 = w.s0, s1 = w.s1;
     const uint32_t gc = __popc(s1 & v);                                    // C = 2, G = 3: high code bit
     const uint32_t isT = ~s1 & s0 & v;

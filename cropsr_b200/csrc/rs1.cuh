@@ -48,7 +48,8 @@ __device__ __forceinline__ double rs1_canonical(const double *__restrict__ T, ui
     const double first = __dadd_rn(__dadd_rn(fA, fC), __dadd_rn(fT, fG));
     const double second = __dadd_rn(__dadd_rn(dA, dC), __dadd_rn(dT, dG));
     // (score_first + score_second + intersect + low_gc) * -1, CROPSR.py:312
-    return -__dadd_rn(__dadd_rn(__dadd_rn(first, second), RS1_K(RS1_K_INTERCEPT)), RS1_K(RS1_K_LOW_GC));
+    // -(t + k) == (-t) + (-k) in IEEE arithmetic: the final negation rides on the operands
+    return __dadd_rn(-__dadd_rn(__dadd_rn(first, second), RS1_K(RS1_K_INTERCEPT)), -RS1_K(RS1_K_LOW_GC));
 }
 
 // Host side: exact sequential sums of every valid subset of each lane's table entries

@@ -332,11 +332,12 @@ struct Window {
 
 // 30-base window of one hit out of the staged record.
 // '+': tok[t-25, t+5) read backwards (output base q = tok[t+4-q]), upper-case bases complemented;
-// '-': tok[t-2, t+28) read forwards.   pl = position inside the tile.
+// '-': tok[t-2, t+28) read forwards.   ws = position inside the tile + kWinBias: the window start
+// relative to the first halo position (the hit lists hold this biased value).
+static constexpr uint32_t kWinBiasPlus = 7u, kWinBiasMinus = 30u;
 template <bool kMinus>
-__device__ __forceinline__ Window extract_window(const uint4 *__restrict__ rec, uint32_t pl, uint32_t t, uint32_t L) {
-    const uint32_t ws = pl + (kMinus ? 30u : 7u);           // relative to the first halo position
-    const uint32_t wi = 1u + (ws >> 5), sh = ws & 31u;
+__device__ __forceinline__ Window extract_window(const uint4 *__restrict__ rec, uint32_t ws, uint32_t t, uint32_t L) {
+    const uint32_t wi = 1u + (ws >> 5), sh = ws;            // shf.r.wrap uses the low 5 bits of the amount
     const uint4 lo = rec[wi], hi = rec[wi + 1];
     const uint32_t p0 = __funnelshift_r(lo.x, hi.x, sh), p1 = __funnelshift_r(lo.y, hi.y, sh);
     const uint32_t lw = __funnelshift_r(lo.z, hi.z, sh), ot = __funnelshift_r(lo.w, hi.w, sh);
@@ -352,10 +353,11 @@ __device__ __forceinline__ Window extract_window(const uint4 *__restrict__ rec, 
         w.s1 = __brev(p1) >> 2;
         w.valid = __brev(valid) >> 2;
     }
-    uint32_t hi32 = w.s1;
-    if (w.valid != 0x3FFFFFFFu) hi32 |= (uint32_t)(CRP_PACKED_UNSCORED >> 32);
-    uint32_t lo32 = w.s0;
-    if ((lw | ot) & 0x3FFFFFFFu) lo32 |= (uint32_t)CRP_PACKED_IRREGULAR;
+    // flags without predicates: valid <= 0x3FFFFFFF, so bit 30 of valid + 1 is set iff all 30 bases
+    // score; x <= 0x3FFFFFFF, so bit 30 of x + 0x3FFFFFFF is set iff x != 0
+    const uint32_t hi32 = w.s1 | (~(w.valid + 1u) & (uint32_t)(CRP_PACKED_UNSCORED >> 32));
+    const uint32_t irr = (lw | ot) & 0x3FFFFFFFu;
+    uint32_t lo32 = w.s0 | ((irr + 0x3FFFFFFFu) & (uint32_t)CRP_PACKED_IRREGULAR);
     if (t + (kMinus ? 28u : 5u) > L) lo32 |= (uint32_t)CRP_PACKED_TRUNCATED;
     w.packed = ((unsigned long long)hi32 << 32) | lo32;
     return w;
@@ -412,20 +414,24 @@ __device__ __forceinline__ void list_hits_window(uint16_t *__restrict__ list, ui
 template <bool kScore, bool kMinus>
 __device__ __forceinline__ void emit_strand(const ScanArgs &a, const double *__restrict__ tab,
                                             const uint4 *__restrict__ rec, const uint16_t *__restrict__ list,
-                                            uint32_t count, uint64_t out0, uint32_t t_start, uint32_t L, uint32_t slot) {
-    if (out0 >= a.capacity) return;
-    if (count > a.capacity - out0) count = (uint32_t)(a.capacity - out0);
-    uint32_t *const pos = (kMinus ? a.pos_minus : a.pos_plus) + out0;
-    unsigned long long *const packed = (kMinus ? a.packed_minus : a.packed_plus) + out0;
-    double *const xs = (kMinus ? a.x_minus : a.x_plus) + out0;
+                                            uint32_t count, uint32_t row0, uint32_t t_start, uint32_t L, uint32_t slot) {
+    // rows of a strand stream fit 32 bits: the scan state packs the two strand counts of a
+    // shard into one 64-bit word (plus << 32 | minus), and launch_scan clamps the capacity
+    const uint32_t cap = (uint32_t)a.capacity;
+    if (row0 >= cap) return;
+    if (count > cap - row0) count = cap - row0;
+    uint32_t *const pos = kMinus ? a.pos_minus : a.pos_plus;
+    unsigned long long *const packed = kMinus ? a.packed_minus : a.packed_plus;
+    double *const xs = kMinus ? a.x_minus : a.x_plus;
     for (uint32_t i = slot; i < count; i += kThreads) {
-        const uint32_t pl = list[i], t = t_start + pl;
-        __stcs(pos + i, t);
+        const uint32_t ws = list[i], t = t_start - (kMinus ? kWinBiasMinus : kWinBiasPlus) + ws;
+        const uint32_t row = row0 + i;
+        __stcs(pos + row, t);
         if (kScore) {
-            const Window w = extract_window<kMinus>(rec, pl, t, L);
+            const Window w = extract_window<kMinus>(rec, ws, t, L);
             const double x = rs1_canonical(tab, w.s0, w.s1, w.valid);
-            __stcs(packed + i, w.packed);
-            __stcs(xs + i, x);
+            __stcs(packed + row, w.packed);
+            __stcs(xs + row, x);
         }
     }
 }
@@ -679,7 +685,7 @@ k_scan_score(const ScanArgs a) {
             const unsigned long long off = ring.pref[s][warp] - tile_pref;          // hits of the tile before my warp chunk
             const unsigned long long tot = ring.pref[s][kWarps] - tile_pref;
             const uint32_t np = (uint32_t)(tot >> 32), nm = (uint32_t)tot;
-            const uint64_t base_p = base >> 32, base_m = base & 0xFFFFFFFFull;
+            const uint32_t base_p = (uint32_t)(base >> 32), base_m = (uint32_t)base;
             const uint32_t wordA = 64 * warp + lane;
             const Hits h = tile_hits(rec, td, l, wordA);
             // ---- warp scan of the per-word counts: the A words of the chunk precede its B words
@@ -699,10 +705,10 @@ k_scan_score(const ScanArgs a) {
             const uint32_t op = (uint32_t)(off >> 32), om = (uint32_t)off;
             const uint32_t epA = op + (xA & 0xFFFFu), emA = om + (xA >> 16), epB = op + (xB & 0xFFFFu), emB = om + (xB >> 16);
             if (np <= (uint32_t)kListCap && nm <= (uint32_t)kListCap) {
-                list_hits(list_p + epA, h.pA, 32u * wordA);
-                list_hits(list_p + epB, h.pB, 32u * (wordA + 32));
-                list_hits(list_m + emA, h.mA, 32u * wordA);
-                list_hits(list_m + emB, h.mB, 32u * (wordA + 32));
+                list_hits(list_p + epA, h.pA, 32u * wordA + kWinBiasPlus);
+                list_hits(list_p + epB, h.pB, 32u * (wordA + 32) + kWinBiasPlus);
+                list_hits(list_m + emA, h.mA, 32u * wordA + kWinBiasMinus);
+                list_hits(list_m + emB, h.mB, 32u * (wordA + 32) + kWinBiasMinus);
                 __syncthreads();
                 emit_strand<kScore, false>(a, s_tab, rec, list_p, np, base_p, td.t_start, td.L, tid);
                 emit_strand<kScore, true>(a, s_tab, rec, list_m, nm, base_m, td.t_start, td.L, tid ^ (kThreads / 2));
@@ -711,10 +717,10 @@ k_scan_score(const ScanArgs a) {
                     const uint32_t cp = np > lo ? min(np - lo, (uint32_t)kListCap) : 0u;
                     const uint32_t cm = nm > lo ? min(nm - lo, (uint32_t)kListCap) : 0u;
                     if (lo) __syncthreads();
-                    list_hits_window(list_p, h.pA, epA, 32u * wordA, lo);
-                    list_hits_window(list_p, h.pB, epB, 32u * (wordA + 32), lo);
-                    list_hits_window(list_m, h.mA, emA, 32u * wordA, lo);
-                    list_hits_window(list_m, h.mB, emB, 32u * (wordA + 32), lo);
+                    list_hits_window(list_p, h.pA, epA, 32u * wordA + kWinBiasPlus, lo);
+                    list_hits_window(list_p, h.pB, epB, 32u * (wordA + 32) + kWinBiasPlus, lo);
+                    list_hits_window(list_m, h.mA, emA, 32u * wordA + kWinBiasMinus, lo);
+                    list_hits_window(list_m, h.mB, emB, 32u * (wordA + 32) + kWinBiasMinus, lo);
                     __syncthreads();
                     emit_strand<kScore, false>(a, s_tab, rec, list_p, cp, base_p + lo, td.t_start, td.L, tid);
                     emit_strand<kScore, true>(a, s_tab, rec, list_m, cm, base_m + lo, td.t_start, td.L, tid);
@@ -767,7 +773,7 @@ __global__ void k_rescore(const uint4 *__restrict__ records, const RescoreItem *
     if (i >= n) return;
     const RescoreItem it = items[i];
     const uint4 *rec = records + (size_t)it.tile * kRecWords;
-    const Window w = it.strand == '-' ? extract_window<true>(rec, it.pl, 0u, 0xFFFFFFFFu)
-                                      : extract_window<false>(rec, it.pl, 0u, 0xFFFFFFFFu);
+    const Window w = it.strand == '-' ? extract_window<true>(rec, it.pl + kWinBiasMinus, 0u, 0xFFFFFFFFu)
+                                      : extract_window<false>(rec, it.pl + kWinBiasPlus, 0u, 0xFFFFFFFFu);
     x_out[i] = rs1_dense(w.s0, w.s1, w.valid, (int)(it.cls & 15u), (int)(it.cls >> 4));
 }

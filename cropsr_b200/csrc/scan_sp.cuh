@@ -152,7 +152,7 @@ __device__ __forceinline__ void emit_strand_sp(const SpArgs &a, const double *__
         const uint32_t pl = list[i], t = t_start + pl;
         __stcs(pos + i, t);
         if (kScore) {
-            const Window w = extract_window<kMinus>(rec, pl, t, L);
+            const Window w = extract_window<kMinus>(rec, pl + (kMinus ? kWinBiasMinus : kWinBiasPlus), t, L);
             const double x = rs1_canonical(tab, w.s0, w.s1, w.valid);
             __stcs(packed + i, w.packed);
             __stcs(xs + i, x);

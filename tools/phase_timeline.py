@@ -31,10 +31,10 @@ for rep in range(3):
     r.free()
 _native.check(_native.lib.crp_debug_set_times(None))
 T = buf.cpu().numpy().reshape(-1, 8)
-T = T[T[:, 0] > 0][:, :6]
+T = T[T[:, 0] > 0]
 t0 = T[:, 0].min()
 rel = (T - t0) / 1000.0
-names = ["start", "count_begin", "count_end", "grid_sync_end", "emit_begin", "emit_end"]
+names = ["start", "count_begin", "count_end", "grid_sync_end", "emit_begin", "emit_end", "range_scan_end", "first_tile"]
 print(f"scan {ms * 1e3:.1f} us (events), {len(T)} CTAs; microseconds since the first CTA started")
 for k, n in enumerate(names):
     c = rel[:, k]
