@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcropsr_b200.so")
+# CROPSR_B200_LIB: another build of the same library (kernel experiments, tools/variants.sh)
+LIB_PATH = os.environ.get("CROPSR_B200_LIB") or os.path.join(_HERE, "libcropsr_b200.so")
 
 ABI_VERSION = 4
 

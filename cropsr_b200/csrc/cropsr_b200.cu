@@ -25,6 +25,7 @@
 #endif
 #include "scan.cuh"
 #include "scan_sp.cuh"
+#include "scan_ws.cuh"
 #include "extras.cuh"
 
 #define CRP_ABI_VERSION 4
@@ -55,6 +56,7 @@ struct Context {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t lanes[3] = {nullptr, nullptr, nullptr};   // crp_scan_segments pipeline
+    cudaStream_t lane_out = nullptr;                       // its device-to-host row copies
     uint64_t launches = 0;
     double *d_tables = nullptr;        // RS1 lane tables in device memory
 };
@@ -97,7 +99,7 @@ struct crp_genome {
 struct crp_result {
     const crp_genome *g = nullptr;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev[2] = {nullptr, nullptr};    // scan timing
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // scan start, scan end, counts on the host
     unsigned long long *h_counts = nullptr;    // pinned, [2*n_seg]: counts land here when the scan has run
     int guide_len = 0;
     uint32_t flags = 0;
@@ -134,15 +136,70 @@ static int need_ctx() {
     return 0;
 }
 
-// Device memory comes from the stream-ordered pool of the device, which crp_init tells to keep
-// freed blocks (cudaMalloc / cudaFree cost 10-70 ms per call on a 180 GB part; a genome commit
-// and a scan allocate ~1 GB between them).
+// Device memory comes from a block cache of this library: cudaMalloc / cudaFree cost 10-70 ms per
+// call on a 180 GB part and the driver's stream-ordered pool grows for milliseconds whenever the
+// set of live sizes changes, while a genome commit and a scan allocate ~1 GB between them.  A freed
+// block keeps an event recorded on the stream that used it last; whoever gets the block next makes
+// its stream wait for that event, so reuse across streams is ordered without any host wait.
+// Blocks are handed out best-fit within 1/8 of slack and only returned to the driver by crp_shutdown.
+struct DevBlock {
+    void *ptr;
+    size_t bytes;
+    cudaEvent_t ev;
+};
+static std::vector<DevBlock> g_dev_free;                       // idle blocks
+static std::vector<DevBlock> g_dev_live;                       // blocks handed out
 template <typename T>
 static cudaError_t dev_alloc(T **ptr, size_t bytes, cudaStream_t st) {
-    return cudaMallocAsync(reinterpret_cast<void **>(ptr), bytes ? bytes : 16, st);
+    const size_t want = (bytes ? bytes : 16) + 255 & ~(size_t)255;
+    size_t best = g_dev_free.size();
+    for (size_t i = 0; i < g_dev_free.size(); ++i) {
+        const size_t b = g_dev_free[i].bytes;
+        if (b >= want && b - want <= want / 8 + 4096 && (best == g_dev_free.size() || b < g_dev_free[best].bytes)) best = i;
+    }
+    DevBlock blk;
+    if (best < g_dev_free.size()) {
+        blk = g_dev_free[best];
+        g_dev_free.erase(g_dev_free.begin() + best);
+        if (cudaError_t e = cudaStreamWaitEvent(st, blk.ev, 0)) return e;
+    } else {
+        blk.bytes = want;
+        if (cudaMalloc(&blk.ptr, want) != cudaSuccess) {        // out of memory: give the idle blocks back first
+            cudaGetLastError();
+            cudaDeviceSynchronize();
+            for (DevBlock &b : g_dev_free) {
+                cudaFree(b.ptr);
+                cudaEventDestroy(b.ev);
+            }
+            g_dev_free.clear();
+            if (cudaError_t e = cudaMalloc(&blk.ptr, want)) return e;
+        }
+        if (cudaError_t e = cudaEventCreateWithFlags(&blk.ev, cudaEventDisableTiming)) {
+            cudaFree(blk.ptr);
+            return e;
+        }
+    }
+    g_dev_live.push_back(blk);
+    *ptr = reinterpret_cast<T *>(blk.ptr);
+    return cudaSuccess;
 }
 static void dev_free(void *ptr, cudaStream_t st) {
-    if (ptr) cudaFreeAsync(ptr, st);
+    if (!ptr) return;
+    for (size_t i = g_dev_live.size(); i-- > 0;)
+        if (g_dev_live[i].ptr == ptr) {
+            DevBlock blk = g_dev_live[i];
+            g_dev_live.erase(g_dev_live.begin() + i);
+            cudaEventRecord(blk.ev, st);
+            g_dev_free.push_back(blk);
+            return;
+        }
+}
+static void dev_cache_release() {
+    for (DevBlock &b : g_dev_free) {
+        cudaFree(b.ptr);
+        cudaEventDestroy(b.ev);
+    }
+    g_dev_free.clear();
 }
 
 // Small pinned host blocks (the per-scan counts) are recycled: cudaHostAlloc takes ~0.1 ms.
@@ -201,12 +258,6 @@ int crp_init(int device) {
                     prop.major, prop.minor);
     CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
     {
-        cudaMemPool_t pool;
-        CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t keep = UINT64_MAX;
-        CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    }
-    {
         std::vector<double> tab;
         char msg[128];
         if (build_rs1_tables(tab, msg, sizeof msg)) return fail(CRP_ERR_STATE, "%s", msg);
@@ -223,15 +274,14 @@ int crp_init(int device) {
 int crp_shutdown(void) {
     if (!g_ctx.ready) return 0;
     cudaStreamSynchronize(g_ctx.stream);
-    {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, g_ctx.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
-    }
+    cudaDeviceSynchronize();
+    dev_cache_release();
     for (auto &pf : g_pinned_free) cudaFreeHost(reinterpret_cast<char *>(pf.second) - sizeof(size_t) * 2);
     g_pinned_free.clear();
     cudaStreamDestroy(g_ctx.stream);
     for (cudaStream_t l : g_ctx.lanes)
         if (l) cudaStreamDestroy(l);
+    if (g_ctx.lane_out) cudaStreamDestroy(g_ctx.lane_out);
     cudaFree(g_ctx.d_tables);
     g_ctx = Context();
     return 0;
@@ -575,12 +625,52 @@ oom:
 // Launch geometry of the cooperative scan kernel for a genome of n_tiles tiles.
 struct ScanPlan {
     const void *fn;
-    unsigned grid;
+    unsigned grid, threads;
     size_t smem;
     uint32_t wave_tiles, n_waves;
 };
 
+// CRP_SCAN_KERNEL: "ws" = warp-specialised kernel (scan_ws.cuh), "sp" = experimental single-pass
+// kernel (scan_sp.cuh), anything else = the two-phase kernel of scan.cuh
+static int scan_kernel_choice() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CRP_SCAN_KERNEL");
+        v = (e && !strcmp(e, "sp")) ? 1 : (e && !strcmp(e, "ws")) ? 2 : 0;
+    }
+    return v;
+}
+
+static int plan_scan_ws(const crp_genome *g, bool scored, ScanPlan *p) {
+    p->fn = scored ? (const void *)k_scan_ws<true> : (const void *)k_scan_ws<false>;
+    p->threads = kWsThreads;
+    p->smem = kWsSmem;
+    static bool ready[2] = {false, false};
+    if (!ready[scored ? 1 : 0]) {
+        CUDA_TRY(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p->fn, kWsThreads, p->smem));
+        if (per_sm < 1) return fail(CRP_ERR_CUDA, "warp-specialised scan kernel does not fit on an SM");
+        ready[scored ? 1 : 0] = true;
+    }
+    uint64_t grid = (uint64_t)g_ctx.sm_count;
+    if (grid > (uint64_t)kWsMaxGrid) grid = kWsMaxGrid;
+    if (grid > g->n_tiles) grid = g->n_tiles;
+    if (grid < 1) grid = 1;
+    p->grid = (unsigned)grid;
+    uint64_t wave = grid * kWsMaxRange;
+    if (const char *e = getenv("CRP_WAVE_TILES")) {
+        const long v = atol(e);
+        if (v > 0 && (uint64_t)v < wave) wave = (uint64_t)v;
+    }
+    p->wave_tiles = (uint32_t)wave;
+    p->n_waves = (uint32_t)((g->n_tiles + wave - 1) / wave);
+    return 0;
+}
+
 static int plan_scan(const crp_genome *g, bool scored, ScanPlan *p) {
+    if (scan_kernel_choice() == 2) return plan_scan_ws(g, scored, p);
+    p->threads = kThreads;
     p->fn = scored ? (const void *)k_scan_score<true> : (const void *)k_scan_score<false>;
     const unsigned grid_max = (unsigned)g_ctx.sm_count * CRP_CTAS_PER_SM;
     p->smem = kScanSmemFixed + (size_t)grid_max * sizeof(unsigned long long);
@@ -612,14 +702,7 @@ static int plan_scan(const crp_genome *g, bool scored, ScanPlan *p) {
 
 // CRP_SCAN_KERNEL=sp selects the experimental single-pass kernel (scan_sp.cuh); the default
 // is the two-phase cooperative kernel (scan.cuh), which is faster
-static bool use_single_pass() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("CRP_SCAN_KERNEL");
-        v = (e && !strcmp(e, "sp")) ? 1 : 0;
-    }
-    return v == 1;
-}
+static bool use_single_pass() { return scan_kernel_choice() == 1; }
 
 // single-pass kernel (scan_sp.cuh): one CTA of 4 teams per SM, ordinary launch
 static int launch_scan_sp(const crp_genome *g, crp_result *r) {
@@ -676,6 +759,7 @@ static int launch_scan_sp(const crp_genome *g, crp_result *r) {
     if (n_seg)
         CUDA_TRY(cudaMemcpyAsync(r->h_counts, r->d_counts, 2 * (size_t)n_seg * sizeof(unsigned long long),
                                  cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(r->ev[2], st));
     return 0;
 }
 
@@ -711,7 +795,7 @@ static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p) {
     CUDA_TRY(cudaEventRecord(r->ev[0], st));
     if (g->n_tiles) {
         void *params[] = {(void *)&a};
-        CUDA_TRY(cudaLaunchCooperativeKernel(p.fn, dim3(p.grid), dim3(kThreads), params, p.smem, st));
+        CUDA_TRY(cudaLaunchCooperativeKernel(p.fn, dim3(p.grid), dim3(p.threads), params, p.smem, st));
         g_ctx.launches++;
         CUDA_TRY(cudaGetLastError());
     } else if (n_seg) {
@@ -721,6 +805,7 @@ static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p) {
     if (n_seg)
         CUDA_TRY(cudaMemcpyAsync(r->h_counts, r->d_counts, 2 * (size_t)n_seg * sizeof(unsigned long long),
                                  cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(r->ev[2], st));
     return 0;
 }
 
@@ -749,7 +834,8 @@ static int scan_enqueue(crp_genome *g, int guide_len, uint32_t flags, crp_result
     r->d_counts = reinterpret_cast<unsigned long long *>(r->state + r->zero_offset);
     r->h_counts = static_cast<unsigned long long *>(pinned_get((2 * (size_t)n_seg + 1) * sizeof(unsigned long long)));
     if (!r->h_counts) return bail(fail(CRP_ERR_NOMEM, "cudaHostAlloc of the counts failed"));
-    if (cudaEventCreate(&r->ev[0]) != cudaSuccess || cudaEventCreate(&r->ev[1]) != cudaSuccess)
+    if (cudaEventCreate(&r->ev[0]) != cudaSuccess || cudaEventCreate(&r->ev[1]) != cudaSuccess ||
+        cudaEventCreateWithFlags(&r->ev[2], cudaEventDisableTiming) != cudaSuccess)
         return bail(fail(CRP_ERR_CUDA, "cudaEventCreate failed"));
     // First guess of the per-strand capacity: 1/8 candidate per position (GC 70 %
     // upper-case sequence gives 0.1225); a second pass with the exact counts
@@ -764,7 +850,7 @@ static int scan_enqueue(crp_genome *g, int guide_len, uint32_t flags, crp_result
 static int scan_finish(crp_genome *g, crp_result *r) {
     const uint32_t n_seg = (uint32_t)g->segs.size();
     for (int attempt = 0; attempt < 2; ++attempt) {
-        if (cudaError_t e = cudaStreamSynchronize(r->st))
+        if (cudaError_t e = cudaEventSynchronize(r->ev[2]))   // not the stream: it may already hold later segments
             return fail(CRP_ERR_CUDA, "scan kernels failed: %s", cudaGetErrorString(e));
         r->n_plus = r->n_minus = 0;
         r->seg_plus.assign(n_seg, 0);
@@ -885,8 +971,8 @@ int crp_result_device_counts(const crp_result *res, void **dev_ptr) {
 
 // D2H of rows [first, first + count) of one strand stream, enqueued on the result's stream
 static int fetch_enqueue(const crp_result *res, int s, uint64_t first, uint64_t count, uint32_t *pos, uint64_t *packed,
-                         double *x) {
-    cudaStream_t st = res->st;
+                         double *x, cudaStream_t st = nullptr) {
+    if (!st) st = res->st;
     if (count) {
         if (pos) CUDA_TRY(cudaMemcpyAsync(pos, res->pos[s] + first, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         if (packed)
@@ -952,8 +1038,12 @@ int crp_scan_segments(uint32_t n_segments, const crp_segment_desc *segments, int
     uint64_t off[2] = {0, 0};
     float ms = 0.f;
     bool overflow = false;
-    // counts of segment k are needed on the host before its rows can be placed: finish k-1
-    // right after k has been enqueued, so that the copy engines and the SMs never wait for us
+    // Segments are enqueued AHEAD of the one whose counts the host waits for (its rows can only be
+    // placed once the counts of every earlier segment are known): up to kAheadBytes of tokens, at
+    // least two segments, so that the host-to-device copy engine always has the next token queued.
+    // The rows leave on a stream of their own: a lane may already hold later segments.
+    constexpr uint64_t kAheadBytes = 512ull << 20;
+    if (!g_ctx.lane_out) CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.lane_out, cudaStreamNonBlocking));
     auto finish = [&](uint32_t k) -> int {
         if (int e = scan_finish(gs[k], rs[k])) return e;
         n_plus[k] = rs[k]->n_plus;
@@ -964,29 +1054,42 @@ int crp_scan_segments(uint32_t n_segments, const crp_segment_desc *segments, int
         } else {
             if (int e = fetch_enqueue(rs[k], 0, 0, rs[k]->n_plus, pos_plus ? pos_plus + off[0] : nullptr,
                                       scored && packed_plus ? packed_plus + off[0] : nullptr,
-                                      scored && x_plus ? x_plus + off[0] : nullptr)) return e;
+                                      scored && x_plus ? x_plus + off[0] : nullptr, g_ctx.lane_out)) return e;
             if (int e = fetch_enqueue(rs[k], 1, 0, rs[k]->n_minus, pos_minus ? pos_minus + off[1] : nullptr,
                                       scored && packed_minus ? packed_minus + off[1] : nullptr,
-                                      scored && x_minus ? x_minus + off[1] : nullptr)) return e;
+                                      scored && x_minus ? x_minus + off[1] : nullptr, g_ctx.lane_out)) return e;
         }
         off[0] += rs[k]->n_plus;
         off[1] += rs[k]->n_minus;
         return 0;
     };
-    for (uint32_t k = 0; k < n_segments && !rc; ++k) {
+    auto enqueue = [&](uint32_t k) -> int {
         const crp_segment_desc &sd = segments[k];
-        if ((rc = crp_genome_new(&gs[k]))) break;
+        if (int e = crp_genome_new(&gs[k])) return e;
         gs[k]->st = g_ctx.lanes[k % kLanes];
-        if ((rc = crp_genome_add_segment(gs[k], sd.token_id, sd.token, sd.token_len, sd.begin, sd.end))) break;
-        if ((rc = commit_enqueue(gs[k]))) break;
-        if ((rc = scan_enqueue(gs[k], guide_len, flags, &rs[k]))) break;
+        if (int e = crp_genome_add_segment(gs[k], sd.token_id, sd.token, sd.token_len, sd.begin, sd.end)) return e;
+        if (int e = commit_enqueue(gs[k])) return e;
+        return scan_enqueue(gs[k], guide_len, flags, &rs[k]);
+    };
+    auto seg_bytes = [&](uint32_t k) -> uint64_t {
+        const uint64_t end = segments[k].end ? segments[k].end : segments[k].token_len;
+        return end > segments[k].begin ? end - segments[k].begin : 0;
+    };
+    uint32_t next_enq = 0;
+    uint64_t ahead = 0;
+    for (uint32_t k = 0; k < n_segments && !rc; ++k) {
+        while (!rc && next_enq < n_segments && (next_enq < k + 2 || ahead + seg_bytes(next_enq) <= kAheadBytes)) {
+            rc = enqueue(next_enq);
+            ahead += seg_bytes(next_enq);
+            ++next_enq;
+        }
         tr.lap("enqueue");
-        if (k > 0) rc = finish(k - 1);
-        tr.lap("finish prev");
+        if (!rc) rc = finish(k);
+        ahead -= seg_bytes(k);
+        tr.lap("finish");
     }
-    if (!rc && n_segments) rc = finish(n_segments - 1);
-    tr.lap("finish last");
     for (int i = 0; i < kLanes; ++i) cudaStreamSynchronize(g_ctx.lanes[i]);
+    cudaStreamSynchronize(g_ctx.lane_out);
     tr.lap("drain");
     for (uint32_t k = 0; k < n_segments; ++k) {
         crp_result_free(rs[k]);

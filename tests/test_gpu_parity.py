@@ -421,16 +421,26 @@ def test_logistic_flag_stores_the_reference_score(eng):
             h.free()
 
 
-def test_experimental_single_pass_kernel_is_exact_too(eng):
-    """CRP_SCAN_KERNEL=sp (csrc/scan_sp.cuh, decoupled look-back; slower, kept as a measured
-    alternative) must give the same candidates and the same fp64 x: smoke() in a subprocess."""
+@pytest.mark.parametrize("kernel", ["sp", "ws"])
+def test_alternative_scan_kernels_are_exact_too(eng, kernel):
+    """CRP_SCAN_KERNEL=sp (csrc/scan_sp.cuh, single pass with decoupled look-back) and =ws
+    (csrc/scan_ws.cuh, warp-specialised emit phase) are slower than the default kernel and kept as
+    measured alternatives; they must give the same candidates and the same fp64 x.
+    The library reads the variable once, so they run in a subprocess: smoke(), and for ws the
+    tile-edge / dense-tile / multi-wave / random-FASTA / sharding cases of this file as well."""
     import subprocess, sys
     root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
-    env = dict(os.environ, CRP_SCAN_KERNEL="sp")
+    env = dict(os.environ, CRP_SCAN_KERNEL=kernel)
     out = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, env=env,
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "smoke ok" in out.stdout
+    if kernel == "sp" or os.environ.get("CRP_SCAN_KERNEL"):
+        return                      # the wider set is for ws; and never recurse from inside such a subprocess
+    out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_parity.py", "-k",
+                          "tile_boundaries or multi_wave or random_fastas or many_scaffolds or sharded_scan"],
+                         cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
 
 
 def test_many_scaffolds_match_oracle(eng):

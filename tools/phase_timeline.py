@@ -41,3 +41,10 @@ for k, n in enumerate(names):
     print(f"{n:>14}: min {c.min():7.1f}  p50 {np.median(c):7.1f}  p90 {np.percentile(c, 90):7.1f}  max {c.max():7.1f}")
 d = rel[:, 5] - rel[:, 4]
 print(f"emit duration per CTA: min {d.min():.1f} p50 {np.median(d):.1f} max {d.max():.1f}")
+
+if os.environ.get("CRP_WS_WAITSTATS"):
+    # slots 1, 6, 7 hold cycle counts (front-end warp 0 waiting for records, loader waiting for a free
+    # stage, first body warp waiting for lists), accumulated since the buffer was zeroed
+    for k, n in ((1, "fe wait rec_full"), (6, "loader wait empty"), (7, "body wait list_full")):
+        c = T[:, k].astype(float) / 1.9e3
+        print(f"{n:>22}: p50 {np.median(c):7.1f} us  max {c.max():7.1f} us (at 1.9 GHz)")
