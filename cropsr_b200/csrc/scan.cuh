@@ -292,6 +292,39 @@ __device__ __forceinline__ Hits tile_hits_pam(const unsigned char *__restrict__ 
     return hits_from_planes(a.x, an.x, a.y, an.y, b.x, bn.x, b.y, bn.y, td, l, wordA);
 }
 
+// Count phase: ONE warp counts a whole staged PAM record.  Lane l owns the words 32 i + l
+// (i = 0 .. 15); warp chunk c of the tile (what a warp of the emit phase compacts) is the words
+// [64 c, 64 c + 64), i.e. iterations 2 c and 2 c + 1.  cnt[c] = (plus | minus << 16) of chunk c.
+__device__ __forceinline__ void warp_count_tile(const unsigned char *__restrict__ rec, int l, int lane,
+                                                uint32_t *__restrict__ cnt) {
+    const uint4 d = *reinterpret_cast<const uint4 *>(rec);
+    const uint2 *w = reinterpret_cast<const uint2 *>(rec + 16);
+    const int32_t t0 = (int32_t)d.x, L = (int32_t)d.y;
+    const int32_t last_owned = t0 + (int32_t)d.z - 1;
+    const int32_t hi_p = min(L - 3, last_owned);
+    const int32_t hi_m = min(L - l + 7, hi_p);
+    const bool edge = t0 < l + 5 || t0 + kTile - 1 > hi_m;         // warp-uniform
+#pragma unroll
+    for (int c = 0; c < kWarps; ++c) {
+        uint32_t n = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int word = 64 * c + 32 * h + lane;
+            const uint2 a = w[word], an = w[word + 1];
+            uint32_t p = __funnelshift_r(a.x, an.x, 1) & __funnelshift_r(a.x, an.x, 2);
+            uint32_t m = a.y & __funnelshift_r(a.y, an.y, 1);
+            if (edge) {
+                const int32_t tw = t0 + 32 * word;
+                p &= range_mask(tw, l + 5, hi_p);
+                m &= range_mask(tw, 2, hi_m);
+            }
+            n += __popc(p) | (__popc(m) << 16);
+        }
+        n = __reduce_add_sync(0xFFFFFFFFu, n);
+        if (lane == 0) cnt[c] = n;
+    }
+}
+
 struct ScanArgs {
     const uint4 *records;            // n_tiles records of kRecWords words
     const unsigned char *pam;        // n_tiles PAM records of kPamBytes bytes (count phase)
@@ -441,6 +474,7 @@ __device__ __forceinline__ void emit_strand(const ScanArgs &a, const double *__r
 struct __align__(16) Ring {
     unsigned long long pref[kStages][kPrefWords];   // bulk-copy destination (emit phase)
     unsigned long long full[kCountStages];          // mbarriers (the emit phase uses the first kStages)
+    unsigned long long pre;                         // first emit tile of a wave, fetched before the grid barrier
     unsigned long long rbase[kStages];              // global prefix of the count range of the staged tile (emit phase)
     uint32_t tile[kCountStages];                    // staged tile, or kNoTile: the sequence has ended
     uint32_t done[kCountStages];                    // warps finished with the slot (count phase)
@@ -464,7 +498,7 @@ __device__ __forceinline__ void bulk_copy(void *dst, const void *src, uint32_t b
 }
 
 // (re)arm the ring at the start of a phase; every thread of the CTA calls it
-__device__ __forceinline__ void ring_reset(Ring &ring, bool first) {
+__device__ __forceinline__ void ring_reset(Ring &ring, bool first, bool wave_start) {
     __syncthreads();
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -472,6 +506,11 @@ __device__ __forceinline__ void ring_reset(Ring &ring, bool first) {
             if (!first) mbar_inval(&ring.full[s]);
             mbar_init(&ring.full[s], 1);
             ring.done[s] = 0;
+            ring.tile[s] = kNoTile;
+        }
+        if (wave_start) {
+            if (!first) mbar_inval(&ring.pre);
+            mbar_init(&ring.pre, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -510,17 +549,6 @@ k_scan_score(const ScanArgs a) {
     }
 
     auto record = [&](uint32_t tile) { return a.records + (size_t)tile * kRecWords; };
-    // warp-level: count this warp done with slot s; true on the lane that must refill the slot
-    auto release_slot = [&](int s) -> bool {
-        __syncwarp();
-        bool refill = false;
-        if (lane == 0) {
-            refill = atomicAdd(&ring.done[s], 1u) == (uint32_t)kWarps - 1u;
-            if (refill) ring.done[s] = 0;
-        }
-        return refill;
-    };
-
     unsigned long long wave_base = 0;
     uint32_t wave = 0;
     for (uint32_t w_lo = 0; w_lo < a.n_tiles; w_lo += a.wave_tiles, ++wave) {
@@ -531,34 +559,28 @@ k_scan_score(const ScanArgs a) {
         // ================================================= count phase: tiles [r_lo, r_lo + n_mine)
         const uint32_t r_lo = min(w_hi, w_lo + cta * k), n_mine = min(w_hi, r_lo + k) - r_lo;
         auto pam_stage = [&](int s) { return s_dyn + (size_t)s * kPamBytes; };
-        auto produce_count = [&](uint32_t n, int s) {
-            if (n < n_mine) {
-                ring.tile[s] = r_lo + n;
-                mbar_expect(&ring.full[s], kPamBytes);
-                bulk_copy(pam_stage(s), a.pam + (size_t)(r_lo + n) * kPamBytes, kPamBytes, &ring.full[s]);
-            } else {
-                ring.tile[s] = kNoTile;
-                mbar_arrive(&ring.full[s]);
-            }
+        auto produce_count = [&](uint32_t n) {            // n < n_mine
+            const int s = n % kCountStages;
+            *reinterpret_cast<volatile uint32_t *>(&ring.tile[s]) = n;    // which tile of the range the slot is (being) filled with
+            mbar_expect(&ring.full[s], kPamBytes);
+            bulk_copy(pam_stage(s), a.pam + (size_t)(r_lo + n) * kPamBytes, kPamBytes, &ring.full[s]);
         };
         if (cta == 0 && tid == 0) a.tickets[wave] = 0;             // read after the grid barrier
-        ring_reset(ring, wave == 0);
+        ring_reset(ring, wave == 0, true);
         dbg_stamp(1);
         if (tid == 0)
-            for (int s = 0; s < kCountStages; ++s) produce_count(s, s);
-        for (uint32_t n = 0;; ++n) {
+            for (uint32_t n = 0; n < (uint32_t)kCountStages && n < n_mine; ++n) produce_count(n);
+        // Tile n of the range goes to warp n % 8, which counts all of it and then refills the slot
+        // with tile n + 6: no hand-over between warps, ~250 instructions per tile instead of 8 x 80.
+        // A warp only visits its own tiles, so it may find the slot several refills behind; the
+        // parity of an mbarrier cannot tell those apart, the slot's tile number can.
+        for (uint32_t n = warp; n < n_mine; n += kWarps) {
             const int s = n % kCountStages;
+            while (*reinterpret_cast<volatile uint32_t *>(&ring.tile[s]) != n) __nanosleep(32);
             mbar_wait(&ring.full[s], (n / kCountStages) & 1u);
-            if (ring.tile[s] == kNoTile) break;
-            const uint4 d = *reinterpret_cast<const uint4 *>(pam_stage(s));
-            const TileDesc td = {d.x, d.y, d.z, d.w};
-            const Hits h = tile_hits_pam(pam_stage(s), td, l, 64 * warp + lane);
-            uint32_t c = (__popc(h.pA) + __popc(h.pB)) | ((__popc(h.mA) + __popc(h.mB)) << 16);
-            c = __reduce_add_sync(0xFFFFFFFFu, c);
-            if (lane == 0) {
-                s_cnt[n][warp] = c;
-            }
-            if (release_slot(s)) produce_count(n + kCountStages, s);
+            warp_count_tile(pam_stage(s), l, lane, s_cnt[n]);
+            __syncwarp();
+            if (lane == 0 && n + kCountStages < n_mine) produce_count(n + kCountStages);
         }
         __syncthreads();
         {   // exclusive scan over the (tile, warp) counts of the range: thread tid owns tile tid / 8, warp tid % 8
@@ -587,9 +609,20 @@ k_scan_score(const ScanArgs a) {
             }
             if (tid == 0) a.cta_tot[(wave & 1u) * G + cta] = total;
         }
+        // The first emit tile of this CTA is known (static share): its record is fetched across the
+        // grid barrier -- the count ring is idle now -- and its prefix block, which another CTA may
+        // have written, right after the barrier.
+        const uint32_t ns = (uint32_t)((unsigned long long)nt * a.static_eighths / 8 / G);
+        const bool pre = ns > 0;
+        const uint32_t t_pre = w_lo + cta;
+        if (pre && tid == 0) {
+            mbar_expect(&ring.pre, kRecBytes + kPrefWords * 8);
+            bulk_copy(stage(0), record(t_pre), kRecBytes, &ring.pre);
+        }
         dbg_stamp(2);
         grid.sync();
         dbg_stamp(3);
+        if (pre && tid == 0) bulk_copy(ring.pref[0], a.warp_pref + (size_t)t_pre * kPrefWords, kPrefWords * 8, &ring.pre);
 
         // ================================================= exclusive scan of the range totals
         unsigned long long wave_total;
@@ -630,7 +663,6 @@ k_scan_score(const ScanArgs a) {
         // The first ns * G tiles of the wave are dealt round-robin (tile known without a
         // round trip); the rest go through the ticket counter, which evens out what the
         // data-dependent emit work left unbalanced.
-        const uint32_t ns = (uint32_t)((unsigned long long)nt * a.static_eighths / 8 / G);
         const uint32_t dyn_lo = w_lo + ns * G, n_dyn = w_hi - dyn_lo;
         unsigned int *const ticket = a.tickets + wave;
         auto produce_emit = [&](uint32_t n, int s) {     // one thread: stage tile number n of this CTA into slot s
@@ -651,7 +683,7 @@ k_scan_score(const ScanArgs a) {
                 mbar_arrive(&ring.full[s]);
             }
         };
-        ring_reset(ring, false);                                   // also publishes s_rangepref
+        ring_reset(ring, false, false);                            // also publishes s_rangepref
         dbg_stamp(4);
         if (kScore && wave == 0) mbar_wait(&s_tabbar, 0);
         // per-segment candidate counts of this wave: prefix at the end of the segment's last
@@ -668,20 +700,25 @@ k_scan_score(const ScanArgs a) {
             a.seg_counts[sg] = (wave ? a.seg_counts[sg] : 0ull) + plus;
             a.seg_counts[a.n_seg + sg] = (wave ? a.seg_counts[a.n_seg + sg] : 0ull) + minus;
         }
-        if (tid == 0) produce_emit(0, 0);
+        if (tid == 0) {
+            if (pre) mbar_arrive(&ring.full[0]);                   // tile 0 came through ring.pre: skip that phase of slot 0
+            else produce_emit(0, 0);
+        }
         uint16_t *const list_p = s_list, *const list_m = s_list + kListCap;
         for (uint32_t n = 0;; ++n) {
             const int s = n % kStages;
             // next tile of this CTA: its copies land while this tile is emitted (slot s^1 was
             // released by the barrier that ended tile n - 1)
             if (tid == 0) produce_emit(n + 1, s ^ 1);
-            mbar_wait(&ring.full[s], (n / kStages) & 1u);
-            if (ring.tile[s] == kNoTile) break;
+            const bool first_pre = pre && n == 0;
+            if (first_pre) mbar_wait(&ring.pre, 0u);
+            else mbar_wait(&ring.full[s], (n / kStages) & 1u);
+            if (!first_pre && ring.tile[s] == kNoTile) break;
             const uint4 *rec = stage(s);
             const uint4 d = rec[0];
             const TileDesc td = {d.x, d.y, d.z, d.w};
             const unsigned long long tile_pref = ring.pref[s][0];
-            const unsigned long long base = ring.rbase[s] + tile_pref;
+            const unsigned long long base = (first_pre ? s_rangepref[(t_pre - w_lo) / k] : ring.rbase[s]) + tile_pref;
             const unsigned long long off = ring.pref[s][warp] - tile_pref;          // hits of the tile before my warp chunk
             const unsigned long long tot = ring.pref[s][kWarps] - tile_pref;
             const uint32_t np = (uint32_t)(tot >> 32), nm = (uint32_t)tot;

@@ -246,6 +246,21 @@ def test_multi_wave_scan_matches_oracle(eng, monkeypatch):
     _check_against_oracle(eng, synthetic_fasta(23, [90000], gc=0.5), 20)
 
 
+def test_long_count_ranges_and_prefetched_first_tile(eng, monkeypatch):
+    """With few CTAs every CTA counts a long range of tiles (the 6-slot ring of PAM records is
+    refilled several times, by different warps) and its first emit tile is fetched across the
+    grid barrier; on a full-size genome that is the normal case, here 3 and 7 CTAs force it on
+    ~100 tiles.  Also with two waves."""
+    text = synthetic_fasta(31, [900000, 650000, 37], gc=0.45, lower_frac=0.15, n_frac=0.001)
+    monkeypatch.setenv("CRP_SCAN_GRID", "3")
+    _check_against_oracle(eng, text, 20)
+    monkeypatch.setenv("CRP_SCAN_GRID", "7")
+    monkeypatch.setenv("CRP_WAVE_TILES", "60")
+    _check_against_oracle(eng, text, 20)
+    monkeypatch.setenv("CRP_STATIC_EIGHTHS", "8")
+    _check_against_oracle(eng, text, 20)
+
+
 def test_pipelined_call_equals_plain_scan(eng):
     """crp_scan_segments (overlapped H2D / pack / scan / D2H, one segment at a time) returns
     exactly the rows of the plain add_segment/commit/scan/fetch path, in segment order."""
