@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CROPSR_B200_LIB: another build of the same library (kernel experiments, tools/variants.sh)
 LIB_PATH = os.environ.get("CROPSR_B200_LIB") or os.path.join(_HERE, "libcropsr_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 CRP_SCAN_DEFAULT = 0
 CRP_SCAN_NO_SCORE = 1
@@ -31,6 +31,12 @@ class SegmentDesc(C.Structure):
     """crp_segment_desc"""
     _fields_ = [("token_id", C.c_uint32), ("token", C.c_void_p), ("token_len", C.c_uint64),
                 ("begin", C.c_uint64), ("end", C.c_uint64)]
+
+
+class PrimerParams(C.Structure):
+    """crp_primer_params: the CLI flags -e -s -l -m -x -M -X -D of the reference's prmrdsgn2.py (:26-54)"""
+    _fields_ = [("e", C.c_uint32), ("s", C.c_uint32), ("l", C.c_uint32), ("m", C.c_double), ("x", C.c_double),
+                ("M", C.c_double), ("X", C.c_double), ("D", C.c_double)]
 
 
 class CropsrError(RuntimeError):
@@ -85,6 +91,8 @@ SIGNATURES = {
     "crp_result_extras": (C.c_int, [C.c_void_p, C.c_uint32, C.c_char, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "crp_result_annotate": (C.c_int, [C.c_void_p, C.c_uint32, C.c_char, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crp_primer_windows": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrimerParams),
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crp_format_rows": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_int, C.c_void_p, C.c_uint64, _u64p]),

@@ -26,9 +26,10 @@
 #include "scan.cuh"
 #include "scan_sp.cuh"
 #include "scan_ws.cuh"
+#include "primers.cuh"
 #include "extras.cuh"
 
-#define CRP_ABI_VERSION 4
+#define CRP_ABI_VERSION 5
 
 static constexpr size_t kScanSmemFixed = (size_t)kStages * kRecBytes + 2 * (size_t)kListCap * sizeof(uint16_t);
 
@@ -1171,6 +1172,91 @@ int crp_result_extras(const crp_result *res, uint32_t segment, char strand, uint
         rc = fail(CRP_ERR_CUDA, "extras kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
     dev_free(d8, st);
     dev_free(d32, st);
+    return rc;
+}
+
+int crp_primer_windows(const crp_genome *g, uint64_t n, const uint32_t *segment, const uint32_t *lo, const uint32_t *hi,
+                       const crp_primer_params *prm, uint32_t *n_fwd, uint32_t *n_rev, uint64_t *n_pairs,
+                       uint16_t *first, uint8_t *status) {
+    if (!g || !prm) return fail(CRP_ERR_ARG, "NULL argument");
+    if (int rc = need_ctx()) return rc;
+    if (!g->committed) return fail(CRP_ERR_STATE, "genome is not committed");
+    if (n == 0) return 0;
+    if (!segment || !lo || !hi) return fail(CRP_ERR_ARG, "NULL window arrays");
+    if (prm->e < 1 || prm->e + prm->l > (uint32_t)kPrimerMaxRegion)
+        return fail(CRP_ERR_ARG, "primer extension e=%u with l=%u unsupported: need 1 <= e and e + l <= %d", prm->e, prm->l,
+                    kPrimerMaxRegion);
+    PrimerClasses pc;
+    memset(&pc, 0, sizeof pc);
+    char msg[160];
+    if (build_primer_classes((int)prm->s, (int)prm->l, prm->m, prm->x, prm->M, prm->X, prm->D, &pc, msg, sizeof msg))
+        return fail(CRP_ERR_ARG, "%s", msg);
+    std::vector<uint32_t> h(4 * n);             // first_tile | seg_begin | lo | hi
+    for (uint64_t i = 0; i < n; ++i) {
+        if (segment[i] >= g->segs.size()) return fail(CRP_ERR_ARG, "window %llu: segment %u out of range", (unsigned long long)i, segment[i]);
+        const Segment &sg = g->segs[segment[i]];
+        if (lo[i] > hi[i] || lo[i] < sg.begin || hi[i] > sg.end)
+            return fail(CRP_ERR_ARG, "window %llu [%u, %u) is not inside the positions [%llu, %llu) segment %u owns",
+                        (unsigned long long)i, lo[i], hi[i], (unsigned long long)sg.begin, (unsigned long long)sg.end, segment[i]);
+        h[i] = sg.first_tile;
+        h[n + i] = (uint32_t)sg.begin;
+        h[2 * n + i] = lo[i];
+        h[3 * n + i] = hi[i];
+    }
+    cudaStream_t st = stream_of(g);
+    uint32_t *d_in = nullptr, *d_cnt = nullptr;
+    unsigned long long *d_pairs = nullptr;
+    uint16_t *d_first = nullptr;
+    uint8_t *d_status = nullptr;
+    PrimerClasses *d_cls = nullptr;
+    int rc = 0;
+    if (dev_alloc(&d_in, 4 * n * sizeof(uint32_t), st) || dev_alloc(&d_cnt, 2 * n * sizeof(uint32_t), st) ||
+        dev_alloc(&d_pairs, n * sizeof(unsigned long long), st) || dev_alloc(&d_first, 4 * n * sizeof(uint16_t), st) ||
+        dev_alloc(&d_status, n, st) || dev_alloc(&d_cls, sizeof(PrimerClasses), st)) {
+        cudaGetLastError();
+        rc = fail(CRP_ERR_NOMEM, "cudaMalloc of primer buffers failed");
+    }
+    if (!rc) {
+        PrimerArgs a;
+        a.records = g->records;
+        a.cls = d_cls;
+        a.first_tile = d_in;
+        a.seg_begin = d_in + n;
+        a.lo = d_in + 2 * n;
+        a.hi = d_in + 3 * n;
+        a.n = n;
+        a.e = prm->e;
+        a.n_fwd = d_cnt;
+        a.n_rev = d_cnt + n;
+        a.n_pairs = d_pairs;
+        a.first = d_first;
+        a.status = d_status;
+        const uint64_t want = (n + 7) / 8, cap = (uint64_t)g_ctx.sm_count * 8;
+        if (cudaMemcpyAsync(d_in, h.data(), 4 * n * sizeof(uint32_t), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaMemcpyAsync(d_cls, &pc, sizeof pc, cudaMemcpyHostToDevice, st) != cudaSuccess)
+            rc = fail(CRP_ERR_CUDA, "H2D of primer windows failed");
+        if (!rc) {
+            k_primers<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(a);
+            g_ctx.launches++;
+            auto back = [&](void *dst, const void *src, size_t bytes) {
+                if (dst && !rc && cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+                    rc = fail(CRP_ERR_CUDA, "D2H of primer results failed");
+            };
+            back(n_fwd, a.n_fwd, n * 4);
+            back(n_rev, a.n_rev, n * 4);
+            back(n_pairs, a.n_pairs, n * 8);
+            back(first, a.first, n * 8);
+            back(status, a.status, n);
+            if (!rc && cudaStreamSynchronize(st) != cudaSuccess)
+                rc = fail(CRP_ERR_CUDA, "primer kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+    }
+    dev_free(d_in, st);
+    dev_free(d_cnt, st);
+    dev_free(d_pairs, st);
+    dev_free(d_first, st);
+    dev_free(d_status, st);
+    dev_free(d_cls, st);
     return rc;
 }
 

@@ -57,30 +57,39 @@ def scan_fasta_file(fasta, guide_len=20, flags=0):
 def write_side_output(path, tokens, result, gff_frame, flank, formatted_path):
     """Opt-in table of the per-candidate side outputs (one row per unique candidate, reference
     order).  NOT part of the reference's CSV: GC, poly-T / homopolymer flags, cut site, the
-    +-L flank window and the GFF feature under the cut site (device kernels k_extras /
-    k_annotate; semantics in oracle/extras_oracle.py)."""
+    +-L flank window, the GFF feature under the cut site (device kernels k_extras / k_annotate;
+    semantics in oracle/extras_oracle.py) and the prmrdsgn2-style primer enumeration on the flank
+    (k_primers, cropsr_b200/primers.py: primers passing the GC / Tm filter on either side, Tm-compatible
+    pairs, the first pair; empty where the flank is shorter than e + l = 130 bases)."""
     import csv
-    from . import annotate
+    from . import annotate, primers
     ivs = annotate.intervals_for_tokens(gff_frame, list(tokens.keys()), formatted_path)
     with open(path, "w", newline="") as f:
         w = csv.writer(f, delimiter="\t")
         w.writerow(["chromosome", "strand", "pam_pos", "cutsite", "gc", "poly_t", "homopolymer", "low_gc",
-                    "unscored_base", "longest_run", "flank_start", "flank_end", "feature_type", "feature_attributes"])
+                    "unscored_base", "longest_run", "flank_start", "flank_end", "feature_type", "feature_attributes",
+                    "fwd_primers", "rev_primers", "primer_pairs", "first_pair"])
         for seg, key in enumerate(tokens.keys()):
             iv = ivs[seg]
             for strand in "+-":
                 pos = result.fetch_segment(seg, strand, want=("pos",))["pos"]
                 ex = result.extras(seg, strand, flank)
                 feat = result.annotate(seg, strand, iv["start"], iv["end"])
+                pr = primers.design_windows(result.genome, np.full(len(pos), seg, np.uint32), ex["flank_lo"], ex["flank_hi"])
                 rows = np.where(feat >= 0, iv["row"][np.maximum(feat, 0)] if len(iv["row"]) else -1, -1)
                 for i in range(len(pos)):
                     fl = int(ex["flags"][i])
                     ft, fa = "", ""
                     if rows[i] >= 0:
                         ft, fa = gff_frame.at[rows[i], "feature"], gff_frame.at[rows[i], "attributes"]
+                    prim = ["", "", "", ""]
+                    if pr["status"][i] == 0:
+                        fp = pr["first"][i]
+                        prim = [int(pr["n_fwd"][i]), int(pr["n_rev"][i]), int(pr["n_pairs"][i]),
+                                "" if fp[0] == 0xFFFF else f"{fp[0]}+{fp[1]}/{fp[2]}+{fp[3]}"]
                     w.writerow([key[1:], strand, int(pos[i]), int(ex["cut"][i]), int(ex["gc"][i]), fl & 1, (fl >> 1) & 1,
                                 (fl >> 2) & 1, (fl >> 3) & 1, int(ex["run"][i]), int(ex["flank_lo"][i]),
-                                int(ex["flank_hi"][i]), ft, fa])
+                                int(ex["flank_hi"][i]), ft, fa] + prim)
 
 
 def run_cas9(fasta, gff, output="data.csv", guide_len=20, verbose=False, blas_threads=1,

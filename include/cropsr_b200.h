@@ -201,6 +201,31 @@ int crp_result_extras(const crp_result *res, uint32_t segment, char strand, uint
 int crp_result_annotate(const crp_result *res, uint32_t segment, char strand, uint32_t n_intervals,
                         const uint32_t *start, const uint32_t *end, int32_t *feature);
 
+/* ---- primer enumeration over windows of a packed genome (opt-in).
+ * Replaces the part of /root/reference/prmrdsgn2.py that needs no aligner, for many fragments at
+ * once: get_primers (:115-124) on the fragment and on its reverse complement (:104-112), the
+ * Primer GC % / Tm (:76-95), filter_primers (:127-137) and the Tm pairing of main() (:260-266).
+ * The fields of crp_primer_params are the reference's CLI flags -e -s -l -m -x -M -X -D (:26-54).
+ * Window i is token positions [lo[i], hi[i]) of segment[i] (inside the positions that segment
+ * owns), e.g. the flank_lo / flank_hi of crp_result_extras.  Per window:
+ *   n_fwd / n_rev   primers that pass the GC / Tm filter, forward and reverse-complement side
+ *   n_pairs         pairs of itertools.product(forward, reverse) with math.isclose(Tm, Tm, abs_tol=D)
+ *   first[4 i ..]   the first such pair in the reference's order: forward (start, length),
+ *                   reverse (start on the reverse complement, length); 0xFFFF x 4 if there is none
+ *   status          0, or 1 if the window is shorter than e + l bases (the reference would slice
+ *                   short or empty primers there; such windows are reported, not designed)
+ * Limits: 12 <= s < l <= 32 (so every primer has >= 13 bases: one Tm formula), e + l <= 1024.
+ * Any output pointer may be NULL. */
+typedef struct crp_primer_params {
+    uint32_t e, s, l;           /* -e extension, -s shortest, -l longest                   */
+    double m, x;                /* -m / -x  min / max Tm                                   */
+    double M, X;                /* -M / -X  min / max GC percentage                        */
+    double D;                   /* -D accepted Tm difference of a pair                     */
+} crp_primer_params;
+int crp_primer_windows(const crp_genome *g, uint64_t n, const uint32_t *segment, const uint32_t *lo,
+                       const uint32_t *hi, const crp_primer_params *params, uint32_t *n_fwd, uint32_t *n_rev,
+                       uint64_t *n_pairs, uint16_t *first, uint8_t *status);
+
 /* ---- host-side row formatter: replaces the per-row tuple + csv.writer path of
  * CROPSR.py:463-474.  Writes n_rows CSV rows (excel dialect, "\r\n", repr() floats,
  * the 11-field error-row variant where scored[i] == 0) into `out`, byte-identical
