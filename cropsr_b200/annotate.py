@@ -43,3 +43,53 @@ def intervals_for_tokens(frame, keys, formatted_path, features=DEFAULT_FEATURES)
         out.append({"start": start[order].astype(np.uint32), "end": end[order].astype(np.uint32),
                     "row": g.index.to_numpy()[order]})
     return out
+
+
+# ------------------------------------------------------------------ Phytozome annotation_info.txt
+# The reference accepts -p / --phytozome and only echoes the path (/root/reference/CROPSR.py:32,364);
+# its README.md:71-74 states the intent ("functional annotation").  Here the file enriches the opt-in
+# side output: the annotation_info row of the locus / transcript a GFF feature belongs to.  Semantics
+# are this module's own (unpinned by the reference), tested in tests/test_host_logic.py.
+PHYTOZOME_COLUMNS = ("pacId", "locusName", "transcriptName", "peptideName", "Pfam", "Panther", "KOG", "ec", "KO", "GO",
+                     "Best-hit-arabi-name", "arabi-symbol", "arabi-defline")
+
+
+def read_annotation_info(path):
+    """Phytozome `*.annotation_info.txt` (tab separated, optional '#pacId ...' header line) ->
+    dict: pacId / locusName / transcriptName / peptideName -> 'column=value;...' of the non-empty columns."""
+    table = {}
+    names = list(PHYTOZOME_COLUMNS)
+    with open(path, "r") as f:
+        for line in f:
+            line = line.rstrip("\r\n")
+            if not line:
+                continue
+            cells = line.split("\t")
+            if line.startswith("#"):
+                head = [c.lstrip("#").strip() for c in cells]
+                if head and head[0] == "pacId":
+                    names = head
+                continue
+            text = ";".join(f"{n}={c}" for n, c in zip(names[4:], cells[4:]) if c.strip())
+            for key in cells[:4]:
+                if key.strip():
+                    table.setdefault(key.strip(), text)
+    return table
+
+
+def lookup_annotation_info(table, attributes):
+    """GFF3 attribute string -> annotation_info text of the feature: the first of its pacid / ID / Name /
+    Parent values (version suffixes like '.v3.1', feature suffixes like '.CDS.2' peeled off) the table knows."""
+    if not table or not isinstance(attributes, str):
+        return ""
+    fields = dict(kv.split("=", 1) for kv in attributes.split(";") if "=" in kv)
+    for name in ("pacid", "ID", "Name", "Parent"):
+        for value in fields.get(name, "").split(","):
+            v = value.strip()
+            while v:
+                if v in table:
+                    return table[v]
+                if "." not in v:
+                    break
+                v = v.rsplit(".", 1)[0]
+    return ""

@@ -62,5 +62,5 @@ def main(argv=None):
     from . import engine, pipeline
     engine.init(args.device)
     pipeline.run_cas9(args.f, args.g, args.o, args.l, args.verbose, args.blas_threads,
-                      side_output=args.side_output, flank=args.L)
+                      side_output=args.side_output, flank=args.L, annotation_info=args.p)
     return 0

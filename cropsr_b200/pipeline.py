@@ -54,7 +54,7 @@ def scan_fasta_file(fasta, guide_len=20, flags=0):
     return [rec[0] for rec in layout], genome, result, token_bytes
 
 
-def write_side_output(path, tokens, result, gff_frame, flank, formatted_path):
+def write_side_output(path, tokens, result, gff_frame, flank, formatted_path, annotation_info=None):
     """Opt-in table of the per-candidate side outputs (one row per unique candidate, reference
     order).  NOT part of the reference's CSV: GC, poly-T / homopolymer flags, cut site, the
     +-L flank window, the GFF feature under the cut site (device kernels k_extras / k_annotate;
@@ -64,11 +64,12 @@ def write_side_output(path, tokens, result, gff_frame, flank, formatted_path):
     import csv
     from . import annotate, primers
     ivs = annotate.intervals_for_tokens(gff_frame, list(tokens.keys()), formatted_path)
+    info = annotate.read_annotation_info(annotation_info) if annotation_info else {}    # -p: Phytozome annotation_info.txt
     with open(path, "w", newline="") as f:
         w = csv.writer(f, delimiter="\t")
         w.writerow(["chromosome", "strand", "pam_pos", "cutsite", "gc", "poly_t", "homopolymer", "low_gc",
                     "unscored_base", "longest_run", "flank_start", "flank_end", "feature_type", "feature_attributes",
-                    "fwd_primers", "rev_primers", "primer_pairs", "first_pair"])
+                    "fwd_primers", "rev_primers", "primer_pairs", "first_pair", "annotation_info"])
         for seg, key in enumerate(tokens.keys()):
             iv = ivs[seg]
             for strand in "+-":
@@ -89,11 +90,11 @@ def write_side_output(path, tokens, result, gff_frame, flank, formatted_path):
                                 "" if fp[0] == 0xFFFF else f"{fp[0]}+{fp[1]}/{fp[2]}+{fp[3]}"]
                     w.writerow([key[1:], strand, int(pos[i]), int(ex["cut"][i]), int(ex["gc"][i]), fl & 1, (fl >> 1) & 1,
                                 (fl >> 2) & 1, (fl >> 3) & 1, int(ex["run"][i]), int(ex["flank_lo"][i]),
-                                int(ex["flank_hi"][i]), ft, fa] + prim)
+                                int(ex["flank_hi"][i]), ft, fa] + prim + [annotate.lookup_annotation_info(info, fa)])
 
 
 def run_cas9(fasta, gff, output="data.csv", guide_len=20, verbose=False, blas_threads=1,
-             time_path="time.txt", out=print, side_output=None, flank=200, device_ingest=True):
+             time_path="time.txt", out=print, side_output=None, flank=200, device_ingest=True, annotation_info=None):
     begin = time.time()
     timing = open(time_path, "w")                       # CROPSR.py:371
     fast = scan_fasta_file(fasta, guide_len) if device_ingest else None
@@ -132,7 +133,7 @@ def run_cas9(fasta, gff, output="data.csv", guide_len=20, verbose=False, blas_th
     if side_output and guide_len == 20:
         with open(fasta, "r") as f:
             formatted_path = ingest.needs_formatting(f.read())
-        write_side_output(side_output, tokens, result, gff_frame, flank, formatted_path)
+        write_side_output(side_output, tokens, result, gff_frame, flank, formatted_path, annotation_info)
     stats = {"tokens": len(tokens), "candidates": len(table), "rows": rows_written,
              "scan_ms": result.scan_ms(), **genome.timing()}
     result.free()

@@ -347,7 +347,7 @@ def test_cli_side_output_leaves_csv_untouched(manifest, eng, tmp_path):
     assert any(r[12] == "CDS" for r in rows[1:]) and any(r[12] == "" for r in rows[1:])
     assert all(0 <= int(r[4]) <= 20 for r in rows[1:])
     # primer columns: filled wherever the flank holds e + l = 130 bases, and consistent
-    assert rows[0][14:] == ["fwd_primers", "rev_primers", "primer_pairs", "first_pair"]
+    assert rows[0][14:] == ["fwd_primers", "rev_primers", "primer_pairs", "first_pair", "annotation_info"]
     filled = [r for r in rows[1:] if r[14] != ""]
     assert len(filled) > 0.99 * stats["candidates"]
     assert all(int(r[16]) <= int(r[14]) * int(r[15]) and (r[17] != "") == (int(r[16]) > 0) for r in filled)

@@ -253,3 +253,22 @@ def test_cropsr_module_keeps_the_reference_callables(built_lib):
     assert np.array_equal(a, np.random.choice(CROPSR.alphanum, [5, 7]))
     with pytest.raises(NotImplementedError):
         CROPSR.find_PAM_site("(?=TTT)", "ACGT")
+
+
+def test_phytozome_annotation_info_join(tmp_path):
+    """-p annotation_info.txt (echoed and ignored by the reference, CROPSR.py:32,364): rows keyed by
+    pacId / locus / transcript / peptide, looked up from GFF3 attributes with version suffixes peeled."""
+    from cropsr_b200 import annotate
+    p = tmp_path / "Sbicolor_454_v3.1.1.annotation_info.txt"
+    p.write_text("#pacId\tlocusName\ttranscriptName\tpeptideName\tPfam\tPanther\tKOG\tec\tKO\tGO\tBest-hit-arabi-name\tarabi-symbol\tarabi-defline\n"
+                 "37916712\tSobic.001G000100\tSobic.001G000100.1\tSobic.001G000100.1.p\tPF00069\t\t\t2.7.11.1\t\tGO:0004672\tAT1G01540.2\t\tProtein kinase\n"
+                 "37916713\tSobic.001G000200\tSobic.001G000200.2\tSobic.001G000200.2.p\t\t\t\t\t\t\t\t\t\n")
+    t = annotate.read_annotation_info(str(p))
+    want = "Pfam=PF00069;ec=2.7.11.1;GO=GO:0004672;Best-hit-arabi-name=AT1G01540.2;arabi-defline=Protein kinase"
+    assert t["Sobic.001G000100"] == want and t["37916712"] == want and t["Sobic.001G000100.1.p"] == want
+    assert t["Sobic.001G000200"] == ""
+    look = annotate.lookup_annotation_info
+    assert look(t, "ID=Sobic.001G000100.v3.1;Name=Sobic.001G000100") == want
+    assert look(t, "ID=Sobic.001G000100.1.v3.1.CDS.2;Parent=Sobic.001G000100.1.v3.1;pacid=37916712") == want
+    assert look(t, "ID=cds-1;Parent=Sobic.001G000100.1.v3.1") == want
+    assert look(t, "ID=unknown.7;Name=other") == "" and look(t, float("nan")) == "" and look({}, "ID=x") == ""
