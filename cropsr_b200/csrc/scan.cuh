@@ -91,11 +91,18 @@ __host__ __device__ inline uint32_t classify(uint32_t c) {
 // descs == NULL: the shard is ONE segment, described by `one` (descriptor of its first tile,
 // td.n = positions of the whole segment); tile j then follows by arithmetic, so that a
 // pipelined ingest needs no descriptor upload.
+// The byte classes come from a 256-entry table whose entries hold the four plane bits one per
+// BYTE lane (code low | code high << 8 | lower << 16 | other << 24): eight consecutive bases
+// accumulate as  acc += entry << k  (one IMAD each, no bit twiddling), which leaves 8 positions
+// of every plane in one byte of acc, and byte permutes assemble the 32-position planes.
 __global__ void __launch_bounds__(256)
 k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, const PackDesc one, uint64_t n_items,
        uint4 *__restrict__ records, unsigned char *__restrict__ pam) {
-    __shared__ uint8_t lut[256];
-    lut[threadIdx.x] = (uint8_t)classify(threadIdx.x);
+    __shared__ uint32_t lut[256];
+    {
+        const uint32_t nib = classify(threadIdx.x);
+        lut[threadIdx.x] = (nib & 1u) | ((nib >> 1) & 1u) << 8 | ((nib >> 2) & 1u) << 16 | ((nib >> 3) & 1u) << 24;
+    }
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += stride) {
@@ -123,27 +130,29 @@ k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, co
             const uint4 *src = reinterpret_cast<const uint4 *>(ascii + pd.ascii_off + (uint64_t)(p0 - lo));
             const uint4 a = __ldg(src), b = __ldg(src + 1);
             const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            uint32_t acc[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int g = 0; g < 4; ++g) {                  // 8 bases -> one byte of every plane
+                uint32_t s = 0;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t nib = lut[(v[i] >> (8 * q)) & 0xFFu];
-                    const int bit = 4 * i + q;
-                    o0 |= (nib & 1u) << bit;
-                    o1 |= ((nib >> 1) & 1u) << bit;
-                    ol |= ((nib >> 2) & 1u) << bit;
-                    oo |= ((nib >> 3) & 1u) << bit;
-                }
+                for (int j = 0; j < 8; ++j) s += lut[(v[2 * g + (j >> 2)] >> (8 * (j & 3))) & 0xFFu] << j;
+                acc[g] = s;
             }
+            const uint32_t t01 = __byte_perm(acc[0], acc[1], 0x5140), t23 = __byte_perm(acc[2], acc[3], 0x5140);
+            const uint32_t u01 = __byte_perm(acc[0], acc[1], 0x7362), u23 = __byte_perm(acc[2], acc[3], 0x7362);
+            o0 = __byte_perm(t01, t23, 0x5410);
+            o1 = __byte_perm(t01, t23, 0x7632);
+            ol = __byte_perm(u01, u23, 0x5410);
+            oo = __byte_perm(u01, u23, 0x7632);
         } else {
             for (int bit = 0; bit < 32; ++bit) {
                 const int64_t p = p0 + bit;
-                uint32_t nib = 8u;
-                if (p >= lo && p < hi) nib = lut[ascii[pd.ascii_off + (uint64_t)(p - lo)]];
-                o0 |= (nib & 1u) << bit;
-                o1 |= ((nib >> 1) & 1u) << bit;
-                ol |= ((nib >> 2) & 1u) << bit;
-                oo |= ((nib >> 3) & 1u) << bit;
+                uint32_t e = 1u << 24;
+                if (p >= lo && p < hi) e = lut[ascii[pd.ascii_off + (uint64_t)(p - lo)]];
+                o0 |= (e & 1u) << bit;
+                o1 |= ((e >> 8) & 1u) << bit;
+                ol |= ((e >> 16) & 1u) << bit;
+                oo |= ((e >> 24) & 1u) << bit;
             }
         }
         records[it] = make_uint4(o0, o1, ol, oo);
