@@ -259,6 +259,11 @@ def test_long_count_ranges_and_prefetched_first_tile(eng, monkeypatch):
     _check_against_oracle(eng, text, 20)
     monkeypatch.setenv("CRP_STATIC_EIGHTHS", "8")
     _check_against_oracle(eng, text, 20)
+    # one CTA: count ranges of 32 tiles (the ring of 6 PAM slots goes round five times), four waves
+    monkeypatch.delenv("CRP_WAVE_TILES")
+    monkeypatch.setenv("CRP_SCAN_GRID", "1")
+    monkeypatch.setenv("CRP_STATIC_EIGHTHS", "4")
+    _check_against_oracle(eng, text, 20)
 
 
 def test_pipelined_call_equals_plain_scan(eng):
