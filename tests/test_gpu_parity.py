@@ -342,9 +342,12 @@ def test_cli_side_output_leaves_csv_untouched(manifest, eng, tmp_path):
     case = manifest["cases"]["sample"]
     out, side = tmp_path / "out.csv", tmp_path / "side.tsv"
     np.random.seed(case["seed"])
+    info = tmp_path / "annotation_info.txt"       # -p: rows keyed by names the sample GFF uses (Name= of a gene and of a CDS)
+    info.write_text("#pacId\tlocusName\ttranscriptName\tpeptideName\tPfam\tPanther\tKOG\tec\tKO\tGO\n"
+                    "1\tPAU8\tNP_009332.1\tNP_009332.1.p\tPF00660\t\t\t\t\tGO:0030437\n")
     stats = pipeline.run_cas9(fixture_path(case["fasta"]), fixture_path("sample_genome.gff"), str(out), 20, False,
                               case["blas_threads"], str(tmp_path / "time.txt"), out=lambda *a: None,
-                              side_output=str(side), flank=200)
+                              side_output=str(side), flank=200, annotation_info=str(info))
     assert out.read_bytes().decode() == golden_csv("sample")
     rows = list(csv.reader(open(side), delimiter="\t"))
     assert len(rows) == stats["candidates"] + 1
@@ -356,6 +359,8 @@ def test_cli_side_output_leaves_csv_untouched(manifest, eng, tmp_path):
     filled = [r for r in rows[1:] if r[14] != ""]
     assert len(filled) > 0.99 * stats["candidates"]
     assert all(int(r[16]) <= int(r[14]) * int(r[15]) and (r[17] != "") == (int(r[16]) > 0) for r in filled)
+    hit = [r for r in rows[1:] if r[18]]
+    assert hit and all(r[18] == "Pfam=PF00660;GO=GO:0030437" and ("PAU8" in r[13] or "NP_009332.1" in r[13]) for r in hit)
 
 
 def test_device_fasta_ingest_equals_text_ingest(manifest, eng, tmp_path):
