@@ -182,6 +182,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cpus_before = os.sched_getaffinity(0)
+    numa_node = engine.bind_host_near(local)      # before any pinned allocation: staging buffers next to the GPU
     engine.init(local)
 
     # ---- workload and this rank's shard.  Weak scaling: N GPUs scan N genomes of the
@@ -323,7 +325,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": CONFIG_NAME[args.workload] + (f" x{world} (one per GPU)" if world > 1 else ""), "bases": n_bases_total, "candidates": n_cand_total,
                        "guide_len": 20, "sharding": f"{world} contiguous shard(s), tile-aligned, halo 32/32",
-                       "l2": "flushed between steps (512 MiB memset)"},
+                       "l2": "flushed between steps (512 MiB memset)", "host_numa_node": numa_node},
             "e2e": {"value": n_bases_total / (e2e * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": e2e,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
@@ -335,6 +337,7 @@ def main():
             "ingest": ingest_timing,
         }
         if not args.no_cpu_baseline and world == 1:
+            os.sched_setaffinity(0, cpus_before)          # the CPU baseline may use every core of the host
             line["cpu_baseline"] = cpu_port_sample(args.workload)[0]
         print(json.dumps(line))
     if world > 1:

@@ -26,6 +26,38 @@ def init(device=0):
     return _device
 
 
+def bind_host_near(device=0):
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off, so that the pinned
+    staging buffers it allocates next (first touch) and its copies stay on that node's memory and
+    PCIe root.  One process per GPU: with eight ranks on a two-socket host the host side of the
+    end-to-end path is otherwise what limits it.  Best effort: returns the node, or None (no
+    nvidia-smi / sysfs, single node, cgroup without those CPUs) without touching anything."""
+    import os
+    import subprocess
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(int(device))],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return None
+        dom, rest = bus.split(":", 1)
+        with open(f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/numa_node") as f:
+            node = int(f.read())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def shutdown():
     global _device
     check(lib.crp_shutdown())
