@@ -97,6 +97,7 @@ GC_MODEL = 0.42                 # base composition of the Monte-Carlo that ranks
 SEQUENTIAL_MAX = 3               # lanes with at most this many entries are summed without a table
 SWIZZLE_MIN_BITS = 6            # lanes with at least this many index bits add their top 4 hash bits to the slot              # bit-flip hill climbing on the best candidate
 N_CANDIDATES = 24               # injective hashes collected per lane before the best one is kept
+MERGE_GROUPS = True             # dinucleotide groups at disjoint positions: one bit select + one multiply for the set
 
 
 def sample_states(entries, rng, n):
@@ -142,6 +143,17 @@ def find_hash(entries, seed, offset):
     for i, e in enumerate(entries):
         groups.setdefault(e[1], []).append(i)
     glist = list(groups.items())
+    # first-base groups whose match bits sit at disjoint positions share ONE magic: the device then
+    # merges them with bit selects and multiplies once (MERGE_GROUPS; the host table builder does not care)
+    gmask = [sum(1 << bit_of(entries[i]) for i in idxs) for _, idxs in glist]
+    sets = []
+    for gi in sorted(range(len(glist)), key=lambda g: -bin(gmask[g]).count("1")):
+        for st_ in sets:
+            if MERGE_GROUPS and glist[gi][0] is not None and all(gmask[gi] & gmask[o] == 0 for o in st_):
+                st_.append(gi)
+                break
+        else:
+            sets.append([gi])
     states = list(valid_states(entries))
     pat = np.zeros((len(glist), len(states)), dtype=np.uint64)
     for si, st in enumerate(states):
@@ -167,11 +179,12 @@ def find_hash(entries, seed, offset):
         found = []
         for t in range(6000 if bits == need else 800):
             acc = np.zeros((batch, len(states)), dtype=np.uint64)
-            mags = []
-            for gi in range(len(glist)):
+            mags = [None] * len(glist)
+            for st_ in sets:
                 mg = sparse()
-                mags.append(mg)
-                acc += (pat[gi][None, :] * mg[:, None]) & m32
+                for gi in st_:
+                    mags[gi] = mg
+                    acc += (pat[gi][None, :] * mg[:, None]) & m32
             h = (acc & m32) >> np.uint64(32 - bits)
             h.sort(axis=1)
             ok = (np.diff(h.astype(np.int64), axis=1) != 0).all(axis=1) if len(states) > 1 else np.ones(batch, bool)
@@ -201,7 +214,7 @@ def find_hash(entries, seed, offset):
             print(f"lane hash: {len(states)} states, {bits} bits, {len(found)} candidates, expected wavefronts "
                   f"{best[0]:.2f}{' (additive swizzle)' if bits >= SWIZZLE_MIN_BITS else ''}", file=sys.stderr)
             return bits, [(c1, sum(1 << bit_of(entries[i]) for i in idxs), best[1][gi])
-                          for gi, (c1, idxs) in enumerate(glist)]
+                          for gi, (c1, idxs) in enumerate(glist)], sets
     raise SystemExit("no perfect hash found")
 
 
@@ -245,9 +258,9 @@ def main():
         assert all(e[0] < (tail[0][0] if tail else 99) for e in entries if e[3]), "forced entry after a tail entry"
         second = name[0] == "d"
         if table_free or any(e[3] for e in entries):
-            bits, groups = find_hash(table_free, seed=100 + li, offset=offset)
+            bits, groups, sets = find_hash(table_free, seed=100 + li, offset=offset)
         else:
-            bits, groups = -1, []
+            bits, groups, sets = -1, [], []
         n_table = len(entries) - len(tail)          # forced + tabulated entries come first
         ents = ", ".join(f"{{{p}, {-1 if c1 is None else c1}, {hexf(v)}, {bit_of((p, c1))}, {int(f)}}}"
                          for p, c1, v, f, _ in entries)
@@ -256,9 +269,18 @@ def main():
         # ---- device code of this lane
         if bits >= 0:
             terms = []
-            for c1, m, mg in groups:
-                src = f"({shift_name[c1]} & {mask_name[base]} & 0x{m:x}u)" if second else f"({mask_name[base]} & 0x{m:x}u)"
-                terms.append(f"{src} * 0x{mg:x}u")
+            for st_ in sets:
+                c1, m, mg = groups[st_[0]]
+                if not second:
+                    terms.append(f"({mask_name[base]} & 0x{m:x}u) * 0x{mg:x}u")
+                    continue
+                sel, union = shift_name[c1], m
+                for gi in st_[1:]:                      # (sel & union) | (next & ~union): positions are disjoint
+                    c1n, mn, mgn = groups[gi]
+                    assert mgn == mg and union & mn == 0
+                    sel = f"RS1_SEL(0x{union:x}u, {sel}, {shift_name[c1n]})"
+                    union |= mn
+                terms.append(f"({sel} & {mask_name[base]} & 0x{union:x}u) * 0x{mg:x}u")
             top = "RS1_SWZ" if bits >= SWIZZLE_MIN_BITS else "RS1_TOP"
             code.append(f"    double {name} = RS1_LD(T, {offset}u, {top}(" + " + ".join(terms) + f", {bits}));")
             offset += (1 << bits) + (16 if bits >= SWIZZLE_MIN_BITS else 0)

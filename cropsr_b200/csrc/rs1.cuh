@@ -35,6 +35,8 @@ __constant__ double c_rs1_k[] = RS1_K_VALUES;
 // the same with the top 4 hash bits added to the slot (spreads the probable states over the banks;
 // the add is the accumulate operand of the multiply-high)
 #define RS1_SWZ(h, bits) ((__umulhi((h), 1u << (bits)) + __umulhi((h), 16u)) * 8u)
+// bit select: a where the mask is set, b elsewhere (one LOP3)
+#define RS1_SEL(mask, a, b) (((a) & (mask)) | ((b) & ~(mask)))
 #define RS1_SHL1(m) ((m) << 1)
 #define RS1_SHL(m, k) ((m) << (k))
 // acc + w iff the match bit is set, as ONE DFMA: bit (a single bit p >= 20 of a class mask)
