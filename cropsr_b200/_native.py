@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CROPSR_B200_LIB: another build of the same library (kernel experiments, tools/variants.sh)
 LIB_PATH = os.environ.get("CROPSR_B200_LIB") or os.path.join(_HERE, "libcropsr_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 CRP_SCAN_DEFAULT = 0
 CRP_SCAN_NO_SCORE = 1
@@ -93,6 +93,7 @@ SIGNATURES = {
     "crp_result_annotate": (C.c_int, [C.c_void_p, C.c_uint32, C.c_char, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crp_primer_windows": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrimerParams),
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crp_legacy_ids": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_uint64, C.c_void_p]),
     "crp_format_rows": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_int, C.c_void_p, C.c_uint64, _u64p]),

@@ -29,7 +29,7 @@
 #include "primers.cuh"
 #include "extras.cuh"
 
-#define CRP_ABI_VERSION 5
+#define CRP_ABI_VERSION 6
 
 static constexpr size_t kScanSmemFixed = (size_t)kStages * kRecBytes + 2 * (size_t)kListCap * sizeof(uint16_t);
 

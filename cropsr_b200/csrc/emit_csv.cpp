@@ -224,3 +224,59 @@ extern "C" int crp_format_rows(uint64_t n_rows, const char *ids, const uint64_t 
     }
     return 0;
 }
+
+// ---- crispr_id characters: get_id() of the reference (CROPSR.py:316-318) ------------------------
+// np.random.choice(alphanum36, [n, 7]) on numpy's legacy global generator is, value for value,
+// randint(0, 36, (n, 7)): MT19937 32-bit outputs masked with 63, those above 35 rejected
+// (numpy random/src/distributions: buffered_bounded_masked_uint32).  The caller hands over the
+// generator's state (np.random.get_state(): key[624], pos) and puts the advanced state back, so a
+// seeded run keeps the reference's ids and whatever is drawn afterwards is unchanged too.  numpy's
+// own bounded-integer path costs ~27 ns per character; this loop ~3 ns.
+static inline void mt19937_refill(uint32_t *key) {
+    constexpr int N = 624, M = 397;
+    constexpr uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MATRIX = 0x9908b0dfu;
+    int kk = 0;
+    uint32_t y;
+    for (; kk < N - M; ++kk) {
+        y = (key[kk] & UPPER) | (key[kk + 1] & LOWER);
+        key[kk] = key[kk + M] ^ (y >> 1) ^ (-(y & 1u) & MATRIX);
+    }
+    for (; kk < N - 1; ++kk) {
+        y = (key[kk] & UPPER) | (key[kk + 1] & LOWER);
+        key[kk] = key[kk + (M - N)] ^ (y >> 1) ^ (-(y & 1u) & MATRIX);
+    }
+    y = (key[N - 1] & UPPER) | (key[0] & LOWER);
+    key[N - 1] = key[M - 1] ^ (y >> 1) ^ (-(y & 1u) & MATRIX);
+}
+
+extern "C" int crp_legacy_ids(uint32_t *mt_key, int32_t *mt_pos, uint64_t n_ids, uint8_t *out) {
+    if (!mt_key || !mt_pos || (n_ids && !out)) return CRP_ERR_ARG;
+    if (*mt_pos < 0 || *mt_pos > 624) return CRP_ERR_ARG;
+    static const char alnum[65] = "ABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789............................";
+    int pos = *mt_pos;
+    const uint64_t n = n_ids * 7;
+    uint64_t i = 0;
+    while (i < n) {
+        if (pos == 624) {
+            mt19937_refill(mt_key);
+            pos = 0;
+        }
+        // the rest of this block of state words, or as many as can still be accepted without
+        // running past the end of out: branch-free (44 % of the draws are rejected)
+        uint64_t take = (uint64_t)(624 - pos);
+        if (take > n - i) take = n - i;
+        for (uint64_t k = 0; k < take; ++k) {
+            uint32_t y = mt_key[pos + (int)k];
+            y ^= y >> 11;
+            y ^= (y << 7) & 0x9d2c5680u;
+            y ^= (y << 15) & 0xefc60000u;
+            y ^= y >> 18;
+            const uint32_t v = y & 63u;
+            out[i] = (uint8_t)alnum[v];            // overwritten by the next accepted draw if this one is rejected
+            i += v <= 35u;
+        }
+        pos += (int)take;
+    }
+    *mt_pos = pos;
+    return 0;
+}

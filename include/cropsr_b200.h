@@ -201,6 +201,13 @@ int crp_result_extras(const crp_result *res, uint32_t segment, char strand, uint
 int crp_result_annotate(const crp_result *res, uint32_t segment, char strand, uint32_t n_intervals,
                         const uint32_t *start, const uint32_t *end, int32_t *feature);
 
+/* crispr_id characters: replaces get_id() (CROPSR.py:316-318: np.random.choice of 36 characters,
+ * [n, 7]) value for value on numpy's legacy MT19937 generator -- the caller passes the state of
+ * np.random.get_state() (key[624], pos) and stores the advanced state back, so that a seeded run
+ * reproduces the reference's ids and every later draw.  out receives 7 ASCII bytes per id.
+ * Host only, no GPU involved. */
+int crp_legacy_ids(uint32_t *mt_key, int32_t *mt_pos, uint64_t n_ids, uint8_t *out);
+
 /* ---- primer enumeration over windows of a packed genome (opt-in).
  * Replaces the part of /root/reference/prmrdsgn2.py that needs no aligner, for many fragments at
  * once: get_primers (:115-124) on the fragment and on its reverse complement (:104-112), the

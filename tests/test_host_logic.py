@@ -272,3 +272,24 @@ def test_phytozome_annotation_info_join(tmp_path):
     assert look(t, "ID=Sobic.001G000100.1.v3.1.CDS.2;Parent=Sobic.001G000100.1.v3.1;pacid=37916712") == want
     assert look(t, "ID=cds-1;Parent=Sobic.001G000100.1.v3.1") == want
     assert look(t, "ID=unknown.7;Name=other") == "" and look(t, float("nan")) == "" and look({}, "ID=x") == ""
+
+
+def test_legacy_ids_equal_numpy_choice_and_leave_the_same_generator_state(built_lib):
+    """crp_legacy_ids (the library's MT19937 loop) against get_id() = np.random.choice(alphanum, [n, 7])
+    (CROPSR.py:316-318): same characters, same generator state afterwards (so every later draw is the
+    same too), from arbitrary positions in the stream, across state refills, for empty requests."""
+    from cropsr_b200 import emit
+    for seed, skip, n in ((1, 0, 0), (2, 0, 1), (3, 5, 89), (4, 623, 90), (5, 624, 1000), (6, 17, 20011), (7, 1, 250000)):
+        np.random.seed(seed)
+        np.random.randint(0, 2 ** 32, size=skip, dtype=np.uint32)         # move inside the 624-word block
+        want = emit.id_bytes_of(emit.get_id(n)).reshape(-1, 7)
+        state_want = np.random.get_state()
+        after_want = np.random.choice(emit.alphanum, [5, 7])
+        np.random.seed(seed)
+        np.random.randint(0, 2 ** 32, size=skip, dtype=np.uint32)
+        got = emit.legacy_id_bytes(n)
+        state_got = np.random.get_state()
+        after_got = np.random.choice(emit.alphanum, [5, 7])
+        assert got.shape == (n, 7) and np.array_equal(got, want)
+        assert state_got[0] == state_want[0] and np.array_equal(state_got[1], state_want[1]) and state_got[2:] == state_want[2:]
+        assert np.array_equal(after_got, after_want)
