@@ -38,7 +38,17 @@ struct Tables {
 };
 const Tables kTab;
 
-inline void put_field(std::string &out, const char *s, size_t n) {   // QUOTE_MINIMAL
+// Rows are written straight into a region of a scratch buffer that is big enough by construction
+// (max_row_bytes below); the few std::string methods the formatter used keep their names.
+struct Buf {
+    char *p;
+    void push_back(char c) { *p++ = c; }
+    void append(const char *s, size_t n) { memcpy(p, s, n); p += n; }
+    void append(size_t n, char c) { memset(p, c, n); p += n; }
+    Buf &operator+=(const char *s) { const size_t n = strlen(s); memcpy(p, s, n); p += n; return *this; }
+};
+
+inline void put_field(Buf &out, const char *s, size_t n) {   // QUOTE_MINIMAL
     bool quote = false;
     for (size_t i = 0; i < n; ++i) {
         const char c = s[i];
@@ -59,7 +69,7 @@ inline void put_field(std::string &out, const char *s, size_t n) {   // QUOTE_MI
     out.push_back('"');
 }
 
-inline void put_int(std::string &out, long long v) {
+inline void put_int(Buf &out, long long v) {
     char buf[24];
     char *e = buf + sizeof buf, *p = e;
     unsigned long long u = v < 0 ? 0ull - (unsigned long long)v : (unsigned long long)v;
@@ -75,7 +85,7 @@ inline void put_int(std::string &out, long long v) {
 // yields exactly those digits, the closest to x among the shortest -- what CPython's
 // float_repr_style 'short' prints), laid out the way CPython does: fixed notation for
 // 1e-4 <= |x| < 1e16, exponent notation otherwise.
-void put_repr(std::string &out, double x) {
+void put_repr(Buf &out, double x) {
     if (isnan(x)) { out += "nan"; return; }
     if (isinf(x)) { out += x < 0 ? "-inf" : "inf"; return; }
     if (x == 0.0) { out += signbit(x) ? "-0.0" : "0.0"; return; }
@@ -130,10 +140,19 @@ struct Job {
     int guide_len;
 };
 
-void format_range(const Job &j, uint64_t lo, uint64_t hi, std::string &out) {
+// upper bound of one row: every field that can hold token or header bytes fully quoted
+size_t max_row_bytes(const Job &j, uint32_t n_tokens) {
+    size_t chrom = 0;
+    for (uint32_t k = 0; k < n_tokens; ++k)
+        if (j.chrom_len[k] > chrom) chrom = j.chrom_len[k];
+    const size_t l = (size_t)j.guide_len;
+    return 7 + 6 + (2 * l + 2) + 1 + (2 * (l + 10) + 2) + 1 + (2 * chrom + 2) + 1 + 3 * 21 + 2 + 40 + 16;
+}
+
+char *format_range(const Job &j, uint64_t lo, uint64_t hi, char *dst) {
     const int l = j.guide_len;
     std::string seq;
-    out.reserve((size_t)(hi - lo) * (size_t)(96 + 2 * l));
+    Buf out{dst};
     for (uint64_t i = lo; i < hi; ++i) {
         const uint32_t k = j.token_of[i];
         const uint8_t *tok = j.tokens[k];
@@ -185,6 +204,7 @@ void format_range(const Job &j, uint64_t lo, uint64_t hi, std::string &out) {
         }
         out += ",,completed\r\n";
     }
+    return out.p;
 }
 
 }  // namespace
@@ -207,21 +227,40 @@ extern "C" int crp_format_rows(uint64_t n_rows, const char *ids, const uint64_t 
     if (hw == 0) hw = 1;
     uint64_t nt = n_threads > 0 ? (uint64_t)n_threads : (hw > 16 ? 16 : hw);
     if (nt > (n_rows + 4095) / 4096) nt = (n_rows + 4095) / 4096;     // >= 4096 rows per thread
-    std::vector<std::string> parts(nt);
-    std::vector<std::thread> pool;
-    for (uint64_t w = 1; w < nt; ++w)
-        pool.emplace_back([&, w] { format_range(j, n_rows * w / nt, n_rows * (w + 1) / nt, parts[w]); });
-    format_range(j, 0, n_rows / nt, parts[0]);
-    for (std::thread &th : pool) th.join();
+    // every thread formats its rows into its own region of a scratch buffer that lives as long as
+    // the library (fresh 100+ MB buffers per call cost more in page faults than the formatting),
+    // then the regions are copied, again in parallel, to their final offsets in out
+    static std::vector<char> scratch;
+    const size_t row_max = max_row_bytes(j, n_tokens);
+    const uint64_t per = (n_rows + nt - 1) / nt;
+    const size_t stride = (size_t)per * row_max;
+    if (scratch.size() < stride * nt) scratch.resize(stride * nt);
+    std::vector<size_t> len(nt, 0);
+    auto rows_of = [&](uint64_t w, uint64_t *lo, uint64_t *hi) {
+        *lo = w * per < n_rows ? w * per : n_rows;
+        *hi = (w + 1) * per < n_rows ? (w + 1) * per : n_rows;
+    };
+    auto run = [&](auto &&fn) {
+        std::vector<std::thread> pool;
+        for (uint64_t w = 1; w < nt; ++w) pool.emplace_back([&, w] { fn(w); });
+        fn(0);
+        for (std::thread &th : pool) th.join();
+    };
+    run([&](uint64_t w) {
+        uint64_t lo, hi;
+        rows_of(w, &lo, &hi);
+        char *base = scratch.data() + w * stride;
+        len[w] = (size_t)(format_range(j, lo, hi, base) - base);
+    });
     uint64_t total = 0;
-    for (const std::string &p : parts) total += p.size();
+    std::vector<uint64_t> off(nt, 0);
+    for (uint64_t w = 0; w < nt; ++w) {
+        off[w] = total;
+        total += len[w];
+    }
     *out_bytes = total;
     if (total > out_capacity || !out) return CRP_ERR_RANGE;          // caller retries with *out_bytes
-    char *dst = out;
-    for (const std::string &p : parts) {
-        memcpy(dst, p.data(), p.size());
-        dst += p.size();
-    }
+    run([&](uint64_t w) { memcpy(out + off[w], scratch.data() + w * stride, len[w]); });
     return 0;
 }
 

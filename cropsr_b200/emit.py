@@ -226,20 +226,40 @@ def format_rows(table, ids, scores, scored, start, count, n_threads=0):
     chroms = [c.encode("utf-8") for c in table.chroms]
     chrom_ptr = (C.c_char_p * n_tok)(*chroms)
     chrom_len = np.array([len(c) for c in chroms], dtype=np.uint32)
-    cap = count * (96 + 4 * table.guide_len + 2 * int(chrom_len.max(initial=0)))
-    for _ in range(2):
-        out = np.empty(cap, dtype=np.uint8)
-        need = C.c_uint64(0)
-        rc = lib.crp_format_rows(count, id_bytes.ctypes.data, id_index.ctypes.data, tok.ctypes.data, t.ctypes.data,
-                                 minus.ctypes.data, ok.ctypes.data, sc.ctypes.data, n_tok, tok_ptr, tok_len.ctypes.data,
-                                 chrom_ptr, chrom_len.ctypes.data, int(table.guide_len), int(n_threads),
-                                 out.ctypes.data, cap, C.byref(need))
-        if rc == -5:
-            cap = need.value
-            continue
-        check(rc)
-        return out[:need.value].data        # a memoryview: no copy on the way to f.write()
-    raise RuntimeError("crp_format_rows: capacity negotiation failed")
+    # One call formats at most _FORMAT_BUDGET bytes worth of rows (the library's scratch regions are sized for the
+    # worst row); the output lands in a buffer that is kept between calls -- a fresh 100+ MB buffer
+    # per 1M-row slice costs more in page faults than the formatting itself.  The memoryview that is
+    # returned is only valid until the next call.
+    global _OUT
+    row_bound = 256 + 4 * table.guide_len + 2 * int(chrom_len.max(initial=0))
+    step = max(4096, _FORMAT_BUDGET // row_bound)
+    pieces = []
+    for lo in range(0, count, step):
+        n = min(step, count - lo)
+        cap = n * row_bound
+        for _ in range(2):
+            if _OUT is None or len(_OUT) < cap:
+                _OUT = np.empty(cap, dtype=np.uint8)
+            need = C.c_uint64(0)
+            rc = lib.crp_format_rows(n, id_bytes.ctypes.data, id_index[lo:].ctypes.data, tok[lo:].ctypes.data,
+                                     t[lo:].ctypes.data, minus[lo:].ctypes.data, ok[lo:].ctypes.data, sc[lo:].ctypes.data,
+                                     n_tok, tok_ptr, tok_len.ctypes.data, chrom_ptr, chrom_len.ctypes.data,
+                                     int(table.guide_len), int(n_threads), _OUT.ctypes.data, len(_OUT), C.byref(need))
+            if rc == -5:
+                cap = need.value
+                continue
+            check(rc)
+            break
+        else:
+            raise RuntimeError("crp_format_rows: capacity negotiation failed")
+        if n == count:
+            return _OUT[:need.value].data   # a memoryview: no copy on the way to f.write()
+        pieces.append(_OUT[:need.value].tobytes())
+    return b"".join(pieces)
+
+
+_OUT = None
+_FORMAT_BUDGET = 512 << 20       # a 1,000,000-row slice of the reference's chunk plan is one call
 
 
 def write_header(path):

@@ -162,7 +162,7 @@ def _table_from_oracle(text, guide_len):
 
 @pytest.mark.parametrize("fasta,guide_len", [("edge_fmt.fa", 20), ("edge_clean.fa", 20), ("multi3.fa", 18),
                                              ("mid50k.fa", 20), ("ws_header.fa", 20)])
-def test_c_row_formatter_equals_python_csv_writer(built_lib, fasta, guide_len):
+def test_c_row_formatter_equals_python_csv_writer(built_lib, fasta, guide_len, monkeypatch):
     """csrc/emit_csv.cpp vs the literal Python row tuples + csv.writer: quoting of decoration
     bytes, truncated windows / 11-field error rows, repr() of the scores, id reverse indexing."""
     import csv, io
@@ -182,10 +182,11 @@ def test_c_row_formatter_equals_python_csv_writer(built_lib, fasta, guide_len):
         want = io.StringIO(newline="")
         csv.writer(want).writerows(emit.slice_rows(table, emit.ids_to_strings(ids), scores[start:start + count],
                                                    scored[start:start + count], start, count))
-        for threads in (1, 3):
+        for threads, budget in ((1, 512 << 20), (3, 512 << 20), (2, 1 << 20)):      # the last one: several calls per slice
+            monkeypatch.setattr(emit, "_FORMAT_BUDGET", budget)
             got = emit.format_rows(table, ids, scores[start:start + count], scored[start:start + count], start, count,
                                    n_threads=threads)
-            assert got == want.getvalue().encode()
+            assert bytes(got) == want.getvalue().encode()
 
 
 def test_c_float_repr_matches_python(built_lib):
