@@ -129,14 +129,19 @@ class CandidateTable:
 
 
 def long_length(table, idx):
-    """len(long_sequence) of candidates idx (vectorised Python-slice arithmetic)."""
+    """len(long_sequence) of candidates idx -- an index array or a slice -- (vectorised Python-slice
+    arithmetic)."""
     l = table.guide_len
     t = table.t[idx].astype(np.int64)
     L = np.array([len(tok) for tok in table.tokens], dtype=np.int64)[table.tok[idx]]
     minus = table.minus[idx]
-    lo = np.where(minus, t - 2, t - l - 5)
-    hi = np.where(minus, t + l + 8, t + 5)
-    return np.minimum(hi, L) - np.maximum(lo, 0)
+    # '+': [t - l - 5, t + 5), '-': [t - 2, t + l + 8), clipped to the token
+    lo = t - np.where(minus, 2, l + 5)
+    hi = t + np.where(minus, l + 8, 5)
+    np.minimum(hi, L, out=hi)
+    np.maximum(lo, 0, out=lo)
+    hi -= lo
+    return hi
 
 
 def slice_scores(table, genome, start, count, blas_threads=1):
@@ -145,8 +150,8 @@ def slice_scores(table, genome, start, count, blas_threads=1):
     non-canonical lane order re-evaluated on the GPU, then the reference's
     logistic.  Rows whose long_sequence is not 30 long get NaN (score -1 rows)."""
     idx = np.arange(start, start + count)
-    x = table.x[idx].copy()
-    scored = long_length(table, idx) == 30
+    x = table.x[start:start + count].copy()
+    scored = long_length(table, slice(start, start + count)) == 30
     fix = {}
     if table.guide_len != 20:
         # a window truncated by the token end to exactly 30 bases is scored by the
@@ -204,7 +209,7 @@ def id_bytes_of(ids):
     return np.ascontiguousarray(ids).view(np.uint32).astype(np.uint8)
 
 
-def format_rows(table, ids, scores, scored, start, count, n_threads=0):
+def format_rows(table, ids, scores, scored, start, count, n_threads=0, buffer=0):
     """CSV bytes of one emitted slice through the library's multi-threaded row formatter
     (csrc/emit_csv.cpp) -- byte-identical to csv.writer().writerows(slice_rows(...))."""
     import ctypes as C
@@ -229,8 +234,7 @@ def format_rows(table, ids, scores, scored, start, count, n_threads=0):
     # One call formats at most _FORMAT_BUDGET bytes worth of rows (the library's scratch regions are sized for the
     # worst row); the output lands in a buffer that is kept between calls -- a fresh 100+ MB buffer
     # per 1M-row slice costs more in page faults than the formatting itself.  The memoryview that is
-    # returned is only valid until the next call.
-    global _OUT
+    # returned is only valid until the next call with the same `buffer` (0 or 1).
     row_bound = 256 + 4 * table.guide_len + 2 * int(chrom_len.max(initial=0))
     step = max(4096, _FORMAT_BUDGET // row_bound)
     pieces = []
@@ -238,13 +242,14 @@ def format_rows(table, ids, scores, scored, start, count, n_threads=0):
         n = min(step, count - lo)
         cap = n * row_bound
         for _ in range(2):
-            if _OUT is None or len(_OUT) < cap:
-                _OUT = np.empty(cap, dtype=np.uint8)
+            if _OUT[buffer] is None or len(_OUT[buffer]) < cap:
+                _OUT[buffer] = np.empty(cap, dtype=np.uint8)
+            out = _OUT[buffer]
             need = C.c_uint64(0)
             rc = lib.crp_format_rows(n, id_bytes.ctypes.data, id_index[lo:].ctypes.data, tok[lo:].ctypes.data,
                                      t[lo:].ctypes.data, minus[lo:].ctypes.data, ok[lo:].ctypes.data, sc[lo:].ctypes.data,
                                      n_tok, tok_ptr, tok_len.ctypes.data, chrom_ptr, chrom_len.ctypes.data,
-                                     int(table.guide_len), int(n_threads), _OUT.ctypes.data, len(_OUT), C.byref(need))
+                                     int(table.guide_len), int(n_threads), out.ctypes.data, len(out), C.byref(need))
             if rc == -5:
                 cap = need.value
                 continue
@@ -253,12 +258,12 @@ def format_rows(table, ids, scores, scored, start, count, n_threads=0):
         else:
             raise RuntimeError("crp_format_rows: capacity negotiation failed")
         if n == count:
-            return _OUT[:need.value].data   # a memoryview: no copy on the way to f.write()
-        pieces.append(_OUT[:need.value].tobytes())
+            return out[:need.value].data    # a memoryview: no copy on the way to f.write()
+        pieces.append(out[:need.value].tobytes())
     return b"".join(pieces)
 
 
-_OUT = None
+_OUT = [None, None]
 _FORMAT_BUDGET = 512 << 20       # a 1,000,000-row slice of the reference's chunk plan is one call
 
 
@@ -273,10 +278,19 @@ def emit_cumulative(path, table, genome, blas_threads=1):
     chunk plan.  Returns the number of rows written."""
     size = len(table)
     written = 0
-    with open(path, "ab") as f:
+    # the file write of slice k (0.8 s of 3.3 s on a 4 GB CSV) runs on a helper thread while slice
+    # k + 1 is scored and formatted into the other output buffer; both release the GIL
+    from concurrent.futures import ThreadPoolExecutor
+    with open(path, "ab") as f, ThreadPoolExecutor(max_workers=1) as writer:
         ids = legacy_id_bytes(size)                         # get_id(size), CROPSR.py:448
-        for start, count in emission_slices(size):
+        pending = [None, None]
+        for k, (start, count) in enumerate(emission_slices(size)):
             scores, scored = slice_scores(table, genome, start, count, blas_threads)
-            f.write(format_rows(table, ids, scores, scored, start, count))
+            if pending[k & 1] is not None:
+                pending[k & 1].result()                     # that buffer's previous rows are on their way to disk
+            pending[k & 1] = writer.submit(f.write, format_rows(table, ids, scores, scored, start, count, buffer=k & 1))
             written += count
+        for p in pending:
+            if p is not None:
+                p.result()
     return written
