@@ -44,6 +44,57 @@ def legacy_id_bytes(num_to_gen):
     return out
 
 
+class IdStream:
+    """get_id() for a known sequence of sizes, drawn ahead on a helper thread (crp_legacy_ids releases
+    the GIL): the ids of the next emission are generated while the current one is formatted.  The
+    generator state is taken from numpy when the stream is opened and handed back by close(), so the
+    values and the state afterwards are those of calling get_id(size) for every size in turn; nothing
+    else may draw from np.random in between."""
+
+    def __init__(self, sizes):
+        import queue
+        import threading
+        self.sizes = [int(n) for n in sizes]
+        self.state = np.random.get_state()
+        self.q = queue.Queue(maxsize=1)
+        self.thread = None
+        self.k = 0
+        if self.state[0] == "MT19937" and self.sizes:
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+
+    def _run(self):
+        import ctypes as C
+        from ._native import lib
+        kind, key, pos, has_gauss, cached = self.state
+        key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+        p = C.c_int32(int(pos))
+        for n in self.sizes:
+            out = np.empty((n, 7), dtype=np.uint8)
+            rc = lib.crp_legacy_ids(key.ctypes.data, C.byref(p), n, out.ctypes.data if n else None)
+            self.q.put(out if rc == 0 else None)
+        self.state = (kind, key, p.value, has_gauss, cached)
+
+    def next(self, size):
+        if self.thread is None:
+            return legacy_id_bytes(size)
+        assert self.k < len(self.sizes) and self.sizes[self.k] == int(size), "IdStream: sizes out of sequence"
+        self.k += 1
+        out = self.q.get()
+        if out is None:
+            raise RuntimeError("crp_legacy_ids failed")
+        return out
+
+    def close(self):
+        if self.thread is not None:
+            while self.k < len(self.sizes):            # drain what was never asked for
+                self.q.get()
+                self.k += 1
+            self.thread.join()
+            np.random.set_state(self.state)
+            self.thread = None
+
+
 def ids_to_strings(ids):
     ids = np.ascontiguousarray(ids)
     if ids.size == 0:
@@ -272,7 +323,7 @@ def write_header(path):
         csv.writer(f).writerow(HEADER)
 
 
-def emit_cumulative(path, table, genome, blas_threads=1):
+def emit_cumulative(path, table, genome, blas_threads=1, id_stream=None):
     """Append the rows the reference writes after one more token has been
     scanned: ALL candidates accumulated so far (CROPSR.py:407,442), through the
     chunk plan.  Returns the number of rows written."""
@@ -282,7 +333,7 @@ def emit_cumulative(path, table, genome, blas_threads=1):
     # k + 1 is scored and formatted into the other output buffer; both release the GIL
     from concurrent.futures import ThreadPoolExecutor
     with open(path, "ab") as f, ThreadPoolExecutor(max_workers=1) as writer:
-        ids = legacy_id_bytes(size)                         # get_id(size), CROPSR.py:448
+        ids = id_stream.next(size) if id_stream else legacy_id_bytes(size)   # get_id(size), CROPSR.py:448
         pending = [None, None]
         for k, (start, count) in enumerate(emission_slices(size)):
             scores, scored = slice_scores(table, genome, start, count, blas_threads)

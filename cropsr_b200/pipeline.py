@@ -118,6 +118,9 @@ def run_cas9(fasta, gff, output="data.csv", guide_len=20, verbose=False, blas_th
         genome, result, token_bytes = scan_tokens(tokens, guide_len)
     table = emit.CandidateTable(guide_len)
     rows_written = 0
+    # the cumulative list sizes of every emission are known once the scan is through: their ids
+    # (CROPSR.py:448) are drawn ahead, in the reference's order, while rows are being written
+    id_stream = emit.IdStream(np.cumsum(result.seg_plus.astype(np.int64) + result.seg_minus.astype(np.int64)))
     for seg, (key, value) in enumerate(tokens.items()):
         out("Searching on Chromosome: ", key[:25])       # :410-411
         out("With start of sequence: ", value[:25])
@@ -127,8 +130,9 @@ def run_cas9(fasta, gff, output="data.csv", guide_len=20, verbose=False, blas_th
         if verbose:
             n = len(plus["pos"]) + len(minus["pos"])
             out(f"\n                {n:n} Cas9 PAM sites were found on {key[1:]}\n                ")
-        rows_written += emit.emit_cumulative(output, table, genome, blas_threads)
+        rows_written += emit.emit_cumulative(output, table, genome, blas_threads, id_stream)
         timing.write("Total runtime of the program is " + str(time.time() - begin))   # :476-477
+    id_stream.close()
     timing.close()
     if side_output and guide_len == 20:
         with open(fasta, "r") as f:

@@ -294,3 +294,27 @@ def test_legacy_ids_equal_numpy_choice_and_leave_the_same_generator_state(built_
         assert got.shape == (n, 7) and np.array_equal(got, want)
         assert state_got[0] == state_want[0] and np.array_equal(state_got[1], state_want[1]) and state_got[2:] == state_want[2:]
         assert np.array_equal(after_got, after_want)
+
+
+def test_id_stream_draws_ahead_what_get_id_would_draw(built_lib):
+    """emit.IdStream: ids of a known sequence of emission sizes generated on a helper thread -- same
+    characters as get_id(size) per emission, same generator state after close(), also when the
+    stream is closed early."""
+    from cropsr_b200 import emit
+    sizes = [3, 10, 10, 0, 2500, 40001]
+    np.random.seed(77)
+    want = [emit.id_bytes_of(emit.get_id(n)).reshape(-1, 7) for n in sizes]
+    after_want = np.random.randint(0, 1000, 4)
+    np.random.seed(77)
+    st = emit.IdStream(sizes)
+    got = [st.next(n) for n in sizes]
+    st.close()
+    after_got = np.random.randint(0, 1000, 4)
+    assert all(np.array_equal(a, b) for a, b in zip(got, want)) and np.array_equal(after_got, after_want)
+    np.random.seed(77)
+    st = emit.IdStream(sizes)
+    assert np.array_equal(st.next(3), want[0])
+    with pytest.raises(AssertionError):
+        st.next(11)
+    st.close()                                   # drains: the state is the one after all six draws
+    assert np.array_equal(np.random.randint(0, 1000, 4), after_want)
