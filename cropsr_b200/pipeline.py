@@ -62,35 +62,57 @@ def write_side_output(path, tokens, result, gff_frame, flank, formatted_path, an
     (k_primers, cropsr_b200/primers.py: primers passing the GC / Tm filter on either side, Tm-compatible
     pairs, the first pair; empty where the flank is shorter than e + l = 130 bases)."""
     import csv
+    import pandas as pd
     from . import annotate, primers
     ivs = annotate.intervals_for_tokens(gff_frame, list(tokens.keys()), formatted_path)
     info = annotate.read_annotation_info(annotation_info) if annotation_info else {}    # -p: Phytozome annotation_info.txt
+    columns = ["chromosome", "strand", "pam_pos", "cutsite", "gc", "poly_t", "homopolymer", "low_gc",
+               "unscored_base", "longest_run", "flank_start", "flank_end", "feature_type", "feature_attributes",
+               "fwd_primers", "rev_primers", "primer_pairs", "first_pair", "annotation_info"]
     with open(path, "w", newline="") as f:
-        w = csv.writer(f, delimiter="\t")
-        w.writerow(["chromosome", "strand", "pam_pos", "cutsite", "gc", "poly_t", "homopolymer", "low_gc",
-                    "unscored_base", "longest_run", "flank_start", "flank_end", "feature_type", "feature_attributes",
-                    "fwd_primers", "rev_primers", "primer_pairs", "first_pair", "annotation_info"])
-        for seg, key in enumerate(tokens.keys()):
-            iv = ivs[seg]
-            for strand in "+-":
-                pos = result.fetch_segment(seg, strand, want=("pos",))["pos"]
-                ex = result.extras(seg, strand, flank)
-                feat = result.annotate(seg, strand, iv["start"], iv["end"])
-                pr = primers.design_windows(result.genome, np.full(len(pos), seg, np.uint32), ex["flank_lo"], ex["flank_hi"])
-                rows = np.where(feat >= 0, iv["row"][np.maximum(feat, 0)] if len(iv["row"]) else -1, -1)
-                for i in range(len(pos)):
-                    fl = int(ex["flags"][i])
-                    ft, fa = "", ""
-                    if rows[i] >= 0:
-                        ft, fa = gff_frame.at[rows[i], "feature"], gff_frame.at[rows[i], "attributes"]
-                    prim = ["", "", "", ""]
-                    if pr["status"][i] == 0:
-                        fp = pr["first"][i]
-                        prim = [int(pr["n_fwd"][i]), int(pr["n_rev"][i]), int(pr["n_pairs"][i]),
-                                "" if fp[0] == 0xFFFF else f"{fp[0]}+{fp[1]}/{fp[2]}+{fp[3]}"]
-                    w.writerow([key[1:], strand, int(pos[i]), int(ex["cut"][i]), int(ex["gc"][i]), fl & 1, (fl >> 1) & 1,
-                                (fl >> 2) & 1, (fl >> 3) & 1, int(ex["run"][i]), int(ex["flank_lo"][i]),
-                                int(ex["flank_hi"][i]), ft, fa] + prim + [annotate.lookup_annotation_info(info, fa)])
+        csv.writer(f, delimiter="\t").writerow(columns)
+    # GFF rows are looked up per DISTINCT feature, then spread over the candidates: whole columns,
+    # one strand of one token at a time, no Python work per candidate
+    gff_feature = gff_frame["feature"].to_numpy(dtype=object)
+    gff_attr = gff_frame["attributes"].to_numpy(dtype=object)
+    for seg, key in enumerate(tokens.keys()):
+        iv = ivs[seg]
+        for strand in "+-":
+            pos = result.fetch_segment(seg, strand, want=("pos",))["pos"]
+            n = len(pos)
+            if n == 0:
+                continue
+            ex = result.extras(seg, strand, flank)
+            feat = result.annotate(seg, strand, iv["start"], iv["end"])
+            pr = primers.design_windows(result.genome, np.full(n, seg, np.uint32), ex["flank_lo"], ex["flank_hi"])
+            rows = np.where(feat >= 0, iv["row"][np.maximum(feat, 0)] if len(iv["row"]) else -1, -1)
+            ft = np.full(n, "", dtype=object)
+            fa = np.full(n, "", dtype=object)
+            ai = np.full(n, "", dtype=object)
+            hit = rows >= 0
+            if hit.any():
+                uniq, inv = np.unique(rows[hit], return_inverse=True)
+                ft[hit] = gff_feature[uniq][inv]
+                fa[hit] = gff_attr[uniq][inv]
+                ai[hit] = np.array([annotate.lookup_annotation_info(info, a) for a in gff_attr[uniq]], dtype=object)[inv]
+            fl = ex["flags"].astype(np.int64)
+            ok = pr["status"] == 0
+            first = pr["first"].astype(np.int64)
+            has_pair = ok & (first[:, 0] != 0xFFFF)
+            pair = np.full(n, "", dtype=object)
+            if has_pair.any():
+                fp = first[has_pair]
+                pair[has_pair] = [f"{a}+{b}/{c}+{d}" for a, b, c, d in fp.tolist()]
+            blank_unless_ok = lambda a: np.where(ok, a.astype(np.int64).astype(str).astype(object), "")
+            frame = pd.DataFrame({
+                "chromosome": key[1:], "strand": strand, "pam_pos": pos.astype(np.int64), "cutsite": ex["cut"].astype(np.int64),
+                "gc": ex["gc"].astype(np.int64), "poly_t": fl & 1, "homopolymer": (fl >> 1) & 1, "low_gc": (fl >> 2) & 1,
+                "unscored_base": (fl >> 3) & 1, "longest_run": ex["run"].astype(np.int64),
+                "flank_start": ex["flank_lo"].astype(np.int64), "flank_end": ex["flank_hi"].astype(np.int64),
+                "feature_type": ft, "feature_attributes": fa, "fwd_primers": blank_unless_ok(pr["n_fwd"]),
+                "rev_primers": blank_unless_ok(pr["n_rev"]), "primer_pairs": blank_unless_ok(pr["n_pairs"]),
+                "first_pair": pair, "annotation_info": ai}, columns=columns)
+            frame.to_csv(path, sep="\t", mode="a", header=False, index=False, lineterminator="\r\n")
 
 
 def run_cas9(fasta, gff, output="data.csv", guide_len=20, verbose=False, blas_threads=1,
