@@ -238,7 +238,9 @@ int crp_primer_windows(const crp_genome *g, uint64_t n, const uint32_t *segment,
  * the 11-field error-row variant where scored[i] == 0) into `out`, byte-identical
  * to the reference's writer; multi-threaded, no GPU involved.  Row i is the
  * candidate (token_of[i], t[i], minus[i]) with id ids[7 * id_index[i] .. +7).
- * Returns CRP_ERR_RANGE (and the size needed in *out_bytes) if out is too small. */
+ * Returns CRP_ERR_RANGE (and the size needed in *out_bytes) if out is too small.
+ * Rows are formatted into a scratch buffer the library keeps between calls (sized for the worst
+ * row of the largest call so far): one call at a time per process. */
 int crp_format_rows(uint64_t n_rows, const char *ids, const uint64_t *id_index, const uint32_t *token_of,
                     const uint32_t *t, const uint8_t *minus, const uint8_t *scored, const double *score,
                     uint32_t n_tokens, const uint8_t *const *tokens, const uint64_t *token_len,
