@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CROPSR_B200_LIB: another build of the same library (kernel experiments, tools/variants.sh)
 LIB_PATH = os.environ.get("CROPSR_B200_LIB") or os.path.join(_HERE, "libcropsr_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 CRP_SCAN_DEFAULT = 0
 CRP_SCAN_NO_SCORE = 1
@@ -103,7 +103,22 @@ SIGNATURES = {
     "crp_genome_timing": (C.c_int, [C.c_void_p, _f32p, _f32p]),
     "crp_result_timing": (C.c_int, [C.c_void_p, _f32p]),
     "crp_launch_count": (C.c_int, [_u64p]),
+    "crp_debug_set_times": (C.c_int, [C.c_void_p]),
+    "crp_device_synchronize": (C.c_int, []),
+    "crp_flush_l2": (C.c_int, []),
+    "crp_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "crp_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
+    "crp_comm_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "crp_comm_barrier": (C.c_int, []),
+    "crp_comm_max_f64": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "crp_comm_sum_f64": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "crp_comm_shutdown": (C.c_int, []),
+    "crp_scan_score_sharded": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, _vpp]),
+    "crp_result_gathered_counts": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "crp_result_timing_detail": (C.c_int, [C.c_void_p, _f32p, _f32p, _u32p]),
+    "crp_rs1_preactivation": (C.c_int, [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
+COMM_ID_BYTES = 128
 
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(lib, _name)       # AttributeError here = library/header mismatch

@@ -14,6 +14,8 @@
 #include <stdarg.h>
 #include <string.h>
 #include <stdlib.h>
+#include <atomic>
+#include <mutex>
 #include <new>
 #include <utility>
 #include <vector>
@@ -24,12 +26,10 @@
 #define CRP_CTAS_PER_SM 4
 #endif
 #include "scan.cuh"
-#include "scan_sp.cuh"
-#include "scan_ws.cuh"
 #include "primers.cuh"
 #include "extras.cuh"
 
-#define CRP_ABI_VERSION 6
+#define CRP_ABI_VERSION 7
 
 static constexpr size_t kScanSmemFixed = (size_t)kStages * kRecBytes + 2 * (size_t)kListCap * sizeof(uint16_t);
 
@@ -58,7 +58,7 @@ struct Context {
     cudaStream_t stream = nullptr;
     cudaStream_t lanes[3] = {nullptr, nullptr, nullptr};   // crp_scan_segments pipeline
     cudaStream_t lane_out = nullptr;                       // its device-to-host row copies
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};
     double *d_tables = nullptr;        // RS1 lane tables in device memory
 };
 static Context g_ctx;
@@ -88,20 +88,21 @@ struct crp_genome {
     uint32_t n_tiles = 0;
     uint32_t *d_seg_first = nullptr, *d_seg_count = nullptr;
     float ms_h2d = 0.f, ms_pack = 0.f;
-    // state of the single-pass scan kernel (scan_sp.cuh): zeroed once at commit, then only
-    // ever advanced by the launches, which are ordered on the genome's stream
     uint8_t *d_ascii = nullptr;                // ASCII tokens, kept after the pack only for device-ingested FASTA records
     bool fasta = false;
     unsigned int *h_bad = nullptr;             // pinned: non-zero after the commit if a FASTA record was not plain
-    unsigned char *sp_state = nullptr;         // agg[n_tiles] | incl[n_tiles] | ctl[2]
-    mutable uint32_t sp_epoch = 0, sp_ticket = 0, sp_done = 0;
 };
 
 struct crp_result {
     const crp_genome *g = nullptr;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // scan start, scan end, counts on the host
-    unsigned long long *h_counts = nullptr;    // pinned, [2*n_seg]: counts land here when the scan has run
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // scan start, scan (+ all-gather) end, counts on the host
+    cudaEvent_t ev_kernel = nullptr;           // sharded scans: between the kernel and the all-gather
+    unsigned long long *h_counts = nullptr;    // pinned, [2*stride]: counts land here when the scan has run
+    uint32_t stride = 0;                       // count slots per strand: n_seg, or the `slots` of a sharded scan
+    unsigned long long *d_gather = nullptr;    // sharded scans: [world][2*stride] counts of every rank (NCCL all-gather)
+    unsigned long long *h_gather = nullptr;    // pinned copy
+    float ms_kernel = 0.f;
     int guide_len = 0;
     uint32_t flags = 0;
     uint64_t capacity = 0;
@@ -112,9 +113,10 @@ struct crp_result {
     double *x[2] = {nullptr, nullptr};
     unsigned char *state = nullptr;            // warp_pref | cta_tot | segment counts | tickets, one allocation
     size_t state_bytes = 0, zero_offset = 0;   // segment counts and tickets start at zero_offset
-    unsigned long long *d_counts = nullptr;    // [2*n_seg], inside state
+    unsigned long long *d_counts = nullptr;    // [2*stride], inside state
     std::vector<uint64_t> seg_plus, seg_minus;
-    float ms_scan = 0.f;
+    float ms_scan = 0.f;                       // every launch of this scan, a capacity rerun included
+    uint32_t n_launches = 0;
 };
 
 // CRP_TRACE=1: host-side wall time of every stage of the big calls, on stderr
@@ -150,8 +152,10 @@ struct DevBlock {
 };
 static std::vector<DevBlock> g_dev_free;                       // idle blocks
 static std::vector<DevBlock> g_dev_live;                       // blocks handed out
+static std::mutex g_mem_mu;                                    // guards both block lists and the pinned list
 template <typename T>
 static cudaError_t dev_alloc(T **ptr, size_t bytes, cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(g_mem_mu);
     const size_t want = (bytes ? bytes : 16) + 255 & ~(size_t)255;
     size_t best = g_dev_free.size();
     for (size_t i = 0; i < g_dev_free.size(); ++i) {
@@ -186,6 +190,7 @@ static cudaError_t dev_alloc(T **ptr, size_t bytes, cudaStream_t st) {
 }
 static void dev_free(void *ptr, cudaStream_t st) {
     if (!ptr) return;
+    std::lock_guard<std::mutex> lock(g_mem_mu);
     for (size_t i = g_dev_live.size(); i-- > 0;)
         if (g_dev_live[i].ptr == ptr) {
             DevBlock blk = g_dev_live[i];
@@ -196,6 +201,7 @@ static void dev_free(void *ptr, cudaStream_t st) {
         }
 }
 static void dev_cache_release() {
+    std::lock_guard<std::mutex> lock(g_mem_mu);
     for (DevBlock &b : g_dev_free) {
         cudaFree(b.ptr);
         cudaEventDestroy(b.ev);
@@ -206,6 +212,7 @@ static void dev_cache_release() {
 // Small pinned host blocks (the per-scan counts) are recycled: cudaHostAlloc takes ~0.1 ms.
 static std::vector<std::pair<size_t, void *>> g_pinned_free;
 static void *pinned_get(size_t bytes) {
+    std::lock_guard<std::mutex> lock(g_mem_mu);
     for (size_t i = 0; i < g_pinned_free.size(); ++i)
         if (g_pinned_free[i].first >= bytes) {
             void *p = g_pinned_free[i].second;
@@ -220,12 +227,72 @@ static void *pinned_get(size_t bytes) {
 }
 static void pinned_put(void *p) {
     if (!p) return;
+    std::lock_guard<std::mutex> lock(g_mem_mu);
     const size_t cap = *reinterpret_cast<size_t *>(reinterpret_cast<char *>(p) - sizeof(size_t) * 2);
     g_pinned_free.emplace_back(cap, p);
 }
 
+
+// ------------------------------------------------------------------ NCCL (one process per GPU)
+// The library talks to NCCL through dlopen: a single-GPU run needs no NCCL at all, and inside a
+// process that already carries one (PyTorch's bundled copy) the same copy is used.
+#include <dlfcn.h>
+#include <nccl.h>
+struct Comm {
+    void *dl = nullptr;
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    unsigned long long *d_scratch = nullptr;   // barrier payload
+};
+static Comm g_comm;
+
+static int comm_load() {
+    if (g_comm.dl) return 0;
+    const char *names[] = {getenv("CRP_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        if (!n) continue;
+        if ((g_comm.dl = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    }
+    if (!g_comm.dl) return fail(CRP_ERR_STATE, "libnccl.so.2 not found: %s", dlerror());
+#define CRP_NCCL_SYM(field, name)                                                         \
+    if (!(*(void **)(&g_comm.field) = dlsym(g_comm.dl, name))) {                          \
+        dlclose(g_comm.dl);                                                               \
+        g_comm.dl = nullptr;                                                              \
+        return fail(CRP_ERR_STATE, "NCCL symbol %s missing", name);                       \
+    }
+    CRP_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    CRP_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    CRP_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    CRP_NCCL_SYM(AllGather, "ncclAllGather")
+    CRP_NCCL_SYM(AllReduce, "ncclAllReduce")
+    CRP_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef CRP_NCCL_SYM
+    return 0;
+}
+#define NCCL_TRY(expr)                                                                                \
+    do {                                                                                              \
+        ncclResult_t e_ = (expr);                                                                     \
+        if (e_ != ncclSuccess) return fail(CRP_ERR_CUDA, "%s failed: %s", #expr, g_comm.GetErrorString(e_)); \
+    } while (0)
+
+static int comm_allgather_u64(const unsigned long long *send, unsigned long long *recv, size_t count, cudaStream_t st) {
+    if (!g_comm.comm) return fail(CRP_ERR_STATE, "crp_comm_init has not been called");
+    NCCL_TRY(g_comm.AllGather(send, recv, count, ncclUint64, g_comm.comm, st));
+    return 0;
+}
+
 // ------------------------------------------------------------------ C ABI
 extern "C" {
+
+int crp_result_free(crp_result *r);
+int crp_comm_shutdown(void);
+
 
 int crp_abi_version(void) { return CRP_ABI_VERSION; }
 
@@ -233,7 +300,7 @@ int crp_tile_size(void) { return kTile; }
 
 const char *crp_last_error(void) { return g_err; }
 
-/* debug only (not part of the public header): device buffer of 8 x u64 per CTA, or NULL */
+/* debug hook of tools/phase_timeline.py: device buffer of 8 x u64 per CTA, or NULL */
 int crp_debug_set_times(void *dev_ptr) {
     unsigned long long *p = (unsigned long long *)dev_ptr;
     CUDA_TRY(cudaMemcpyToSymbol(g_dbg_times, &p, sizeof p));
@@ -274,23 +341,136 @@ int crp_init(int device) {
 
 int crp_shutdown(void) {
     if (!g_ctx.ready) return 0;
+    crp_comm_shutdown();
     cudaStreamSynchronize(g_ctx.stream);
     cudaDeviceSynchronize();
     dev_cache_release();
-    for (auto &pf : g_pinned_free) cudaFreeHost(reinterpret_cast<char *>(pf.second) - sizeof(size_t) * 2);
-    g_pinned_free.clear();
+    {
+        std::lock_guard<std::mutex> lock(g_mem_mu);
+        for (auto &pf : g_pinned_free) cudaFreeHost(reinterpret_cast<char *>(pf.second) - sizeof(size_t) * 2);
+        g_pinned_free.clear();
+    }
     cudaStreamDestroy(g_ctx.stream);
     for (cudaStream_t l : g_ctx.lanes)
         if (l) cudaStreamDestroy(l);
     if (g_ctx.lane_out) cudaStreamDestroy(g_ctx.lane_out);
     cudaFree(g_ctx.d_tables);
-    g_ctx = Context();
+    g_ctx.ready = false;
+    g_ctx.device = -1;
+    g_ctx.stream = nullptr;
+    for (cudaStream_t &l : g_ctx.lanes) l = nullptr;
+    g_ctx.lane_out = nullptr;
+    g_ctx.d_tables = nullptr;
+    g_ctx.launches = 0;
     return 0;
 }
 
 int crp_launch_count(uint64_t *n) {
     if (!n) return fail(CRP_ERR_ARG, "n is NULL");
     *n = g_ctx.launches;
+    return 0;
+}
+
+int crp_comm_unique_id(uint8_t *id) {
+    if (!id) return fail(CRP_ERR_ARG, "id is NULL");
+    if (int rc = comm_load()) return rc;
+    ncclUniqueId u;
+    NCCL_TRY(g_comm.GetUniqueId(&u));
+    static_assert(sizeof u == CRP_COMM_ID_BYTES, "ncclUniqueId size");
+    memcpy(id, &u, sizeof u);
+    return 0;
+}
+
+int crp_comm_init(int rank, int world, const uint8_t *id) {
+    if (int rc = need_ctx()) return rc;
+    if (!id || world < 1 || rank < 0 || rank >= world) return fail(CRP_ERR_ARG, "bad rank %d / world %d", rank, world);
+    if (g_comm.comm) return fail(CRP_ERR_STATE, "communicator already initialised (rank %d of %d)", g_comm.rank, g_comm.world);
+    if (int rc = comm_load()) return rc;
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof u);
+    CUDA_TRY(cudaSetDevice(g_ctx.device));
+    NCCL_TRY(g_comm.CommInitRank(&g_comm.comm, world, u, rank));
+    g_comm.rank = rank;
+    g_comm.world = world;
+    CUDA_TRY(cudaMalloc(&g_comm.d_scratch, 2 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(g_comm.d_scratch, 0, 2 * sizeof(unsigned long long)));
+    return 0;
+}
+
+int crp_comm_info(int *rank, int *world) {
+    if (rank) *rank = g_comm.comm ? g_comm.rank : 0;
+    if (world) *world = g_comm.comm ? g_comm.world : 1;
+    return 0;
+}
+
+/* all ranks' streams have drained and every rank has arrived (all-reduce of one word + sync) */
+int crp_comm_barrier(void) {
+    if (int rc = need_ctx()) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (!g_comm.comm) return 0;
+    NCCL_TRY(g_comm.AllReduce(g_comm.d_scratch, g_comm.d_scratch + 1, 1, ncclUint64, ncclSum, g_comm.comm, g_ctx.stream));
+    CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+    return 0;
+}
+
+/* element-wise maximum of n doubles over all ranks (timings: the slowest rank sets the step) */
+int crp_comm_max_f64(double *v, uint32_t n) {
+    if (int rc = need_ctx()) return rc;
+    if (!v && n) return fail(CRP_ERR_ARG, "v is NULL");
+    if (!g_comm.comm || n == 0) return 0;
+    double *d = nullptr;
+    CUDA_TRY(dev_alloc(&d, n * sizeof(double), g_ctx.stream));
+    CUDA_TRY(cudaMemcpyAsync(d, v, n * sizeof(double), cudaMemcpyHostToDevice, g_ctx.stream));
+    NCCL_TRY(g_comm.AllReduce(d, d, n, ncclDouble, ncclMax, g_comm.comm, g_ctx.stream));
+    CUDA_TRY(cudaMemcpyAsync(v, d, n * sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream));
+    CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+    dev_free(d, g_ctx.stream);
+    return 0;
+}
+
+int crp_comm_sum_f64(double *v, uint32_t n) {
+    if (int rc = need_ctx()) return rc;
+    if (!v && n) return fail(CRP_ERR_ARG, "v is NULL");
+    if (!g_comm.comm || n == 0) return 0;
+    double *d = nullptr;
+    CUDA_TRY(dev_alloc(&d, n * sizeof(double), g_ctx.stream));
+    CUDA_TRY(cudaMemcpyAsync(d, v, n * sizeof(double), cudaMemcpyHostToDevice, g_ctx.stream));
+    NCCL_TRY(g_comm.AllReduce(d, d, n, ncclDouble, ncclSum, g_comm.comm, g_ctx.stream));
+    CUDA_TRY(cudaMemcpyAsync(v, d, n * sizeof(double), cudaMemcpyDeviceToHost, g_ctx.stream));
+    CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+    dev_free(d, g_ctx.stream);
+    return 0;
+}
+
+int crp_comm_shutdown(void) {
+    if (g_comm.comm) {
+        cudaDeviceSynchronize();
+        g_comm.CommDestroy(g_comm.comm);
+        cudaFree(g_comm.d_scratch);
+        g_comm.comm = nullptr;
+        g_comm.d_scratch = nullptr;
+        g_comm.rank = 0;
+        g_comm.world = 1;
+    }
+    return 0;
+}
+
+/* Evict the L2 cache (benchmarks: between timed scans): a memset larger than L2, on the library stream. */
+int crp_flush_l2(void) {
+    if (int rc = need_ctx()) return rc;
+    unsigned char *buf = nullptr;                    // from the block cache: allocated once, reused by every call
+    const size_t bytes = 512ull << 20;
+    CUDA_TRY(dev_alloc(&buf, bytes, g_ctx.stream));
+    cudaError_t e = cudaMemsetAsync(buf, 0, bytes, g_ctx.stream);
+    dev_free(buf, g_ctx.stream);
+    CUDA_TRY(e);
+    CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+    return 0;
+}
+
+int crp_device_synchronize(void) {
+    if (int rc = need_ctx()) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
     return 0;
 }
 
@@ -462,15 +642,6 @@ static int commit_enqueue(crp_genome *g) {
         return fail(CRP_ERR_NOMEM, "cudaMalloc of %llu record bytes + %llu staging bytes failed",
                     (unsigned long long)rec_bytes, (unsigned long long)ascii_bytes);
     }
-    {
-        const size_t sp_bytes = (size_t)g->n_tiles * (sizeof(unsigned long long) + sizeof(ulonglong2)) + 48;
-        if (dev_alloc(&g->sp_state, sp_bytes, st) != cudaSuccess) {
-            cudaGetLastError();
-            return fail(CRP_ERR_NOMEM, "cudaMalloc of %llu bytes of scan state failed", (unsigned long long)sp_bytes);
-        }
-        CUDA_TRY(cudaMemsetAsync(g->sp_state, 0, sp_bytes, st));
-        g->sp_epoch = g->sp_ticket = g->sp_done = 0;
-    }
     for (int i = 0; i < 3; ++i)
         if (!g->ev[i]) CUDA_TRY(cudaEventCreate(&g->ev[i]));
     CUDA_TRY(cudaEventRecord(g->ev[0], st));
@@ -583,7 +754,6 @@ int crp_genome_free(crp_genome *g) {
     cudaStream_t st = stream_of(g);
     dev_free(g->records, st);
     dev_free(g->pam, st);
-    dev_free(g->sp_state, st);
     dev_free(g->d_ascii, st);
     pinned_put(g->h_bad);
     dev_free(g->d_seg_first, st);
@@ -631,46 +801,7 @@ struct ScanPlan {
     uint32_t wave_tiles, n_waves;
 };
 
-// CRP_SCAN_KERNEL: "ws" = warp-specialised kernel (scan_ws.cuh), "sp" = experimental single-pass
-// kernel (scan_sp.cuh), anything else = the two-phase kernel of scan.cuh
-static int scan_kernel_choice() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("CRP_SCAN_KERNEL");
-        v = (e && !strcmp(e, "sp")) ? 1 : (e && !strcmp(e, "ws")) ? 2 : 0;
-    }
-    return v;
-}
-
-static int plan_scan_ws(const crp_genome *g, bool scored, ScanPlan *p) {
-    p->fn = scored ? (const void *)k_scan_ws<true> : (const void *)k_scan_ws<false>;
-    p->threads = kWsThreads;
-    p->smem = kWsSmem;
-    static bool ready[2] = {false, false};
-    if (!ready[scored ? 1 : 0]) {
-        CUDA_TRY(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
-        int per_sm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p->fn, kWsThreads, p->smem));
-        if (per_sm < 1) return fail(CRP_ERR_CUDA, "warp-specialised scan kernel does not fit on an SM");
-        ready[scored ? 1 : 0] = true;
-    }
-    uint64_t grid = (uint64_t)g_ctx.sm_count;
-    if (grid > (uint64_t)kWsMaxGrid) grid = kWsMaxGrid;
-    if (grid > g->n_tiles) grid = g->n_tiles;
-    if (grid < 1) grid = 1;
-    p->grid = (unsigned)grid;
-    uint64_t wave = grid * kWsMaxRange;
-    if (const char *e = getenv("CRP_WAVE_TILES")) {
-        const long v = atol(e);
-        if (v > 0 && (uint64_t)v < wave) wave = (uint64_t)v;
-    }
-    p->wave_tiles = (uint32_t)wave;
-    p->n_waves = (uint32_t)((g->n_tiles + wave - 1) / wave);
-    return 0;
-}
-
 static int plan_scan(const crp_genome *g, bool scored, ScanPlan *p) {
-    if (scan_kernel_choice() == 2) return plan_scan_ws(g, scored, p);
     p->threads = kThreads;
     p->fn = scored ? (const void *)k_scan_score<true> : (const void *)k_scan_score<false>;
     const unsigned grid_max = (unsigned)g_ctx.sm_count * CRP_CTAS_PER_SM;
@@ -705,71 +836,7 @@ static int plan_scan(const crp_genome *g, bool scored, ScanPlan *p) {
     return 0;
 }
 
-// CRP_SCAN_KERNEL=sp selects the experimental single-pass kernel (scan_sp.cuh); the default
-// is the two-phase cooperative kernel (scan.cuh), which is faster
-static bool use_single_pass() { return scan_kernel_choice() == 1; }
-
-// single-pass kernel (scan_sp.cuh): one CTA of 4 teams per SM, ordinary launch
-static int launch_scan_sp(const crp_genome *g, crp_result *r) {
-    cudaStream_t st = r->st;
-    const void *fn = r->scored ? (const void *)k_scan_sp<true> : (const void *)k_scan_sp<false>;
-    const size_t tab = r->scored ? (kRs1TableBytes + 127) / 128 * 128 : 0;
-    const size_t smem = tab + kTeams * kTeamBytes;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[r->scored ? 1 : 0]) {
-        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[r->scored ? 1 : 0] = true;
-    }
-    const uint32_t n_seg = (uint32_t)g->segs.size();
-    unsigned grid = (unsigned)g_ctx.sm_count;
-    const unsigned want = (g->n_tiles + kTeams - 1) / kTeams;
-    if (grid > want) grid = want;
-    SpArgs a;
-    a.records = g->records;
-    a.n_tiles = g->n_tiles;
-    a.guide_len = r->guide_len;
-    a.flags = r->flags;
-    if (const char *e = getenv("CRP_SP_DEBUG")) a.flags |= (uint32_t)strtoul(e, nullptr, 0);
-    g->sp_epoch = g->sp_epoch % 255u + 1u;
-    a.epoch = g->sp_epoch;
-    a.ticket_base = g->sp_ticket;
-    a.done_base = g->sp_done;
-    g->sp_ticket += g->n_tiles + 2u * grid * kTeams;      // every team draws (tiles it scans + 2) tickets
-    g->sp_done += g->n_tiles;
-    a.tables = g_ctx.d_tables;
-    a.capacity = r->capacity;
-    a.pos_plus = r->pos[0];
-    a.pos_minus = r->pos[1];
-    a.packed_plus = r->packed[0];
-    a.packed_minus = r->packed[1];
-    a.x_plus = r->x[0];
-    a.x_minus = r->x[1];
-    a.agg = reinterpret_cast<unsigned long long *>(g->sp_state);
-    a.incl = reinterpret_cast<ulonglong2 *>(g->sp_state + ((size_t)g->n_tiles * sizeof(unsigned long long) + 15) / 16 * 16);
-    a.ctl = reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned char *>(a.incl) + (size_t)g->n_tiles * sizeof(ulonglong2));
-    a.seg_counts = r->d_counts;
-    a.seg_first_tile = g->d_seg_first;
-    a.seg_tile_count = g->d_seg_count;
-    a.n_seg = n_seg;
-    CUDA_TRY(cudaEventRecord(r->ev[0], st));
-    if (g->n_tiles) {
-        void *params[] = {(void *)&a};
-        CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(kSpThreads), params, smem, st));
-        g_ctx.launches++;
-        CUDA_TRY(cudaGetLastError());
-    } else if (n_seg) {
-        CUDA_TRY(cudaMemsetAsync(r->d_counts, 0, 2 * (size_t)n_seg * sizeof(unsigned long long), st));
-    }
-    CUDA_TRY(cudaEventRecord(r->ev[1], st));
-    if (n_seg)
-        CUDA_TRY(cudaMemcpyAsync(r->h_counts, r->d_counts, 2 * (size_t)n_seg * sizeof(unsigned long long),
-                                 cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaEventRecord(r->ev[2], st));
-    return 0;
-}
-
 static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p) {
-    if (use_single_pass()) return launch_scan_sp(g, r);
     cudaStream_t st = r->st;
     ScanArgs a;
     a.records = g->records;
@@ -793,8 +860,9 @@ static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p) {
     a.warp_pref = s64;
     a.cta_tot = s64 + (size_t)g->n_tiles * kPrefWords;
     a.seg_counts = r->d_counts;
-    a.tickets = reinterpret_cast<unsigned int *>(r->d_counts + 2 * (size_t)n_seg);
+    a.tickets = reinterpret_cast<unsigned int *>(r->d_counts + 2 * (size_t)r->stride);
     a.n_seg = n_seg;
+    a.seg_stride = r->stride;
     a.seg_first_tile = g->d_seg_first;      // NULL for a single-segment genome
     a.seg_tile_count = g->d_seg_count;
     CUDA_TRY(cudaEventRecord(r->ev[0], st));
@@ -803,19 +871,28 @@ static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p) {
         CUDA_TRY(cudaLaunchCooperativeKernel(p.fn, dim3(p.grid), dim3(p.threads), params, p.smem, st));
         g_ctx.launches++;
         CUDA_TRY(cudaGetLastError());
-    } else if (n_seg) {
-        CUDA_TRY(cudaMemsetAsync(r->d_counts, 0, 2 * (size_t)n_seg * sizeof(unsigned long long), st));
+    } else if (r->stride) {
+        CUDA_TRY(cudaMemsetAsync(r->d_counts, 0, 2 * (size_t)r->stride * sizeof(unsigned long long), st));
+    }
+    if (r->d_gather) {
+        // the one exchange step of a sharded scan: every rank's per-segment counts to every rank, right
+        // behind the kernel on the same stream, so the CUDA events bracket kernel + collective
+        CUDA_TRY(cudaEventRecord(r->ev_kernel, st));
+        if (int rc = comm_allgather_u64(r->d_counts, r->d_gather, 2 * (size_t)r->stride, st)) return rc;
     }
     CUDA_TRY(cudaEventRecord(r->ev[1], st));
-    if (n_seg)
-        CUDA_TRY(cudaMemcpyAsync(r->h_counts, r->d_counts, 2 * (size_t)n_seg * sizeof(unsigned long long),
+    if (r->stride)
+        CUDA_TRY(cudaMemcpyAsync(r->h_counts, r->d_counts, 2 * (size_t)r->stride * sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, st));
+    if (r->d_gather)
+        CUDA_TRY(cudaMemcpyAsync(r->h_gather, r->d_gather, (size_t)g_comm.world * 2 * r->stride * sizeof(unsigned long long),
                                  cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaEventRecord(r->ev[2], st));
     return 0;
 }
 
 // Allocate the result of a scan and enqueue the scan on the genome's stream (no waiting).
-static int scan_enqueue(crp_genome *g, int guide_len, uint32_t flags, crp_result **res) {
+static int scan_enqueue(crp_genome *g, int guide_len, uint32_t flags, crp_result **res, uint32_t slots = 0) {
     crp_result *r = new (std::nothrow) crp_result();
     if (!r) return fail(CRP_ERR_NOMEM, "out of host memory");
     r->g = g;
@@ -831,14 +908,23 @@ static int scan_enqueue(crp_genome *g, int guide_len, uint32_t flags, crp_result
     };
     ScanPlan plan = {};
     if ((rc = plan_scan(g, r->scored, &plan))) return bail(rc);
+    r->stride = slots ? slots : n_seg;
     r->zero_offset = ((size_t)g->n_tiles * kPrefWords + 2 * (size_t)plan.grid) * sizeof(unsigned long long);
-    r->state_bytes = r->zero_offset + 2 * (size_t)n_seg * sizeof(unsigned long long) +
+    r->state_bytes = r->zero_offset + 2 * (size_t)r->stride * sizeof(unsigned long long) +
                      ((size_t)plan.n_waves + 2) * sizeof(unsigned int);
     if (dev_alloc(&r->state, r->state_bytes, r->st) != cudaSuccess)
         return bail(fail(CRP_ERR_NOMEM, "cudaMalloc of scan state failed"));
     r->d_counts = reinterpret_cast<unsigned long long *>(r->state + r->zero_offset);
-    r->h_counts = static_cast<unsigned long long *>(pinned_get((2 * (size_t)n_seg + 1) * sizeof(unsigned long long)));
+    r->h_counts = static_cast<unsigned long long *>(pinned_get((2 * (size_t)r->stride + 1) * sizeof(unsigned long long)));
     if (!r->h_counts) return bail(fail(CRP_ERR_NOMEM, "cudaHostAlloc of the counts failed"));
+    if (slots) {
+        const size_t gb = (size_t)g_comm.world * 2 * slots * sizeof(unsigned long long);
+        if (dev_alloc(&r->d_gather, gb, r->st) != cudaSuccess)
+            return bail(fail(CRP_ERR_NOMEM, "cudaMalloc of the gathered counts failed"));
+        r->h_gather = static_cast<unsigned long long *>(pinned_get(gb));
+        if (!r->h_gather) return bail(fail(CRP_ERR_NOMEM, "cudaHostAlloc of the gathered counts failed"));
+        if (cudaEventCreate(&r->ev_kernel) != cudaSuccess) return bail(fail(CRP_ERR_CUDA, "cudaEventCreate failed"));
+    }
     if (cudaEventCreate(&r->ev[0]) != cudaSuccess || cudaEventCreate(&r->ev[1]) != cudaSuccess ||
         cudaEventCreateWithFlags(&r->ev[2], cudaEventDisableTiming) != cudaSuccess)
         return bail(fail(CRP_ERR_CUDA, "cudaEventCreate failed"));
@@ -862,9 +948,17 @@ static int scan_finish(crp_genome *g, crp_result *r) {
         r->seg_minus.assign(n_seg, 0);
         for (uint32_t s = 0; s < n_seg; ++s) {
             r->seg_plus[s] = r->h_counts[s];
-            r->seg_minus[s] = r->h_counts[n_seg + s];
+            r->seg_minus[s] = r->h_counts[r->stride + s];
             r->n_plus += r->seg_plus[s];
             r->n_minus += r->seg_minus[s];
+        }
+        {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, r->ev[0], r->ev[1]);
+            r->ms_scan += ms;
+            if (r->ev_kernel) cudaEventElapsedTime(&ms, r->ev[0], r->ev_kernel);
+            r->ms_kernel += ms;
+            r->n_launches++;
         }
         const uint64_t need = r->n_plus > r->n_minus ? r->n_plus : r->n_minus;
         if (need <= r->capacity) break;
@@ -875,7 +969,6 @@ static int scan_finish(crp_genome *g, crp_result *r) {
         if (int rc = plan_scan(g, r->scored, &plan)) return rc;
         if (int rc = launch_scan(g, r, plan)) return rc;
     }
-    cudaEventElapsedTime(&r->ms_scan, r->ev[0], r->ev[1]);
     if (r->scored && (r->flags & CRP_SCAN_LOGISTIC)) {
         const uint64_t n[2] = {r->n_plus, r->n_minus};
         for (int s = 0; s < 2; ++s)
@@ -885,6 +978,8 @@ static int scan_finish(crp_genome *g, crp_result *r) {
                 g_ctx.launches++;
             }
         CUDA_TRY(cudaGetLastError());
+        // whoever reads the streams from another stream (crp_scan_segments) orders itself after this event
+        CUDA_TRY(cudaEventRecord(r->ev[2], r->st));
     }
     return 0;
 }
@@ -907,7 +1002,39 @@ int crp_scan_score(crp_genome *g, int guide_len, uint32_t flags, crp_result **re
     return 0;
 }
 
+int crp_scan_score_sharded(crp_genome *g, int guide_len, uint32_t flags, uint32_t slots, crp_result **res) {
+    if (!g || !res) return fail(CRP_ERR_ARG, "NULL argument");
+    if (int rc = need_ctx()) return rc;
+    if (!g_comm.comm) return fail(CRP_ERR_STATE, "crp_comm_init has not been called");
+    if (!g->committed) return fail(CRP_ERR_STATE, "genome not committed");
+    if (guide_len < 1 || guide_len > 1000000) return fail(CRP_ERR_ARG, "guide_len %d out of range", guide_len);
+    if (slots == 0 || slots < g->segs.size())
+        return fail(CRP_ERR_ARG, "slots = %u is smaller than the %zu segments of this shard", slots, g->segs.size());
+    crp_result *r = nullptr;
+    if (int rc = scan_enqueue(g, guide_len, flags, &r, slots)) return rc;
+    if (int rc = scan_finish(g, r)) {
+        crp_result_free(r);
+        return rc;
+    }
+    *res = r;
+    return 0;
+}
+
+int crp_result_gathered_counts(const crp_result *res, uint64_t *counts) {
+    if (!res || !counts) return fail(CRP_ERR_ARG, "NULL argument");
+    if (!res->h_gather) return fail(CRP_ERR_STATE, "not the result of a sharded scan");
+    memcpy(counts, res->h_gather, (size_t)g_comm.world * 2 * res->stride * sizeof(uint64_t));
+    return 0;
+}
+
+static int rs1_rows(uint64_t n, const uint8_t *rows, const uint8_t *cls, double *score, int logistic);
 int crp_rs1_score(uint64_t n, const uint8_t *rows, const uint8_t *cls, double *score) {
+    return rs1_rows(n, rows, cls, score, 1);
+}
+int crp_rs1_preactivation(uint64_t n, const uint8_t *rows, const uint8_t *cls, double *x) {
+    return rs1_rows(n, rows, cls, x, 0);
+}
+static int rs1_rows(uint64_t n, const uint8_t *rows, const uint8_t *cls, double *score, int logistic) {
     if (n && (!rows || !cls || !score)) return fail(CRP_ERR_ARG, "NULL argument");
     if (int rc = need_ctx()) return rc;
     if (!n) return 0;
@@ -921,7 +1048,7 @@ int crp_rs1_score(uint64_t n, const uint8_t *rows, const uint8_t *cls, double *s
     }
     CUDA_TRY(cudaMemcpyAsync(d_rows, rows, 30 * n, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(d_rows + 30 * n, cls, n, cudaMemcpyHostToDevice, st));
-    k_rs1_rows<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_rows, d_rows + 30 * n, n, d_out);
+    k_rs1_rows<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_rows, d_rows + 30 * n, n, d_out, logistic);
     g_ctx.launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(score, d_out, n * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1010,11 +1137,22 @@ int crp_result_timing(const crp_result *res, float *ms_scan) {
     return 0;
 }
 
+int crp_result_timing_detail(const crp_result *res, float *ms_kernels, float *ms_total, uint32_t *n_launches) {
+    if (!res) return fail(CRP_ERR_ARG, "res is NULL");
+    if (ms_kernels) *ms_kernels = res->ms_kernel;
+    if (ms_total) *ms_total = res->ms_scan;
+    if (n_launches) *n_launches = res->n_launches;
+    return 0;
+}
+
 int crp_result_free(crp_result *r) {
     if (!r) return 0;
     free_streams(r);
     dev_free(r->state, r->st);
+    dev_free(r->d_gather, r->st);
     pinned_put(r->h_counts);
+    pinned_put(r->h_gather);
+    if (r->ev_kernel) cudaEventDestroy(r->ev_kernel);
     for (cudaEvent_t e : r->ev)
         if (e) cudaEventDestroy(e);
     delete r;
@@ -1057,6 +1195,9 @@ int crp_scan_segments(uint32_t n_segments, const crp_segment_desc *segments, int
         if (off[0] + rs[k]->n_plus > capacity || off[1] + rs[k]->n_minus > capacity) {
             overflow = true;        // keep counting so that the caller learns the capacity it needs
         } else {
+            // the rows leave on lane_out: after everything scan_finish queued on the lane (the logistic pass)
+            if (cudaError_t e = cudaStreamWaitEvent(g_ctx.lane_out, rs[k]->ev[2], 0))
+                return fail(CRP_ERR_CUDA, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
             if (int e = fetch_enqueue(rs[k], 0, 0, rs[k]->n_plus, pos_plus ? pos_plus + off[0] : nullptr,
                                       scored && packed_plus ? packed_plus + off[0] : nullptr,
                                       scored && x_plus ? x_plus + off[0] : nullptr, g_ctx.lane_out)) return e;

@@ -351,9 +351,10 @@ struct ScanArgs {
     unsigned long long *warp_pref;   // [n_tiles][kPrefWords] exclusive prefix of every warp chunk inside its count range, then the tile total
     unsigned long long *cta_tot;     // [2][gridDim.x] range totals, double-buffered by wave parity
     unsigned int *tickets;           // [n_waves] emit-phase dispensers of the dynamic tiles
-    unsigned long long *seg_counts;  // [2 * n_seg] out: plus[0..n_seg) then minus[0..n_seg)
+    unsigned long long *seg_counts;  // [2 * seg_stride] out: plus[0..n_seg) then, from seg_stride on, minus[0..n_seg);
+                                     // slots n_seg .. seg_stride-1 are zeroed (fixed-size block of a sharded scan's all-gather)
     const uint32_t *seg_first_tile, *seg_tile_count;   // [n_seg]
-    uint32_t n_seg;
+    uint32_t n_seg, seg_stride;
 };
 
 // optional phase timeline (tools/phase_timeline.py): 8 x u64 per CTA, or NULL
@@ -697,7 +698,12 @@ k_scan_score(const ScanArgs a) {
         if (kScore && wave == 0) mbar_wait(&s_tabbar, 0);
         // per-segment candidate counts of this wave: prefix at the end of the segment's last
         // tile minus prefix at the start of its first one (segments are dealt to threads)
-        for (uint32_t sg = cta * kThreads + tid; sg < a.n_seg; sg += G * kThreads) {
+        for (uint32_t sg = cta * kThreads + tid; sg < a.seg_stride; sg += G * kThreads) {
+            if (sg >= a.n_seg) {                                                        // padding of the all-gather block
+                a.seg_counts[sg] = 0ull;
+                a.seg_counts[a.seg_stride + sg] = 0ull;
+                continue;
+            }
             const uint32_t f = a.seg_first_tile ? a.seg_first_tile[sg] : 0u;            // NULL: one segment = all tiles
             const uint32_t c = a.seg_tile_count ? a.seg_tile_count[sg] : a.n_tiles;
             const uint32_t lo_t = max(f, w_lo), hi_t = min(f + c, w_hi);       // tiles of the segment in this wave
@@ -707,7 +713,7 @@ k_scan_score(const ScanArgs a) {
                       (s_rangepref[(lo_t - w_lo) / k] + a.warp_pref[(size_t)lo_t * kPrefWords]);
             const unsigned long long plus = cnt >> 32, minus = cnt & 0xFFFFFFFFull;
             a.seg_counts[sg] = (wave ? a.seg_counts[sg] : 0ull) + plus;
-            a.seg_counts[a.n_seg + sg] = (wave ? a.seg_counts[a.n_seg + sg] : 0ull) + minus;
+            a.seg_counts[a.seg_stride + sg] = (wave ? a.seg_counts[a.seg_stride + sg] : 0ull) + minus;
         }
         if (tid == 0) {
             if (pre) mbar_arrive(&ring.full[0]);                   // tile 0 came through ring.pre: skip that phase of slot 0
@@ -789,7 +795,7 @@ __global__ void k_logistic(double *__restrict__ x, uint64_t n) {
 // ASCII bytes (only 'A' 'T' 'C' 'G' score, CROPSR.py:300-302), row i summed in the BLAS class
 // cls[i] (first-order matmul | second-order matmul << 4), then the reference's logistic.
 __global__ void k_rs1_rows(const uint8_t *__restrict__ rows, const uint8_t *__restrict__ cls, uint64_t n,
-                           double *__restrict__ score) {
+                           double *__restrict__ score, int logistic) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint8_t *r = rows + 30 * i;
@@ -803,7 +809,8 @@ __global__ void k_rs1_rows(const uint8_t *__restrict__ rows, const uint8_t *__re
             s1 |= (code >> 1) << q;
         }
     }
-    score[i] = np_logistic_f64(rs1_dense(s0, s1, valid, (int)(cls[i] & 15u), (int)(cls[i] >> 4)));
+    const double x = rs1_dense(s0, s1, valid, (int)(cls[i] & 15u), (int)(cls[i] >> 4));
+    score[i] = logistic ? np_logistic_f64(x) : x;
 }
 
 struct RescoreItem {

@@ -77,6 +77,33 @@ int crp_abi_version(void);
  * multiples of this (any multiple of 128 is accepted). */
 int crp_tile_size(void);
 
+/* Wait for everything this library has queued on the device. */
+int crp_device_synchronize(void);
+/* Evict the L2 cache (a 512 MiB memset on the library stream, waited for): benchmarks call it
+ * between timed scans so that no scan finds its tile records in L2. */
+int crp_flush_l2(void);
+
+/* ---- several GPUs: one process per GPU, one NCCL communicator ---------------
+ * The reference scans its chromosomes one after the other in one Python loop
+ * (CROPSR.py:409); here the genome is cut into contiguous, tile-aligned shards
+ * (cropsr_b200/shard.py), every process scans its own shard, and the only exchange is an
+ * all-gather of the per-segment candidate counts, from which every rank derives where its rows
+ * sit in the reference's order (token by token, '+' then '-').  The launcher creates the id on
+ * rank 0 (crp_comm_unique_id), hands the 128 bytes to every rank by whatever channel it has
+ * (cropsr_b200/launch.py: a TCP rendezvous on MASTER_ADDR:MASTER_PORT), and every rank calls
+ * crp_comm_init after crp_init.  NCCL is loaded with dlopen("libnccl.so.2") on first use: a
+ * single-GPU process never needs it. */
+#define CRP_COMM_ID_BYTES 128
+int crp_comm_unique_id(uint8_t *id /* [CRP_COMM_ID_BYTES] */);
+int crp_comm_init(int rank, int world, const uint8_t *id);
+int crp_comm_info(int *rank, int *world);           /* 0 / 1 without a communicator */
+/* Device-wide synchronize, then an all-reduce of one word over all ranks, waited for. */
+int crp_comm_barrier(void);
+/* Element-wise max / sum of n host doubles over all ranks, in place (timings, totals). */
+int crp_comm_max_f64(double *v, uint32_t n);
+int crp_comm_sum_f64(double *v, uint32_t n);
+int crp_comm_shutdown(void);
+
 /* Pinned host memory for staging (FASTA bytes in, candidate arrays out). */
 int crp_host_alloc(void **ptr, uint64_t bytes);
 int crp_host_free(void *ptr);
@@ -138,6 +165,15 @@ int crp_genome_free(crp_genome *g);
  * (CROPSR.py:417-434).
  */
 int crp_scan_score(crp_genome *g, int guide_len, uint32_t flags, crp_result **res);
+/* The same scan on one shard of a genome that is spread over the ranks of crp_comm_init: the
+ * kernel writes this shard's per-segment counts as a block of 2 * slots words
+ * {plus[0..slots), minus[0..slots)} (slots >= the segments of every rank; unused slots are 0) and
+ * an ncclAllGather on the same stream, right behind the kernel, hands every rank the blocks of
+ * all ranks.  crp_result_timing then reports kernel + collective, crp_result_timing_detail the
+ * kernel alone as well.  Collective: every rank must call it, with the same slots. */
+int crp_scan_score_sharded(crp_genome *g, int guide_len, uint32_t flags, uint32_t slots, crp_result **res);
+/* counts[(rank * 2 + strand) * slots + segment] of the scan above, strand 0 = '+'. */
+int crp_result_gathered_counts(const crp_result *res, uint64_t *counts /* [world][2][slots] */);
 int crp_result_totals(const crp_result *res, uint64_t *n_plus, uint64_t *n_minus);
 /* Per-segment candidate counts, arrays of crp_genome_num_segments() entries. */
 int crp_result_segment_counts(const crp_result *res, uint64_t *n_plus, uint64_t *n_minus);
@@ -261,13 +297,24 @@ int crp_logistic(uint64_t n, const double *x, double *score);
  * n-row call are not canonical is index logic, cropsr_b200/blas_order.py).  score[i] is the
  * reference's return value, logistic included. */
 int crp_rs1_score(uint64_t n, const uint8_t *rows, const uint8_t *cls, double *score);
+/* The same without the logistic: x[i] = -(((A+B)+0.59763615)+(-0.2026259)) of row i in class cls[i]
+ * (a host that holds the tokens re-sums the few non-canonical rows of a slice without a genome handle). */
+int crp_rs1_preactivation(uint64_t n, const uint8_t *rows, const uint8_t *cls, double *x);
 
 /* Kernel timings (CUDA events on the library stream) of the last commit /
  * scan: milliseconds. */
 int crp_genome_timing(const crp_genome *g, float *ms_h2d, float *ms_pack);
+/* ms_scan: every launch of the scan (a rerun after a capacity overflow included) and, for a
+ * sharded scan, the all-gather behind it. */
 int crp_result_timing(const crp_result *res, float *ms_scan);
+/* ms_kernels: the scan kernels alone; ms_total = ms_scan above; n_launches: 1, or 2 if the first
+ * capacity guess (1/8 candidate per position and strand) was too small and the scan ran again. */
+int crp_result_timing_detail(const crp_result *res, float *ms_kernels, float *ms_total, uint32_t *n_launches);
 /* Number of kernel launches issued by this library since crp_init. */
 int crp_launch_count(uint64_t *n);
+/* Profiling hook (tools/phase_timeline.py): device buffer of 8 x uint64 per CTA that k_scan_score
+ * stamps with %globaltimer at its phase boundaries, or NULL to switch the stamps off. */
+int crp_debug_set_times(void *dev_ptr);
 
 #ifdef __cplusplus
 }

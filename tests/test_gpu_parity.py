@@ -451,26 +451,24 @@ def test_logistic_flag_stores_the_reference_score(eng):
             h.free()
 
 
-@pytest.mark.parametrize("kernel", ["sp", "ws"])
-def test_alternative_scan_kernels_are_exact_too(eng, kernel):
-    """CRP_SCAN_KERNEL=sp (csrc/scan_sp.cuh, single pass with decoupled look-back) and =ws
-    (csrc/scan_ws.cuh, warp-specialised emit phase) are slower than the default kernel and kept as
-    measured alternatives; they must give the same candidates and the same fp64 x.
-    The library reads the variable once, so they run in a subprocess: smoke(), and for ws the
-    tile-edge / dense-tile / multi-wave / random-FASTA / sharding cases of this file as well."""
-    import subprocess, sys
-    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
-    env = dict(os.environ, CRP_SCAN_KERNEL=kernel)
-    out = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, env=env,
-                         capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr[-2000:]
-    assert "smoke ok" in out.stdout
-    if kernel == "sp" or os.environ.get("CRP_SCAN_KERNEL"):
-        return                      # the wider set is for ws; and never recurse from inside such a subprocess
-    out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_parity.py", "-k",
-                          "tile_boundaries or multi_wave or random_fastas or many_scaffolds or sharded_scan"],
-                         cwd=root, env=env, capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+def test_scan_segments_logistic_equals_scan_score_plus_logistic(eng):
+    """crp_scan_segments with CRP_SCAN_LOGISTIC: the rows leave on their own stream, and must be the
+    rows AFTER the logistic pass the lane queued (the copy used to race the pass)."""
+    from cropsr_b200 import engine, ingest, _native as N
+    toks = [np.frombuffer(v.encode(), np.uint8) for v in
+            ingest.fasta_text_to_tokens(synthetic_fasta(41, [300000, 70000, 120000], gc=0.5, lower_frac=0.1)).values()]
+    segs = [(k, t, 0, None) for k, t in enumerate(toks)]
+    for _ in range(3):
+        a_plain, np_, nm_, _ms = engine.scan_segments(segs, 20)
+        a_log, lp, lm, _ms = engine.scan_segments(segs, 20, flags=N.CRP_SCAN_LOGISTIC)
+        assert np.array_equal(np_, lp) and np.array_equal(nm_, lm)
+        for strand, n in (("+", int(np_.sum())), ("-", int(nm_.sum()))):
+            x = a_plain.arrays[strand]["x"][:n]
+            y = a_log.arrays[strand]["x"][:n]
+            assert n > 1000 and np.array_equal(y, engine.logistic(x))
+            assert np.array_equal(a_plain.arrays[strand]["pos"][:n], a_log.arrays[strand]["pos"][:n])
+        a_plain.free()
+        a_log.free()
 
 
 def test_many_scaffolds_match_oracle(eng):

@@ -18,6 +18,11 @@ def test_library_loads_and_exports_header_symbols(built_lib):
     assert declared == set(built_lib.SIGNATURES), declared ^ set(built_lib.SIGNATURES)
     for name in declared:
         getattr(built_lib.lib, name)
+    # the dynamic symbol table of the .so itself: every crp_* it exports is declared, and nothing else is C-named
+    import subprocess
+    nm = subprocess.run(["nm", "-D", "--defined-only", built_lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {ln.split()[-1] for ln in nm.splitlines() if ln.split()[-1].startswith("crp_")}
+    assert exported == declared, exported ^ declared
     assert built_lib.lib.crp_abi_version() == built_lib.ABI_VERSION
     assert built_lib.lib.crp_last_error() is not None
 
