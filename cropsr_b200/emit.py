@@ -109,16 +109,19 @@ def apply_cutsite(start_pos, end_pos, crispr_sys):
     return cutsite
 
 
-def emission_slices(size):
+def emission_slices(size, chunk_rows=None):
     """(start, count) of every slice of a cumulative list of `size` rows that
     the reference scores and writes (CROPSR.py:451-472): full 1e6-row slices,
     then -- because the start of the last slice is computed as count*counter --
     a last partial slice that starts at r*q instead of 1e6*q; when size is an
-    exact multiple of 1e6 the final full slice is never written."""
-    q, r = divmod(size, CHUNK_ROWS)
+    exact multiple of 1e6 the final full slice is never written.
+    chunk_rows: the reference's literal 1000000 (CROPSR.py:453); tests shrink it to walk the
+    same plan on small inputs."""
+    chunk = CHUNK_ROWS if chunk_rows is None else int(chunk_rows)
+    q, r = divmod(size, chunk)
     if r:
-        return [(CHUNK_ROWS * j, CHUNK_ROWS) for j in range(q)] + [(r * q, r)]
-    return [(CHUNK_ROWS * j, CHUNK_ROWS) for j in range(max(q - 1, 0))]
+        return [(chunk * j, chunk) for j in range(q)] + [(r * q, r)]
+    return [(chunk * j, chunk) for j in range(max(q - 1, 0))]
 
 
 # byte translation of the reference's replace chains (CROPSR.py:120,128)
@@ -323,7 +326,7 @@ def write_header(path):
         csv.writer(f).writerow(HEADER)
 
 
-def emit_cumulative(path, table, genome, blas_threads=1, id_stream=None):
+def emit_cumulative(path, table, genome, blas_threads=1, id_stream=None, chunk_rows=None):
     """Append the rows the reference writes after one more token has been
     scanned: ALL candidates accumulated so far (CROPSR.py:407,442), through the
     chunk plan.  Returns the number of rows written."""
@@ -335,7 +338,7 @@ def emit_cumulative(path, table, genome, blas_threads=1, id_stream=None):
     with open(path, "ab") as f, ThreadPoolExecutor(max_workers=1) as writer:
         ids = id_stream.next(size) if id_stream else legacy_id_bytes(size)   # get_id(size), CROPSR.py:448
         pending = [None, None]
-        for k, (start, count) in enumerate(emission_slices(size)):
+        for k, (start, count) in enumerate(emission_slices(size, chunk_rows)):
             scores, scored = slice_scores(table, genome, start, count, blas_threads)
             if pending[k & 1] is not None:
                 pending[k & 1].result()                     # that buffer's previous rows are on their way to disk

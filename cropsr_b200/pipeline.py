@@ -116,7 +116,8 @@ def write_side_output(path, tokens, result, gff_frame, flank, formatted_path, an
 
 
 def run_cas9(fasta, gff, output="data.csv", guide_len=20, verbose=False, blas_threads=1,
-             time_path="time.txt", out=print, side_output=None, flank=200, device_ingest=True, annotation_info=None):
+             time_path="time.txt", out=print, side_output=None, flank=200, device_ingest=True, annotation_info=None,
+             chunk_rows=None):
     begin = time.time()
     timing = open(time_path, "w")                       # CROPSR.py:371
     fast = scan_fasta_file(fasta, guide_len) if device_ingest else None
@@ -152,7 +153,7 @@ def run_cas9(fasta, gff, output="data.csv", guide_len=20, verbose=False, blas_th
         if verbose:
             n = len(plus["pos"]) + len(minus["pos"])
             out(f"\n                {n:n} Cas9 PAM sites were found on {key[1:]}\n                ")
-        rows_written += emit.emit_cumulative(output, table, genome, blas_threads, id_stream)
+        rows_written += emit.emit_cumulative(output, table, genome, blas_threads, id_stream, chunk_rows)
         timing.write("Total runtime of the program is " + str(time.time() - begin))   # :476-477
     id_stream.close()
     timing.close()

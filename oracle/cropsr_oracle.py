@@ -267,9 +267,11 @@ def score_model(seqs, threads=1):
 
 
 # --------------------------------------------------------------- emission ---
-def emission_slices(size):
+def emission_slices(size, chunk=None):
     """CROPSR.py:451-472 replayed literally: the (start, count) of every slice
-    that gets scored and written for a cumulative list of `size` rows."""
+    that gets scored and written for a cumulative list of `size` rows.
+    chunk: the literal 1000000 of CROPSR.py:453 (tests shrink it)."""
+    CHUNK = globals()["CHUNK"] if chunk is None else chunk
     out = []
     count = 0
     counter = 0
@@ -282,7 +284,8 @@ def emission_slices(size):
     return out
 
 
-def emission_slices_closed_form(size):
+def emission_slices_closed_form(size, chunk=None):
+    CHUNK = globals()["CHUNK"] if chunk is None else chunk
     q, r = divmod(size, CHUNK)
     if r > 0:
         return [(CHUNK * j, CHUNK) for j in range(q)] + [(r * q, r)]
@@ -315,7 +318,7 @@ def rows_for_slice(dataset, ids, start, count, score="blas", threads=1):
     return rows
 
 
-def run(fasta_text, out, guide_len=20, score="blas", threads=1, log=None):
+def run(fasta_text, out, guide_len=20, score="blas", threads=1, log=None, chunk=None):
     """CROPSR.py:333-486 main() on FASTA text, writing the CSV to the text
     stream `out` (must have been opened with newline='').  Returns per-token
     unique candidate lists.  The 5 s sleep per token (:478) is omitted."""
@@ -333,14 +336,14 @@ def run(fasta_text, out, guide_len=20, score="blas", threads=1, log=None):
         dataset.extend(cands)
         size = len(dataset)
         ids = make_ids(size)
-        for start, count in emission_slices(size):
+        for start, count in emission_slices(size, chunk):
             w.writerows(rows_for_slice(dataset, ids, start, count, score, threads))
     return per_token
 
 
-def run_to_string(fasta_text, guide_len=20, score="blas", threads=1):
+def run_to_string(fasta_text, guide_len=20, score="blas", threads=1, chunk=None):
     buf = io.StringIO(newline="")
-    run(fasta_text, buf, guide_len, score, threads)
+    run(fasta_text, buf, guide_len, score, threads, chunk=chunk)
     return buf.getvalue()
 
 

@@ -7,7 +7,11 @@ recording the environment they were produced in.
 The runner only wraps the reference from the outside:
   * time.sleep is stubbed (the reference sleeps 5 s per chromosome, CROPSR.py:478),
   * numpy's legacy global RNG is seeded so crispr_id is reproducible (:316-318),
-  * OPENBLAS_NUM_THREADS is pinned per case (summation order).
+  * OPENBLAS_NUM_THREADS is pinned per case (summation order),
+  * cases with a `chunk` run the reference's source with ONE literal changed in memory: the
+    1000000 of the row-chunk plan (CROPSR.py:451, both occurrences on that line) becomes the
+    case's value, so that the plan's quirks (misplaced last slice, dropped exact multiple,
+    ids[start-k-1]) are walked on small fixtures.  The file on disk is never touched.
 
 usage: python tests/golden/make_golden.py [case ...]
 """
@@ -30,7 +34,14 @@ import numpy as np
 time.sleep = lambda s: None
 np.random.seed(int(os.environ['GOLDEN_SEED']))
 sys.path.insert(0, %r)
-runpy.run_path(%r, run_name='__main__')
+path = %r
+chunk = os.environ.get('GOLDEN_CHUNK')
+if chunk is None:
+    runpy.run_path(path, run_name='__main__')
+else:
+    src = open(path).read()
+    assert src.count('1000000') == 2
+    exec(compile(src.replace('1000000', str(int(chunk))), path, 'exec'), {'__name__': '__main__', '__file__': path})
 """ % (REF, os.path.join(REF, "CROPSR.py"))
 
 #        name                     fasta                    -l  seed threads
@@ -50,12 +61,19 @@ CASES = [
     ("empty_records",         "empty_records.fa",          20, 22, 1),
     ("mid50k",                "mid50k.fa",                 20, 23, 1),
     ("mid50k_t5",             "mid50k.fa",                 20, 23, 5),
+    # the 1,000,000-row chunk plan shrunk (see the module docstring): name, fasta, -l, seed, threads, chunk
+    ("mid50k_c1000",          "mid50k.fa",                 20, 24, 1, 1000),     # q = 4, r = 671: last slice at r*q
+    ("mid50k_c1557",          "mid50k.fa",                 20, 25, 1, 1557),     # 4671 = 3 * 1557: final slice dropped
+    ("multi3_c20",            "multi3.fa",                 20, 26, 1, 20),       # cumulative lists 50 / 79 / 101
+    ("sample_c5000_t4",       "sample_genome.fa",          20, 27, 4, 5000),     # multi-threaded gemv per 5000-row slice
 ]
 
 
-def run_case(name, fasta, guide_len, seed, threads):
+def run_case(name, fasta, guide_len, seed, threads, chunk=None):
     with tempfile.TemporaryDirectory() as wd:
         env = dict(os.environ, GOLDEN_SEED=str(seed), OPENBLAS_NUM_THREADS=str(threads))
+        if chunk is not None:
+            env["GOLDEN_CHUNK"] = str(chunk)
         argv = [sys.executable, "-c", RUNNER, "-f", os.path.join(FIX, fasta),
                 "-g", os.path.join(FIX, "sample_genome.gff"), "-o", os.path.join(wd, "out.csv"),
                 "-l", str(guide_len), "--cas9"]
@@ -69,7 +87,7 @@ def run_case(name, fasta, guide_len, seed, threads):
         f.write(data)
     with open(os.path.join(OUT, name + ".stdout"), "w") as f:
         f.write(p.stdout)
-    return {"fasta": fasta, "guide_len": guide_len, "seed": seed, "blas_threads": threads,
+    return {"fasta": fasta, "guide_len": guide_len, "seed": seed, "blas_threads": threads, "chunk": chunk,
             "csv_sha256": hashlib.sha256(data).hexdigest(), "rows": data.count(b"\r\n") - 1,
             "time_txt_records": time_txt.count("Total runtime of the program is ")}
 

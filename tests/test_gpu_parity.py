@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 ALL_CASES = ["sample", "sample_t6", "multi3", "multi3_l18", "multi3_l23", "clean3", "clean3_trailing_nl",
              "edge_clean", "edge_fmt", "single_candidate", "ws_header", "dup_keys", "empty_records",
-             "mid50k", "mid50k_t5"]
+             "mid50k", "mid50k_t5", "mid50k_c1000", "mid50k_c1557", "multi3_c20", "sample_c5000_t4"]
 
 
 @pytest.fixture(scope="module")
@@ -34,7 +34,7 @@ def test_cli_csv_is_byte_identical_to_reference(name, manifest, eng, tmp_path, c
     lines = []
     pipeline.run_cas9(fixture_path(case["fasta"]), fixture_path("sample_genome.gff"), str(out),
                       case["guide_len"], False, case["blas_threads"], str(tmp_path / "time.txt"),
-                      out=lambda *a: lines.append(" ".join(a)))
+                      out=lambda *a: lines.append(" ".join(a)), chunk_rows=case.get("chunk"))
     got = out.read_bytes().decode()
     assert got == golden_csv(name)
     want_stdout = open(os.path.join(os.path.dirname(fixture_path("x")), "..", "cases", name + ".stdout")).read()
@@ -505,3 +505,37 @@ def test_reference_callables_on_the_device(eng):
     conv = np.array([np.frombuffer(b"ACGT" * 7 + b"AC", np.uint8), np.zeros(30, np.uint8)])
     assert ph.dtype == np.float64
     assert np.array_equal(CROPSR.rs1_score(ph), oracle.score_model(conv, threads=1))
+
+
+@pytest.mark.parametrize("name", ["big1", "big2"])
+def test_cli_over_one_million_candidates_equals_reference_digest(name, eng, tmp_path):
+    """SURVEY 8a row 10 end to end: more than 1,000,000 candidates through the reference's chunk
+    plan (misplaced last slice, ids[start-k-1] with start > 0; big2: cumulative re-emission across
+    the 1e6 boundary and 8-thread BLAS row classes of a 1e6-row matmul).  The golden is the sha256
+    of the CSV the UNMODIFIED reference wrote for the same seeded FASTA
+    (tests/golden/make_big_golden.py -> cases/big_manifest.json)."""
+    import hashlib, importlib.util, json
+    from cropsr_b200 import pipeline
+    here = os.path.dirname(fixture_path("x"))
+    spec = importlib.util.spec_from_file_location("make_big_golden", os.path.join(here, "..", "make_big_golden.py"))
+    mbg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mbg)
+    with open(os.path.join(here, "..", "cases", "big_manifest.json")) as f:
+        case = json.load(f)["cases"][name]
+    text = mbg.big_fasta(name)
+    assert hashlib.sha256(text.encode()).hexdigest() == case["fasta_sha256"]
+    fa = tmp_path / (name + ".fa")
+    with open(fa, "w", newline="") as f:
+        f.write(text)
+    out = tmp_path / "out.csv"
+    np.random.seed(case["seed"])
+    stats = pipeline.run_cas9(str(fa), fixture_path("sample_genome.gff"), str(out), 20, False, case["blas_threads"],
+                              str(tmp_path / "time.txt"), out=lambda *a: None)
+    data = out.read_bytes()
+    assert data.count(b"\r\n") - 1 == case["rows"] == stats["rows"]
+    if hashlib.sha256(data).hexdigest() != case["csv_sha256"]:
+        # say which layer differs before failing: structure, then scores to 12 digits, then raw bytes
+        text = data.decode()
+        assert normalised_digest(text) == case["digest_no_id_no_score"], "rows / sequences / coordinates differ"
+        assert normalised_digest(text, "%.12g") == case["digest_no_id_score_12g"], "scores differ beyond 1e-12"
+        raise AssertionError("ids or last score digits differ from the reference's CSV")

@@ -28,11 +28,14 @@ def test_manifest_matches_files(manifest):
 @pytest.mark.parametrize("name", [
     "sample", "sample_t6", "multi3", "multi3_l18", "multi3_l23", "clean3", "clean3_trailing_nl",
     "edge_clean", "edge_fmt", "single_candidate", "ws_header", "dup_keys", "empty_records",
-    "mid50k", "mid50k_t5"])
+    "mid50k", "mid50k_t5", "mid50k_c1000", "mid50k_c1557", "multi3_c20", "sample_c5000_t4"])
 def test_oracle_reproduces_reference_csv(name, manifest):
+    """The *_c<chunk> cases are the reference run with its 1000000-row chunk literal shrunk
+    (tests/golden/make_golden.py): the chunk plan of CROPSR.py:451-472 on small inputs."""
     case = manifest["cases"][name]
     np.random.seed(case["seed"])
-    got = oracle.run_to_string(fixture_text(case["fasta"]), case["guide_len"], "model", case["blas_threads"])
+    got = oracle.run_to_string(fixture_text(case["fasta"]), case["guide_len"], "model", case["blas_threads"],
+                               chunk=case.get("chunk"))
     assert got == golden_csv(name)
 
 
@@ -124,3 +127,20 @@ def test_every_scored_window_carries_the_pam_as_cc():
                     assert long_[2:4] == "CC", (name, cand)
                     seen += 1
     assert seen > 20000
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("name", ["big1", "big2"])
+def test_oracle_reproduces_reference_over_one_million_candidates(name):
+    """The literal port against the digests of the unmodified reference's >1e6-candidate runs
+    (tests/golden/make_big_golden.py); minutes of Python, so CROPSR_SLOW=1 only."""
+    import importlib.util, json
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_big_golden", os.path.join(here, "make_big_golden.py"))
+    mbg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mbg)
+    with open(os.path.join(here, "cases", "big_manifest.json")) as f:
+        case = json.load(f)["cases"][name]
+    np.random.seed(case["seed"])
+    got = oracle.run_to_string(mbg.big_fasta(name), 20, "model", case["blas_threads"])
+    assert hashlib.sha256(got.encode()).hexdigest() == case["csv_sha256"]
