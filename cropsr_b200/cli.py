@@ -24,6 +24,10 @@ def build_parser():
                    help="prints visual indicators for each iteration")
     # additions (defaults reproduce the reference)
     p.add_argument("--device", type=int, default=0, help="CUDA device ordinal, default = 0")
+    p.add_argument("--devices", metavar="", default=None,
+                   help="several CUDA devices, e.g. 0-7 or 0,2,4: the genome is cut into one contiguous shard per "
+                        "device (one process each), candidate counts are exchanged by one NCCL all-gather and the "
+                        "CSV is written in the same order as on one device")
     p.add_argument("--side-output", metavar="", default=None,
                    help="also write a tab-separated table of opt-in per-candidate side outputs (GC, poly-T, "
                         "homopolymer, +-L flank window, GFF feature under the cut site); the CSV is unaffected")
@@ -53,6 +57,17 @@ def banner(args):
         """
 
 
+def parse_devices(text):
+    """'0-3' / '0,2,5' / '1' -> [ordinals]"""
+    out = []
+    for part in text.split(","):
+        a, _, b = part.strip().partition("-")
+        out += list(range(int(a), int(b or a) + 1))
+    if not out or len(set(out)) != len(out):
+        raise ValueError(f"bad --devices value {text!r}")
+    return out
+
+
 def main(argv=None):
     args = build_parser().parse_args(argv)
     if not args.cas9:
@@ -60,7 +75,8 @@ def main(argv=None):
     if args.verbose:
         print(banner(args))
     from . import engine, pipeline
-    engine.init(args.device)
+    devices = parse_devices(args.devices) if args.devices else [args.device]
+    engine.init(devices[0])
     pipeline.run_cas9(args.f, args.g, args.o, args.l, args.verbose, args.blas_threads,
-                      side_output=args.side_output, flank=args.L, annotation_info=args.p)
+                      side_output=args.side_output, flank=args.L, annotation_info=args.p, devices=devices)
     return 0

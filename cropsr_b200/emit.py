@@ -151,35 +151,87 @@ def guide_strings(token, t, minus, guide_len):
 
 class CandidateTable:
     """Unique candidates of all tokens seen so far, in reference order
-    (per token: '+' by ascending t, then '-' by ascending t)."""
+    (per token: '+' by ascending t, then '-' by ascending t).  The columns live in arrays
+    that are allocated once when the total is known (`capacity`: the scan has counted every
+    token before the first row is written) and otherwise grow geometrically -- appending a token
+    never copies the rows of the tokens before it (20,000 scaffolds: no O(k^2) concatenation)."""
 
-    def __init__(self, guide_len):
+    _COLS = (("tok", np.uint32), ("seg", np.uint32), ("minus", np.bool_), ("t", np.uint32), ("x", np.float64))
+
+    def __init__(self, guide_len, capacity=0):
         self.guide_len = guide_len
         self.tokens = []      # bytes per token
         self.chroms = []      # CSV chromosome string per token (key[1:])
-        self.tok = np.empty(0, np.uint32)
-        self.seg = np.empty(0, np.uint32)
-        self.minus = np.empty(0, np.bool_)
-        self.t = np.empty(0, np.uint32)
-        self.x = np.empty(0, np.float64)
+        self.n = 0
+        self._cap = int(capacity)
+        self._store = {name: np.empty(self._cap, dt) for name, dt in self._COLS}
 
     def __len__(self):
-        return len(self.t)
+        return self.n
+
+    tok = property(lambda self: self._store["tok"][:self.n])
+    seg = property(lambda self: self._store["seg"][:self.n])
+    minus = property(lambda self: self._store["minus"][:self.n])
+    t = property(lambda self: self._store["t"][:self.n])
+    x = property(lambda self: self._store["x"][:self.n])
+
+    @property
+    def token_len(self):
+        """int64 length of every token"""
+        n_tok, _, tok_len = self.formatter_arrays()[:3]
+        return tok_len[:n_tok].astype(np.int64)
+
+    def formatter_arrays(self):
+        """(n_tokens, token pointers, token lengths, chromosome pointers, chromosome lengths, longest
+        chromosome) for crp_format_rows: per-token arrays that only ever get entries appended."""
+        f = self.__dict__.setdefault("_fmt", {"n": 0, "keep": [], "tok_ptr": np.zeros(16, np.uint64),
+                                              "tok_len": np.zeros(16, np.uint64), "chrom_ptr": np.zeros(16, np.uint64),
+                                              "chrom_len": np.zeros(16, np.uint32), "chrom_max": 0})
+        n_tok = len(self.tokens)
+        if n_tok > len(f["tok_ptr"]):
+            for name in ("tok_ptr", "tok_len", "chrom_ptr", "chrom_len"):
+                grown = np.zeros(max(n_tok, 2 * len(f[name])), f[name].dtype)
+                grown[:f["n"]] = f[name][:f["n"]]
+                f[name] = grown
+        for k in range(f["n"], n_tok):
+            view = np.frombuffer(self.tokens[k], dtype=np.uint8)
+            chrom = np.frombuffer(self.chroms[k].encode("utf-8") + b"\0", dtype=np.uint8)
+            f["keep"].append((view, chrom))
+            f["tok_ptr"][k] = view.ctypes.data if len(view) else 0
+            f["tok_len"][k] = len(view)
+            f["chrom_ptr"][k] = chrom.ctypes.data
+            f["chrom_len"][k] = len(chrom) - 1
+            f["chrom_max"] = max(f["chrom_max"], len(chrom) - 1)
+        f["n"] = n_tok
+        return n_tok, f["tok_ptr"], f["tok_len"], f["chrom_ptr"], f["chrom_len"], f["chrom_max"]
+
+    def _reserve(self, n):
+        if n <= self._cap:
+            return
+        cap = max(n, 2 * self._cap, 1024)
+        for name, dt in self._COLS:
+            grown = np.empty(cap, dt)
+            grown[:self.n] = self._store[name][:self.n]
+            self._store[name] = grown
+        self._cap = cap
 
     def append_token(self, key, token_bytes, seg_index, t_plus, x_plus, t_minus, x_minus):
         k = len(self.tokens)
         self.tokens.append(token_bytes)
         self.chroms.append(key[1:])
         n_p, n_m = len(t_plus), len(t_minus)
-        n = n_p + n_m
-        self.tok = np.concatenate((self.tok, np.full(n, k, np.uint32)))
-        self.seg = np.concatenate((self.seg, np.full(n, seg_index, np.uint32)))
-        self.minus = np.concatenate((self.minus, np.zeros(n_p, np.bool_), np.ones(n_m, np.bool_)))
-        self.t = np.concatenate((self.t, t_plus, t_minus)).astype(np.uint32)
-        nan = np.full(0, np.nan)
-        xp = x_plus if x_plus is not None else np.full(n_p, np.nan)
-        xm = x_minus if x_minus is not None else np.full(n_m, np.nan)
-        self.x = np.concatenate((self.x, xp, xm, nan))
+        lo, mid, hi = self.n, self.n + n_p, self.n + n_p + n_m
+        self._reserve(hi)
+        st = self._store
+        st["tok"][lo:hi] = k
+        st["seg"][lo:hi] = seg_index
+        st["minus"][lo:mid] = False
+        st["minus"][mid:hi] = True
+        st["t"][lo:mid] = t_plus
+        st["t"][mid:hi] = t_minus
+        st["x"][lo:mid] = x_plus if x_plus is not None else np.nan
+        st["x"][mid:hi] = x_minus if x_minus is not None else np.nan
+        self.n = hi
 
 
 def long_length(table, idx):
@@ -187,7 +239,7 @@ def long_length(table, idx):
     arithmetic)."""
     l = table.guide_len
     t = table.t[idx].astype(np.int64)
-    L = np.array([len(tok) for tok in table.tokens], dtype=np.int64)[table.tok[idx]]
+    L = table.token_len[table.tok[idx]]
     minus = table.minus[idx]
     # '+': [t - l - 5, t + 5), '-': [t - 2, t + l + 8), clipped to the token
     lo = t - np.where(minus, 2, l + 5)
@@ -221,7 +273,7 @@ def slice_scores(table, genome, start, count, blas_threads=1):
         cand = idx[rows]
         t = table.t[cand].astype(np.int64)
         if table.guide_len != 20:
-            L = np.array([len(tok) for tok in table.tokens], dtype=np.int64)[table.tok[cand]]
+            L = table.token_len[table.tok[cand]]
             t = np.where(table.minus[cand], t, L - 5)
         strand = np.where(table.minus[cand], b"-", b"+").astype("S1")
         cls = np.array([fix[int(i)] for i in rows], dtype=np.uint8)
@@ -278,18 +330,12 @@ def format_rows(table, ids, scores, scored, start, count, n_threads=0, buffer=0)
     minus = np.ascontiguousarray(table.minus[start:start + count], dtype=np.uint8)
     ok = np.ascontiguousarray(scored, dtype=np.uint8)
     sc = np.ascontiguousarray(scores, dtype=np.float64)
-    n_tok = len(table.tokens)
-    views = [np.frombuffer(b, dtype=np.uint8) for b in table.tokens]
-    tok_ptr = (C.c_void_p * n_tok)(*[v.ctypes.data if len(v) else None for v in views])
-    tok_len = np.array([len(b) for b in table.tokens], dtype=np.uint64)
-    chroms = [c.encode("utf-8") for c in table.chroms]
-    chrom_ptr = (C.c_char_p * n_tok)(*chroms)
-    chrom_len = np.array([len(c) for c in chroms], dtype=np.uint32)
+    n_tok, tok_ptr, tok_len, chrom_ptr, chrom_len, chrom_max = table.formatter_arrays()
     # One call formats at most _FORMAT_BUDGET bytes worth of rows (the library's scratch regions are sized for the
     # worst row); the output lands in a buffer that is kept between calls -- a fresh 100+ MB buffer
     # per 1M-row slice costs more in page faults than the formatting itself.  The memoryview that is
     # returned is only valid until the next call with the same `buffer` (0 or 1).
-    row_bound = 256 + 4 * table.guide_len + 2 * int(chrom_len.max(initial=0))
+    row_bound = 256 + 4 * table.guide_len + 2 * chrom_max
     step = max(4096, _FORMAT_BUDGET // row_bound)
     pieces = []
     for lo in range(0, count, step):
@@ -302,7 +348,8 @@ def format_rows(table, ids, scores, scored, start, count, n_threads=0, buffer=0)
             need = C.c_uint64(0)
             rc = lib.crp_format_rows(n, id_bytes.ctypes.data, id_index[lo:].ctypes.data, tok[lo:].ctypes.data,
                                      t[lo:].ctypes.data, minus[lo:].ctypes.data, ok[lo:].ctypes.data, sc[lo:].ctypes.data,
-                                     n_tok, tok_ptr, tok_len.ctypes.data, chrom_ptr, chrom_len.ctypes.data,
+                                     n_tok, tok_ptr.ctypes.data, tok_len.ctypes.data, chrom_ptr.ctypes.data,
+                                     chrom_len.ctypes.data,
                                      int(table.guide_len), int(n_threads), out.ctypes.data, len(out), C.byref(need))
             if rc == -5:
                 cap = need.value

@@ -76,6 +76,56 @@ def launch_count():
     return n.value
 
 
+def device_synchronize():
+    check(lib.crp_device_synchronize())
+
+
+def flush_l2():
+    """Evict L2 (benchmarks, between timed scans)."""
+    check(lib.crp_flush_l2())
+
+
+# ---- one process per GPU: the NCCL communicator of the count all-gather (include/cropsr_b200.h) ----
+def comm_unique_id():
+    buf = (C.c_uint8 * N.COMM_ID_BYTES)()
+    check(lib.crp_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def comm_init(rank, world, unique_id):
+    if _device is None:
+        raise CropsrError(-3, "engine.init(device) comes first")
+    assert len(unique_id) == N.COMM_ID_BYTES
+    buf = (C.c_uint8 * N.COMM_ID_BYTES).from_buffer_copy(unique_id)
+    check(lib.crp_comm_init(int(rank), int(world), buf))
+
+
+def comm_info():
+    r, w = C.c_int(0), C.c_int(1)
+    check(lib.crp_comm_info(C.byref(r), C.byref(w)))
+    return r.value, w.value
+
+
+def comm_barrier():
+    check(lib.crp_comm_barrier())
+
+
+def comm_max(values):
+    v = np.ascontiguousarray(values, dtype=np.float64).copy()
+    check(lib.crp_comm_max_f64(v.ctypes.data, v.size))
+    return v
+
+
+def comm_sum(values):
+    v = np.ascontiguousarray(values, dtype=np.float64).copy()
+    check(lib.crp_comm_sum_f64(v.ctypes.data, v.size))
+    return v
+
+
+def comm_shutdown():
+    check(lib.crp_comm_shutdown())
+
+
 def logistic(x):
     """1 / (1 + np.exp(x)) on the device with numpy's own digits (CROPSR.py:313; csrc/npexp.cuh)."""
     x = np.ascontiguousarray(x, dtype=np.float64)
@@ -90,6 +140,16 @@ def rs1_score(rows, cls):
     cls = np.ascontiguousarray(cls, dtype=np.uint8)
     out = np.empty(len(rows), dtype=np.float64)
     check(lib.crp_rs1_score(len(rows), rows.ctypes.data, cls.ctypes.data, out.ctypes.data))
+    return out
+
+
+def rs1_preactivation(rows, cls):
+    """crp_rs1_preactivation: like rs1_score without the logistic (x of every row)."""
+    rows = np.ascontiguousarray(rows, dtype=np.uint8)
+    cls = np.ascontiguousarray(cls, dtype=np.uint8)
+    out = np.empty(len(rows), dtype=np.float64)
+    if len(rows):
+        check(lib.crp_rs1_preactivation(len(rows), rows.ctypes.data, cls.ctypes.data, out.ctypes.data))
     return out
 
 
@@ -136,15 +196,16 @@ class PinnedBuffer:
 class Arena:
     """Pinned host arrays for the candidate rows of both strands (crp_scan_segments)."""
 
-    def __init__(self, capacity, scored=True):
+    def __init__(self, capacity, scored=True, want=("pos", "packed", "x")):
         self.capacity = int(capacity)
         self.scored = scored
+        self.want = tuple(want)
         self._bufs = []
         self.arrays = {}
         for strand in "+-":
             row = {}
             for name, dt in (("pos", np.uint32), ("packed", np.uint64), ("x", np.float64)):
-                if name != "pos" and not scored:
+                if (name != "pos" and not scored) or name not in self.want:
                     row[name] = None
                     continue
                 b = PinnedBuffer(self.capacity * np.dtype(dt).itemsize)
@@ -159,11 +220,13 @@ class Arena:
         self._bufs = []
 
 
-def scan_segments(segments, guide_len=20, flags=N.CRP_SCAN_DEFAULT, arena=None):
+def scan_segments(segments, guide_len=20, flags=N.CRP_SCAN_DEFAULT, arena=None, want=("pos", "packed", "x")):
     """Pipelined whole call: `segments` = [(token_id, token uint8 array (pinned for full speed),
     begin, end)].  Returns (arena, n_plus[], n_minus[], device_ms); rows of a strand are in
     arena.arrays[strand][name][:sum(counts)] in segment order.  If the arena is too small a
-    larger one is allocated and the call repeated."""
+    larger one is allocated and the call repeated.  `want`: the columns that come back (a caller
+    that formats its rows from the tokens -- the CSV writer -- leaves "packed" out: 12 instead of
+    20 bytes per candidate over the link)."""
     if _device is None:
         init(0)
     scored = int(guide_len) == 20 and not (flags & N.CRP_SCAN_NO_SCORE)
@@ -179,7 +242,7 @@ def scan_segments(segments, guide_len=20, flags=N.CRP_SCAN_DEFAULT, arena=None):
     ms = C.c_float(0)
     if arena is None:
         total = sum((len(k) if b is None else b) - a for k, (_, _, a, b) in zip(keep, segments))
-        arena = Arena(total // 12 + 4096, scored)
+        arena = Arena(total // 12 + 4096, scored, want)
     for attempt in range(2):
         ptr = lambda a: a.ctypes.data if a is not None else None
         p, m = arena.arrays["+"], arena.arrays["-"]
@@ -189,7 +252,7 @@ def scan_segments(segments, guide_len=20, flags=N.CRP_SCAN_DEFAULT, arena=None):
                                    n_plus.ctypes.data, n_minus.ctypes.data, C.byref(ms))
         if rc == -5 and attempt == 0:          # CRP_ERR_RANGE: arena too small, counts are valid
             arena.free()
-            arena = Arena(int(max(n_plus.sum(), n_minus.sum())) + 1024, scored)
+            arena = Arena(int(max(n_plus.sum(), n_minus.sum())) + 1024, scored, want)
             continue
         check(rc)
         break
@@ -265,6 +328,15 @@ class Genome:
         check(lib.crp_scan_score(self._h, int(guide_len), int(flags), C.byref(res)))
         return ScanResult(self, res, guide_len, flags)
 
+    def scan_sharded(self, slots, guide_len=20, flags=N.CRP_SCAN_DEFAULT):
+        """This rank's shard of a genome spread over the communicator: scan + NCCL all-gather of the
+        per-segment counts (`slots` per rank and strand, the same on every rank).  Collective."""
+        res = C.c_void_p()
+        check(lib.crp_scan_score_sharded(self._h, int(guide_len), int(flags), int(slots), C.byref(res)))
+        r = ScanResult(self, res, guide_len, flags)
+        r.slots = int(slots)
+        return r
+
     def rescore(self, segment, t, strand, cls):
         """x of the given candidates re-summed in BLAS class cls (see blas_order)."""
         segment = np.ascontiguousarray(segment, dtype=np.uint32)
@@ -315,6 +387,19 @@ class ScanResult:
         v = C.c_float(0)
         check(lib.crp_result_timing(self._h, C.byref(v)))
         return v.value
+
+    def timing_detail(self):
+        """dict(kernel_ms, total_ms (kernel + all-gather for a sharded scan), launches)"""
+        a, b, n = C.c_float(0), C.c_float(0), C.c_uint32(0)
+        check(lib.crp_result_timing_detail(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return {"kernel_ms": a.value, "total_ms": b.value, "launches": n.value}
+
+    def gathered_counts(self):
+        """uint64[world, 2, slots]: every rank's per-segment counts ('+' then '-') of a sharded scan"""
+        _, world = comm_info()
+        out = np.empty((world, 2, self.slots), dtype=np.uint64)
+        check(lib.crp_result_gathered_counts(self._h, out.ctypes.data))
+        return out
 
     def device_counts_ptr(self):
         p = C.c_void_p()

@@ -375,7 +375,9 @@ def test_device_fasta_ingest_equals_text_ingest(manifest, eng, tmp_path):
         path.write_bytes(data)
         fast = pipeline.scan_fasta_file(str(path), 20)
         assert fast is not None, k
-        keys, genome, result, token_bytes = fast
+        keys, scan = fast
+        (genome, result, _, _), token_bytes = scan.parts[0], scan.token_bytes
+        assert len(scan.parts) == 1
         tokens = ingest.fasta_text_to_tokens(data.decode())
         g2, r2, tb2 = pipeline.scan_tokens(tokens, 20)
         try:
@@ -539,3 +541,60 @@ def test_cli_over_one_million_candidates_equals_reference_digest(name, eng, tmp_
         assert normalised_digest(text) == case["digest_no_id_no_score"], "rows / sequences / coordinates differ"
         assert normalised_digest(text, "%.12g") == case["digest_no_id_score_12g"], "scores differ beyond 1e-12"
         raise AssertionError("ids or last score digits differ from the reference's CSV")
+
+
+def test_several_genome_handles_give_the_same_csv(manifest, eng, tmp_path):
+    """Genomes beyond the 32-bit limits of one handle (the 10 Gbp config) are spread
+    over several handles: with the per-handle limit shrunk, tokens of multi3 / sample land in
+    different handles, rows come from the host rescorer, and the CSV stays byte-identical --
+    through both ingests."""
+    from cropsr_b200 import pipeline
+    for name, limit in (("multi3", 1), ("multi3_c20", 3000), ("mid50k_t5", 100), ("sample_c5000_t4", 1000)):
+        case = manifest["cases"][name]
+        for dev in (True, False):
+            out = tmp_path / f"{name}_{dev}.csv"
+            np.random.seed(case["seed"])
+            pipeline.run_cas9(fixture_path(case["fasta"]), fixture_path("sample_genome.gff"), str(out), case["guide_len"],
+                              False, case["blas_threads"], str(tmp_path / "time.txt"), out=lambda *a: None,
+                              device_ingest=dev, chunk_rows=case.get("chunk"), handle_limit=limit)
+            assert out.read_bytes().decode() == golden_csv(name), (name, dev)
+
+
+def test_host_rescorer_equals_crp_rescore(eng):
+    """HostRescorer (30 scored bytes from the host token through crp_rs1_preactivation) against
+    crp_rescore (packed records) for every class pair, both strands, tile-edge candidates included."""
+    from cropsr_b200 import ingest, pipeline
+    tokens = ingest.fasta_text_to_tokens(synthetic_fasta(52, [40000, 17000], gc=0.5, lower_frac=0.2, n_frac=0.003))
+    genome, result, token_bytes = pipeline.scan_tokens(tokens, 20)
+    host = pipeline.HostRescorer(token_bytes)
+    try:
+        for seg in range(2):
+            for strand in "+-":
+                pos = result.fetch_segment(seg, strand, want=("pos",))["pos"][:600]
+                for cls in (0x00, 0x01, 0x10, 0x11, 0x02, 0x20, 0x22, 0x12, 0x21):
+                    c = np.full(len(pos), cls, np.uint8)
+                    st = np.full(len(pos), strand.encode(), "S1")
+                    sg = np.full(len(pos), seg, np.uint32)
+                    assert np.array_equal(genome.rescore(sg, pos, st, c), host.rescore(sg, pos, st, c)), (seg, strand, cls)
+    finally:
+        result.free()
+        genome.free()
+
+
+@pytest.mark.parametrize("n_dev", [2, 3, 8])
+def test_multi_gpu_cli_writes_the_reference_csv(n_dev, manifest, eng, tmp_path):
+    """CROPSR.py --devices 0-(n-1): one process per GPU, contiguous shards, the NCCL all-gather of the
+    per-segment counts inside the library, rows placed in reference order -- the CSV must be the
+    unmodified reference's, byte for byte.  Needs n GPUs on the box (gpurun --gpus n)."""
+    from cropsr_b200 import pipeline
+    if eng.device_count() < n_dev:
+        pytest.skip(f"needs {n_dev} GPUs")
+    for name in ("multi3", "sample", "mid50k_t5", "multi3_c20", "edge_fmt", "empty_records", "single_candidate"):
+        case = manifest["cases"][name]
+        out = tmp_path / f"{name}.csv"
+        np.random.seed(case["seed"])
+        stats = pipeline.run_cas9(fixture_path(case["fasta"]), fixture_path("sample_genome.gff"), str(out), case["guide_len"],
+                                  False, case["blas_threads"], str(tmp_path / "time.txt"), out=lambda *a: None,
+                                  chunk_rows=case.get("chunk"), devices=list(range(n_dev)))
+        assert out.read_bytes().decode() == golden_csv(name), name
+        assert len(stats["ranks"]) == n_dev

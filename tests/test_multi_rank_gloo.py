@@ -81,3 +81,35 @@ def test_two_ranks_place_candidates_in_reference_order(tmp_path, world):
     got = got[np.argsort(got[:, 0])]
     assert np.array_equal(got[:, 0], np.arange(len(ref)))          # every global row exactly once
     assert np.array_equal(got[:, 1:], ref)                          # and in the reference's order
+
+
+def _rdv_main(rank, world, port, out_dir):
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    from cropsr_b200 import launch
+    rdv = launch.Rendezvous(rank, world, "127.0.0.1", port)
+    got = rdv.all_gather({"rank": rank, "payload": bytes([rank]) * (1 << 18)})
+    assert [g["rank"] for g in got] == list(range(world))
+    assert all(g["payload"] == bytes([r]) * (1 << 18) for r, g in enumerate(got))
+    uid = rdv.broadcast(b"id-from-rank-0" if rank == 0 else None)
+    assert uid == b"id-from-rank-0"
+    for _ in range(20):
+        rdv.barrier()
+    rdv.close()
+    with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
+        f.write("ok")
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_tcp_rendezvous_of_the_launcher(tmp_path, world):
+    """cropsr_b200/launch.py: the channel that hands NCCL's unique id round (no PyTorch)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_rdv_main, args=(r, world, port, str(tmp_path))) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(60)
+    assert all(p.exitcode == 0 for p in procs)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
