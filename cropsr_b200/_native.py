@@ -113,6 +113,8 @@ SIGNATURES = {
     "crp_comm_max_f64": (C.c_int, [C.c_void_p, C.c_uint32]),
     "crp_comm_sum_f64": (C.c_int, [C.c_void_p, C.c_uint32]),
     "crp_comm_shutdown": (C.c_int, []),
+    "crp_comm_allgather_u64": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "crp_link_probe": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint32, _f32p]),
     "crp_scan_score_sharded": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, _vpp]),
     "crp_result_gathered_counts": (C.c_int, [C.c_void_p, C.c_void_p]),
     "crp_result_timing_detail": (C.c_int, [C.c_void_p, _f32p, _f32p, _u32p]),

@@ -442,6 +442,73 @@ int crp_comm_sum_f64(double *v, uint32_t n) {
     return 0;
 }
 
+/* all-gather of n host words per rank: out[rank * n + i] (host in, host out; bootstrap-sized payloads) */
+int crp_comm_allgather_u64(const uint64_t *in, uint32_t n, uint64_t *out) {
+    if (int rc = need_ctx()) return rc;
+    if (n && (!in || !out)) return fail(CRP_ERR_ARG, "NULL argument");
+    if (n == 0) return 0;
+    if (!g_comm.comm) {
+        memcpy(out, in, n * sizeof(uint64_t));
+        return 0;
+    }
+    unsigned long long *d = nullptr;
+    const size_t w = (size_t)g_comm.world;
+    CUDA_TRY(dev_alloc(&d, (w + 1) * n * sizeof(uint64_t), g_ctx.stream));
+    CUDA_TRY(cudaMemcpyAsync(d, in, n * sizeof(uint64_t), cudaMemcpyHostToDevice, g_ctx.stream));
+    if (int rc = comm_allgather_u64(d, d + n, n, g_ctx.stream)) {
+        dev_free(d, g_ctx.stream);
+        return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(out, d + n, w * n * sizeof(uint64_t), cudaMemcpyDeviceToHost, g_ctx.stream));
+    CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+    dev_free(d, g_ctx.stream);
+    return 0;
+}
+
+/* Link probe: h2d_bytes host->device and d2h_bytes device->host, both pinned, both directions at
+ * once on two streams, `reps` times; *ms = mean wall time of one round.  What a step that moves
+ * exactly these bytes could reach if the kernels were free. */
+int crp_link_probe(uint64_t h2d_bytes, uint64_t d2h_bytes, uint32_t reps, float *ms) {
+    if (int rc = need_ctx()) return rc;
+    if (!ms || !reps) return fail(CRP_ERR_ARG, "bad argument");
+    void *h_in = nullptr, *h_out = nullptr;
+    unsigned char *d_in = nullptr, *d_out = nullptr;
+    cudaStream_t s2 = nullptr;
+    int rc = 0;
+    do {
+        if (cudaHostAlloc(&h_in, h2d_bytes + 16, cudaHostAllocDefault) != cudaSuccess ||
+            cudaHostAlloc(&h_out, d2h_bytes + 16, cudaHostAllocDefault) != cudaSuccess) {
+            rc = fail(CRP_ERR_NOMEM, "cudaHostAlloc of the probe buffers failed");
+            break;
+        }
+        memset(h_in, 1, h2d_bytes + 16);
+        memset(h_out, 1, d2h_bytes + 16);
+        if (dev_alloc(&d_in, h2d_bytes + 16, g_ctx.stream) != cudaSuccess || dev_alloc(&d_out, d2h_bytes + 16, g_ctx.stream) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking) != cudaSuccess) {
+            rc = fail(CRP_ERR_NOMEM, "device buffers of the link probe failed");
+            break;
+        }
+        cudaStreamSynchronize(g_ctx.stream);
+        double total = 0.0;
+        for (uint32_t i = 0; i <= reps; ++i) {            // round 0 warms up
+            const auto t0 = std::chrono::steady_clock::now();
+            cudaMemcpyAsync(d_in, h_in, h2d_bytes, cudaMemcpyHostToDevice, g_ctx.stream);
+            cudaMemcpyAsync(h_out, d_out, d2h_bytes, cudaMemcpyDeviceToHost, s2);
+            cudaStreamSynchronize(g_ctx.stream);
+            cudaStreamSynchronize(s2);
+            if (i) total += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
+        if (cudaGetLastError() != cudaSuccess) rc = fail(CRP_ERR_CUDA, "link probe copies failed");
+        *ms = (float)(total / reps);
+    } while (0);
+    if (s2) cudaStreamDestroy(s2);
+    dev_free(d_in, g_ctx.stream);
+    dev_free(d_out, g_ctx.stream);
+    if (h_in) cudaFreeHost(h_in);
+    if (h_out) cudaFreeHost(h_out);
+    return rc;
+}
+
 int crp_comm_shutdown(void) {
     if (g_comm.comm) {
         cudaDeviceSynchronize();

@@ -122,6 +122,22 @@ def comm_sum(values):
     return v
 
 
+def comm_allgather(values):
+    """uint64[n] per rank -> uint64[world, n] on every rank (host in, host out)"""
+    v = np.ascontiguousarray(values, dtype=np.uint64)
+    _, world = comm_info()
+    out = np.empty((world, v.size), dtype=np.uint64)
+    check(lib.crp_comm_allgather_u64(v.ctypes.data, v.size, out.ctypes.data))
+    return out
+
+
+def link_probe(h2d_bytes, d2h_bytes, reps=5):
+    """ms of one round of concurrent pinned H2D + D2H copies of these sizes (what the link allows)"""
+    ms = C.c_float(0)
+    check(lib.crp_link_probe(int(h2d_bytes), int(d2h_bytes), int(reps), C.byref(ms)))
+    return ms.value
+
+
 def comm_shutdown():
     check(lib.crp_comm_shutdown())
 

@@ -102,7 +102,12 @@ int crp_comm_barrier(void);
 /* Element-wise max / sum of n host doubles over all ranks, in place (timings, totals). */
 int crp_comm_max_f64(double *v, uint32_t n);
 int crp_comm_sum_f64(double *v, uint32_t n);
+/* All-gather of n host words per rank, host in / host out: out[rank * n + i]. */
+int crp_comm_allgather_u64(const uint64_t *in, uint32_t n, uint64_t *out);
 int crp_comm_shutdown(void);
+/* Link probe (benchmarks): h2d_bytes up and d2h_bytes down, pinned, both directions at once,
+ * `reps` rounds; *ms = mean wall time of a round. */
+int crp_link_probe(uint64_t h2d_bytes, uint64_t d2h_bytes, uint32_t reps, float *ms);
 
 /* Pinned host memory for staging (FASTA bytes in, candidate arrays out). */
 int crp_host_alloc(void **ptr, uint64_t bytes);

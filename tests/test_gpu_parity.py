@@ -598,3 +598,57 @@ def test_multi_gpu_cli_writes_the_reference_csv(n_dev, manifest, eng, tmp_path):
                                   chunk_rows=case.get("chunk"), devices=list(range(n_dev)))
         assert out.read_bytes().decode() == golden_csv(name), name
         assert len(stats["ranks"]) == n_dev
+
+
+def _gpu_table_digest(eng, workload, limit=None):
+    """digest of the device's unique-candidate table of a whole synthetic config (oracle/vector_oracle.TableDigest)"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools"))
+    import vector_oracle as vo
+    import workloads as W
+    from cropsr_b200 import pipeline
+    lengths = W.token_lengths(workload)
+    d = vo.TableDigest()
+    for first, cnt in pipeline._groups(lengths, limit):
+        g = eng.Genome()
+        for k in range(first, first + cnt):
+            g.add_token(W.token(workload, k))
+        g.commit()
+        r = g.scan(20)
+        plus, minus = r.fetch("+"), r.fetch("-")
+        for s in range(cnt):
+            a, b = int(r.off_plus[s]), int(r.off_plus[s + 1])
+            c, e = int(r.off_minus[s]), int(r.off_minus[s + 1])
+            d.add_token(first + s, (plus["pos"][a:b], plus["packed"][a:b], plus["x"][a:b]),
+                        (minus["pos"][c:e], minus["packed"][c:e], minus["x"][c:e]))
+        r.free()
+        g.free()
+    return d
+
+
+def _table_digests():
+    import json
+    with open(os.path.join(os.path.dirname(fixture_path("x")), "..", "table_digests.json")) as f:
+        return json.load(f)
+
+
+def test_whole_candidate_table_of_configs1_equals_oracle_digest(eng):
+    """configs[1], all 5 chromosomes, 135 Mbp / 7.37 M candidates: pos, packed 30-mer and fp64 x of EVERY
+    candidate against the vectorised oracle's committed digest (tests/golden/make_table_digests.py)."""
+    want = _table_digests()["arabidopsis"]
+    d = _gpu_table_digest(eng, "arabidopsis")
+    assert (d.tokens, d.candidates) == (want["tokens"], want["candidates"])
+    assert d.hexdigest() == want["sha256"]
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("workload", ["sorghum", "maize", "sugarcane"])
+def test_whole_candidate_table_of_larger_configs_equals_oracle_digest(eng, workload):
+    """configs[2..4] (60 % lower-case; repeats + N runs; 20,100 records / 10.5 Gbp over several genome handles):
+    the same whole-table digest.  Minutes of host-side generation and hashing, so CROPSR_SLOW=1."""
+    want = _table_digests().get(workload)
+    if want is None:
+        pytest.skip("digest not generated yet")
+    d = _gpu_table_digest(eng, workload)
+    assert (d.tokens, d.candidates) == (want["tokens"], want["candidates"])
+    assert d.hexdigest() == want["sha256"]

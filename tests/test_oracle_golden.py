@@ -144,3 +144,57 @@ def test_oracle_reproduces_reference_over_one_million_candidates(name):
     np.random.seed(case["seed"])
     got = oracle.run_to_string(mbg.big_fasta(name), 20, "model", case["blas_threads"])
     assert hashlib.sha256(got.encode()).hexdigest() == case["csv_sha256"]
+
+
+def _check_vector_oracle(text, guide_len=20):
+    import vector_oracle as vo
+    tokens = oracle.import_fasta_text(text)
+    for key, tok in tokens.items():
+        arr = np.frombuffer(tok.encode("ascii"), dtype=np.uint8)
+        tab = vo.token_table(arr, guide_len)
+        plus, minus = oracle.pam_hits(tok, guide_len)
+        assert tab["+"][0].tolist() == plus and tab["-"][0].tolist() == minus
+        if guide_len != 20:
+            continue
+        cands = oracle.candidates_for_token(key, tok, guide_len)
+        packed = np.concatenate((tab["+"][1], tab["-"][1]))
+        x = np.concatenate((tab["+"][2], tab["-"][2]))
+        full = np.array([len(c[4]) == 30 for c in cands], dtype=bool)
+        assert np.array_equal((packed & np.uint64(1 << 31)) != 0, ~full)
+        if not full.any():
+            continue
+        seqs = np.array([oracle.scored_bytes(c[4]) for c, f in zip(cands, full) if f])
+        assert np.array_equal(x[full], oracle.preactivation_model(seqs, classes=np.zeros(len(seqs), dtype=np.int8)))
+        code = np.zeros(seqs.shape, dtype=np.uint64)
+        scoring = np.zeros(seqs.shape, dtype=bool)
+        for c, b in enumerate(b"ATCG"):
+            code[seqs == b] = c
+            scoring |= seqs == b
+        sh = np.arange(30, dtype=np.uint64)
+        lo = ((code & np.uint64(1)) << sh).sum(axis=1, dtype=np.uint64)
+        hi = ((code >> np.uint64(1)) << sh).sum(axis=1, dtype=np.uint64)
+        pk = packed[full]
+        assert np.array_equal(pk & np.uint64(0x3FFFFFFF), lo) and np.array_equal((pk >> np.uint64(32)) & np.uint64(0x3FFFFFFF), hi)
+        assert np.array_equal((pk & np.uint64(1 << 62)) != 0, ~scoring.all(axis=1))
+
+
+@pytest.mark.parametrize("fasta", ["multi3.fa", "clean3.fa", "edge_clean.fa", "edge_fmt.fa", "ws_header.fa", "dup_keys.fa",
+                                   "empty_records.fa", "single_candidate.fa", "mid50k.fa", "sample_genome.fa"])
+@pytest.mark.parametrize("guide_len", [20, 18, 23])
+def test_vector_oracle_equals_literal_port(fasta, guide_len):
+    """oracle/vector_oracle.py (numpy, from the spec) against the literal port that the reference's CSVs pin:
+    positions, truncation, scored codes, fp64 x -- so that its digests can stand in at 135 Mbp - 10 Gbp."""
+    _check_vector_oracle(fixture_text(fasta), guide_len)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_vector_oracle_on_random_fastas(seed):
+    rng = np.random.default_rng(2000 + seed)
+    alphabet = np.frombuffer(b"ACGTacgtNRYUZuz'", dtype=np.uint8)
+    p = np.array([20, 20, 20, 20, 3, 3, 3, 3, 1, .3, .3, .2, .2, .1, .1, .1])
+    recs = [(f"r{k}", rng.choice(alphabet, size=int(rng.integers(0, 6000)), p=p / p.sum()).tobytes().decode()) for k in range(4)]
+    if seed % 2:
+        text = "".join(f">{h}\n" + "\n".join(s[i:i + 70] for i in range(0, len(s), 70)) + "\n" for h, s in recs)
+    else:
+        text = "\n".join(f">{h}\n{s}" for h, s in recs if s)
+    _check_vector_oracle(text)
