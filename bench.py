@@ -349,6 +349,25 @@ def main():
         }
         if world > 1:
             line["collective_ms"] = t["ms"] - t["kernel_ms"]
+    # ---- N > 1: the same steps with the other exchange (the default is the fused one when peers map)
+    if world > 1:
+        fused, why = engine.comm_exchange_info()
+        other = "nccl" if fused else None
+        alt = None
+        if other:
+            engine.comm_set_exchange(other)
+            ta = time_scans(engine, sh, min(args.steps, 10), 3)
+            alt_ms = float(engine.comm_max([ta["ms"]])[0])
+            alt = {"ms_per_step": alt_ms, "value": n_bases_total / (alt_ms * 1e-3) / 1e9, "kernel_ms": ta["kernel_ms"],
+                   "collective_ms": ta["ms"] - ta["kernel_ms"]}
+            engine.comm_set_exchange("fused")
+        if rank == 0:
+            line["exchange"] = {"timed": "fused into k_scan_score (peer stores over NVLink, CUDA IPC)" if fused
+                                else "ncclAllGather behind the kernel", "note": why, "nccl_all_gather": alt}
+            line["config"]["collective"] = ("per-segment counts all-gathered INSIDE k_scan_score: peer stores over NVLink after the "
+                                            "count phase, flags, wait at the kernel's end; inside the timed events "
+                                            "(ncclAllGather variant timed beside it: exchange.nccl_all_gather)") if fused else \
+                line["config"]["collective"]
     sh.free()
 
     # ---- N > 1: the single-GPU time of the SAME genome, measured by rank 0 in this run

@@ -109,6 +109,8 @@ SIGNATURES = {
     "crp_comm_unique_id": (C.c_int, [C.c_void_p]),
     "crp_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_void_p]),
     "crp_comm_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "crp_comm_set_exchange": (C.c_int, [C.c_int]),
+    "crp_comm_exchange_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_char_p)]),
     "crp_comm_barrier": (C.c_int, []),
     "crp_comm_max_f64": (C.c_int, [C.c_void_p, C.c_uint32]),
     "crp_comm_sum_f64": (C.c_int, [C.c_void_p, C.c_uint32]),

@@ -102,6 +102,9 @@ struct crp_result {
     uint32_t stride = 0;                       // count slots per strand: n_seg, or the `slots` of a sharded scan
     unsigned long long *d_gather = nullptr;    // sharded scans: [world][2*stride] counts of every rank (NCCL all-gather)
     unsigned long long *h_gather = nullptr;    // pinned copy
+    bool fused = false;                        // counts exchanged by the kernel itself (peer stores), not by NCCL
+    uint32_t epoch = 0;
+    unsigned int *h_xchg_error = nullptr;      // pinned
     float ms_kernel = 0.f;
     int guide_len = 0;
     uint32_t flags = 0;
@@ -249,8 +252,31 @@ struct Comm {
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     unsigned long long *d_scratch = nullptr;   // barrier payload
+    // Fused exchange of the per-segment counts (scan.cuh): every rank owns one buffer
+    //   gather [2 parities][world][2 * kXchgSlots] u64 | flags [2 parities][kMaxPeers] u32 | error u32
+    // that its peers map through CUDA IPC and write with plain stores over NVLink.
+    unsigned char *xchg = nullptr;             // this rank's buffer
+    unsigned char *peer[kMaxPeers] = {};       // every rank's buffer as mapped here (peer[rank] == xchg)
+    bool fused = false;                        // all peers mapped: crp_scan_score_sharded may use the fused exchange
+    int mode = 0;                              // 0 = fused when possible, 1 = always the NCCL all-gather
+    uint32_t epoch = 0;                        // sharded scans so far (the same on every rank: the call is collective)
+    char why_not_fused[160] = "";
 };
 static Comm g_comm;
+static constexpr uint32_t kXchgSlots = 32768;                       // segments per rank the fused exchange has room for
+static size_t xchg_gather_bytes() { return (size_t)2 * kMaxPeers * 2 * kXchgSlots * sizeof(unsigned long long); }
+static size_t xchg_bytes() { return xchg_gather_bytes() + 2 * kMaxPeers * sizeof(unsigned int) + 64; }
+static unsigned long long *xchg_gather(unsigned char *base, uint32_t parity, uint32_t world, uint32_t stride) {
+    (void)world;
+    (void)stride;
+    return reinterpret_cast<unsigned long long *>(base) + (size_t)parity * kMaxPeers * 2 * kXchgSlots;
+}
+static unsigned int *xchg_flags(unsigned char *base, uint32_t parity) {
+    return reinterpret_cast<unsigned int *>(base + xchg_gather_bytes()) + (size_t)parity * kMaxPeers;
+}
+static unsigned int *xchg_error(unsigned char *base) {
+    return reinterpret_cast<unsigned int *>(base + xchg_gather_bytes()) + 2 * kMaxPeers;
+}
 
 static int comm_load() {
     if (g_comm.dl) return 0;
@@ -394,6 +420,79 @@ int crp_comm_init(int rank, int world, const uint8_t *id) {
     g_comm.world = world;
     CUDA_TRY(cudaMalloc(&g_comm.d_scratch, 2 * sizeof(unsigned long long)));
     CUDA_TRY(cudaMemset(g_comm.d_scratch, 0, 2 * sizeof(unsigned long long)));
+    g_comm.epoch = 0;
+    g_comm.mode = 0;
+    if (const char *e = getenv("CRP_COMM_EXCHANGE")) g_comm.mode = !strcmp(e, "nccl") ? 1 : 0;
+    // ---- fused exchange: map every rank's buffer into this process (CUDA IPC, peer access over NVLink).
+    // Anything that does not work here leaves the NCCL all-gather as the exchange; the decision is
+    // made together (an all-reduce of the per-rank verdicts), so that all ranks run the same protocol.
+    g_comm.fused = false;
+    g_comm.why_not_fused[0] = 0;
+    bool ok = world <= kMaxPeers;
+    if (!ok) snprintf(g_comm.why_not_fused, sizeof g_comm.why_not_fused, "world %d > %d", world, kMaxPeers);
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    if (ok) {
+        if (cudaMalloc(&g_comm.xchg, xchg_bytes()) != cudaSuccess || cudaMemset(g_comm.xchg, 0, xchg_bytes()) != cudaSuccess ||
+            cudaIpcGetMemHandle(&mine, g_comm.xchg) != cudaSuccess) {
+            snprintf(g_comm.why_not_fused, sizeof g_comm.why_not_fused, "exchange buffer / IPC handle: %s",
+                     cudaGetErrorString(cudaGetLastError()));
+            ok = false;
+        }
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::vector<uint64_t> handles((size_t)world * 8);
+    {
+        unsigned long long *d = nullptr;
+        CUDA_TRY(cudaMalloc(&d, ((size_t)world + 1) * 64));
+        CUDA_TRY(cudaMemcpy(d, &mine, 64, cudaMemcpyHostToDevice));
+        NCCL_TRY(g_comm.AllGather(d, d + 8, 8, ncclUint64, g_comm.comm, g_ctx.stream));
+        CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+        CUDA_TRY(cudaMemcpy(handles.data(), d + 8, (size_t)world * 64, cudaMemcpyDeviceToHost));
+        cudaFree(d);
+    }
+    for (int q = 0; q < world && ok; ++q) {
+        if (q == rank) {
+            g_comm.peer[q] = g_comm.xchg;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, &handles[(size_t)q * 8], 64);
+        void *ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            snprintf(g_comm.why_not_fused, sizeof g_comm.why_not_fused, "cudaIpcOpenMemHandle(rank %d): %s", q,
+                     cudaGetErrorString(cudaGetLastError()));
+            ok = false;
+        } else {
+            g_comm.peer[q] = static_cast<unsigned char *>(ptr);
+        }
+    }
+    {   // unanimous?
+        unsigned long long v = ok ? 0ull : 1ull;
+        CUDA_TRY(cudaMemcpy(g_comm.d_scratch, &v, sizeof v, cudaMemcpyHostToDevice));
+        NCCL_TRY(g_comm.AllReduce(g_comm.d_scratch, g_comm.d_scratch + 1, 1, ncclUint64, ncclSum, g_comm.comm, g_ctx.stream));
+        CUDA_TRY(cudaStreamSynchronize(g_ctx.stream));
+        CUDA_TRY(cudaMemcpy(&v, g_comm.d_scratch + 1, sizeof v, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemset(g_comm.d_scratch, 0, 2 * sizeof(unsigned long long)));
+        if (v && ok) snprintf(g_comm.why_not_fused, sizeof g_comm.why_not_fused, "%llu other rank(s) could not map the buffers", v);
+        g_comm.fused = v == 0;
+    }
+    return 0;
+}
+
+/* 0: the kernel exchanges the counts itself when every rank could map its peers' buffers (default);
+ * 1: always the NCCL all-gather behind the kernel.  Collective in effect: set it on every rank. */
+int crp_comm_set_exchange(int mode) {
+    if (mode != 0 && mode != 1) return fail(CRP_ERR_ARG, "mode must be 0 (fused) or 1 (nccl)");
+    g_comm.mode = mode;
+    return 0;
+}
+
+/* *fused = 1 if sharded scans of this communicator exchange their counts inside the kernel;
+ * otherwise why (a static string) says what prevented it. */
+int crp_comm_exchange_info(int *fused, const char **why) {
+    if (fused) *fused = g_comm.comm && g_comm.fused && g_comm.mode == 0 ? 1 : 0;
+    if (why) *why = g_comm.mode == 1 ? "NCCL exchange selected" : g_comm.why_not_fused;
     return 0;
 }
 
@@ -512,6 +611,15 @@ int crp_link_probe(uint64_t h2d_bytes, uint64_t d2h_bytes, uint32_t reps, float 
 int crp_comm_shutdown(void) {
     if (g_comm.comm) {
         cudaDeviceSynchronize();
+        // nobody unmaps while a peer may still be storing: everyone meets first (the call is collective)
+        g_comm.AllReduce(g_comm.d_scratch, g_comm.d_scratch + 1, 1, ncclUint64, ncclSum, g_comm.comm, g_ctx.stream);
+        cudaStreamSynchronize(g_ctx.stream);
+        for (int q = 0; q < g_comm.world && q < kMaxPeers; ++q)
+            if (g_comm.peer[q] && q != g_comm.rank) cudaIpcCloseMemHandle(g_comm.peer[q]);
+        for (auto &pp : g_comm.peer) pp = nullptr;
+        if (g_comm.xchg) cudaFree(g_comm.xchg);
+        g_comm.xchg = nullptr;
+        g_comm.fused = false;
         g_comm.CommDestroy(g_comm.comm);
         cudaFree(g_comm.d_scratch);
         g_comm.comm = nullptr;
@@ -865,7 +973,6 @@ struct ScanPlan {
     const void *fn;
     unsigned grid, threads;
     size_t smem;
-    uint32_t wave_tiles, n_waves;
 };
 
 static int plan_scan(const crp_genome *g, bool scored, ScanPlan *p) {
@@ -891,15 +998,6 @@ static int plan_scan(const crp_genome *g, bool scored, ScanPlan *p) {
     if (grid > g->n_tiles) grid = g->n_tiles;
     if (grid < 1) grid = 1;
     p->grid = (unsigned)grid;
-    // Wave = the tiles counted, then emitted, between two grid barriers: as many as the count
-    // ranges allow (measured: fewer, larger waves are faster even when the records outgrow L2).
-    uint64_t wave = grid * kMaxRange;
-    if (const char *e = getenv("CRP_WAVE_TILES")) {
-        const long v = atol(e);
-        if (v > 0 && (uint64_t)v < wave) wave = (uint64_t)v;
-    }
-    p->wave_tiles = (uint32_t)wave;
-    p->n_waves = (uint32_t)((g->n_tiles + wave - 1) / wave);
     return 0;
 }
 
@@ -909,7 +1007,6 @@ static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p) {
     a.records = g->records;
     a.pam = g->pam;
     a.n_tiles = g->n_tiles;
-    a.wave_tiles = p.wave_tiles;
     a.static_eighths = 4;
     if (const char *e = getenv("CRP_STATIC_EIGHTHS")) a.static_eighths = (uint32_t)atoi(e) > 8 ? 8 : (uint32_t)atoi(e);
     a.guide_len = r->guide_len;
@@ -932,28 +1029,58 @@ static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p) {
     a.seg_stride = r->stride;
     a.seg_first_tile = g->d_seg_first;      // NULL for a single-segment genome
     a.seg_tile_count = g->d_seg_count;
+    a.world = 1;
+    a.rank = 0;
+    a.epoch = 0;
+    a.xchg_error = nullptr;
+    a.xchg_timeout_ns = 20ull * 1000 * 1000 * 1000;
+    for (int q = 0; q < kMaxPeers; ++q) {
+        a.peer_gather[q] = nullptr;
+        a.peer_flags[q] = nullptr;
+    }
+    const unsigned long long *gathered = r->d_gather;       // where the blocks of all ranks end up
+    if (r->fused) {
+        // Fused exchange: the kernel stores this rank's counts into every rank's buffer right after its
+        // count phase and leaves once all blocks are in its own -- no collective launch behind the kernel.
+        a.world = (uint32_t)g_comm.world;
+        a.rank = (uint32_t)g_comm.rank;
+        a.epoch = r->epoch;
+        a.xchg_error = xchg_error(g_comm.xchg);
+        if (const char *e = getenv("CRP_XCHG_TIMEOUT_MS")) a.xchg_timeout_ns = strtoull(e, nullptr, 10) * 1000000ull;
+        for (int q = 0; q < g_comm.world; ++q) {
+            a.peer_gather[q] = xchg_gather(g_comm.peer[q], r->epoch & 1u, a.world, r->stride);
+            a.peer_flags[q] = xchg_flags(g_comm.peer[q], r->epoch & 1u);
+        }
+        gathered = xchg_gather(g_comm.xchg, r->epoch & 1u, a.world, r->stride);
+    }
     CUDA_TRY(cudaEventRecord(r->ev[0], st));
     if (g->n_tiles) {
         void *params[] = {(void *)&a};
         CUDA_TRY(cudaLaunchCooperativeKernel(p.fn, dim3(p.grid), dim3(p.threads), params, p.smem, st));
         g_ctx.launches++;
         CUDA_TRY(cudaGetLastError());
+    } else if (r->fused) {
+        k_exchange_empty<<<1, 256, 0, st>>>(a);
+        g_ctx.launches++;
+        CUDA_TRY(cudaGetLastError());
     } else if (r->stride) {
         CUDA_TRY(cudaMemsetAsync(r->d_counts, 0, 2 * (size_t)r->stride * sizeof(unsigned long long), st));
     }
-    if (r->d_gather) {
-        // the one exchange step of a sharded scan: every rank's per-segment counts to every rank, right
-        // behind the kernel on the same stream, so the CUDA events bracket kernel + collective
-        CUDA_TRY(cudaEventRecord(r->ev_kernel, st));
+    if (r->ev_kernel) CUDA_TRY(cudaEventRecord(r->ev_kernel, st));
+    if (r->d_gather && !r->fused) {
+        // NCCL exchange: every rank's per-segment counts to every rank, right behind the kernel on the
+        // same stream, so the CUDA events bracket kernel + collective
         if (int rc = comm_allgather_u64(r->d_counts, r->d_gather, 2 * (size_t)r->stride, st)) return rc;
     }
     CUDA_TRY(cudaEventRecord(r->ev[1], st));
     if (r->stride)
         CUDA_TRY(cudaMemcpyAsync(r->h_counts, r->d_counts, 2 * (size_t)r->stride * sizeof(unsigned long long),
                                  cudaMemcpyDeviceToHost, st));
-    if (r->d_gather)
-        CUDA_TRY(cudaMemcpyAsync(r->h_gather, r->d_gather, (size_t)g_comm.world * 2 * r->stride * sizeof(unsigned long long),
+    if (r->h_gather && gathered)
+        CUDA_TRY(cudaMemcpyAsync(r->h_gather, gathered, (size_t)g_comm.world * 2 * r->stride * sizeof(unsigned long long),
                                  cudaMemcpyDeviceToHost, st));
+    if (r->fused)
+        CUDA_TRY(cudaMemcpyAsync(r->h_xchg_error, xchg_error(g_comm.xchg), sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaEventRecord(r->ev[2], st));
     return 0;
 }
@@ -976,9 +1103,9 @@ static int scan_enqueue(crp_genome *g, int guide_len, uint32_t flags, crp_result
     ScanPlan plan = {};
     if ((rc = plan_scan(g, r->scored, &plan))) return bail(rc);
     r->stride = slots ? slots : n_seg;
-    r->zero_offset = ((size_t)g->n_tiles * kPrefWords + 2 * (size_t)plan.grid) * sizeof(unsigned long long);
+    r->zero_offset = ((size_t)g->n_tiles * kPrefWords + (size_t)plan.grid) * sizeof(unsigned long long);
     r->state_bytes = r->zero_offset + 2 * (size_t)r->stride * sizeof(unsigned long long) +
-                     ((size_t)plan.n_waves + 2) * sizeof(unsigned int);
+                     4 * sizeof(unsigned int);
     if (dev_alloc(&r->state, r->state_bytes, r->st) != cudaSuccess)
         return bail(fail(CRP_ERR_NOMEM, "cudaMalloc of scan state failed"));
     r->d_counts = reinterpret_cast<unsigned long long *>(r->state + r->zero_offset);
@@ -986,6 +1113,13 @@ static int scan_enqueue(crp_genome *g, int guide_len, uint32_t flags, crp_result
     if (!r->h_counts) return bail(fail(CRP_ERR_NOMEM, "cudaHostAlloc of the counts failed"));
     if (slots) {
         const size_t gb = (size_t)g_comm.world * 2 * slots * sizeof(unsigned long long);
+        r->fused = g_comm.fused && g_comm.mode == 0 && slots <= kXchgSlots;
+        r->epoch = ++g_comm.epoch;
+        if (r->fused) {
+            r->h_xchg_error = static_cast<unsigned int *>(pinned_get(sizeof(unsigned int)));
+            if (!r->h_xchg_error) return bail(fail(CRP_ERR_NOMEM, "cudaHostAlloc failed"));
+            *r->h_xchg_error = 0;
+        }
         if (dev_alloc(&r->d_gather, gb, r->st) != cudaSuccess)
             return bail(fail(CRP_ERR_NOMEM, "cudaMalloc of the gathered counts failed"));
         r->h_gather = static_cast<unsigned long long *>(pinned_get(gb));
@@ -1027,9 +1161,17 @@ static int scan_finish(crp_genome *g, crp_result *r) {
             r->ms_kernel += ms;
             r->n_launches++;
         }
+        if (r->fused && *r->h_xchg_error)
+            return fail(CRP_ERR_CUDA, "sharded scan: the counts of rank %u did not arrive (peer not scanning?)", *r->h_xchg_error - 1);
         const uint64_t need = r->n_plus > r->n_minus ? r->n_plus : r->n_minus;
         if (need <= r->capacity) break;
         if (attempt == 1) return fail(CRP_ERR_STATE, "candidate streams overflowed twice");
+        // the rerun is local: the counts are already exchanged, the second launch only fills the streams
+        r->fused = false;
+        if (r->d_gather) {
+            dev_free(r->d_gather, r->st);
+            r->d_gather = nullptr;               // keeps h_gather of the first launch
+        }
         free_streams(r);
         if (int rc = alloc_streams(r, need, r->scored)) return rc;
         ScanPlan plan = {};
@@ -1219,6 +1361,7 @@ int crp_result_free(crp_result *r) {
     dev_free(r->d_gather, r->st);
     pinned_put(r->h_counts);
     pinned_put(r->h_gather);
+    pinned_put(r->h_xchg_error);
     if (r->ev_kernel) cudaEventDestroy(r->ev_kernel);
     for (cudaEvent_t e : r->ev)
         if (e) cudaEventDestroy(e);

@@ -10,10 +10,12 @@
 // A word is a uint4 of four 32-position bit planes {code low bit, code high bit (A0 T1 C2
 // G3, CROPSR.py:300-302), lower-case, other byte}: 0.5 byte per base.
 //
-// k_scan_score is one cooperative, persistent launch.  Per wave of tiles:
+// k_scan_score is one cooperative, persistent launch:
 //   count phase   every CTA counts the PAM hits of a contiguous range of tiles (bandwidth
 //                 bound: bulk copies + a few bit ops per word) and publishes the range total
-//                 and the range-local exclusive prefix of every tile;
+//                 and the range-local exclusive prefix of every tile (ranges of any length are
+//                 walked in batches of kMaxRange tiles with a running prefix: one count phase,
+//                 one grid barrier, one tail for a genome of any size);
 //   grid barrier, every CTA scans the range totals into shared memory;
 //   emit phase    tiles are handed out dynamically; the global output offset of a tile is
 //                 range prefix + tile prefix (one load), so there is no ordering between
@@ -42,7 +44,8 @@ static constexpr int kStages = 2;                          // staged tiles per C
 static constexpr int kListCap = 1024;                      // hits per strand of a tile compacted in one go
 static constexpr int kPrefWords = 10;                      // per tile: 8 warp prefixes, tile total, pad (80 B, one bulk copy)
 static constexpr uint32_t kNoTile = 0xFFFFFFFFu;
-static constexpr int kMaxRange = 32;                       // tiles per CTA per wave in the count phase
+static constexpr int kMaxRange = 32;                       // tiles of a CTA's count range whose (tile, chunk) counts are scanned in one go
+static constexpr int kMaxPeers = 8;                        // GPUs of one box
 static constexpr uint32_t kAlign = 128;                    // positions; segment placement granularity
 
 // PAM record of a tile, read by the count phase instead of the full record: descriptor, then for
@@ -338,8 +341,7 @@ struct ScanArgs {
     const uint4 *records;            // n_tiles records of kRecWords words
     const unsigned char *pam;        // n_tiles PAM records of kPamBytes bytes (count phase)
     uint32_t n_tiles;
-    uint32_t wave_tiles;             // tiles per wave (<= gridDim.x * kMaxRange)
-    uint32_t static_eighths;         // share of a wave's tiles dealt round-robin, in 1/8 (the rest are ticketed)
+    uint32_t static_eighths;         // share of the tiles dealt round-robin, in 1/8 (the rest are ticketed)
     int guide_len;
     uint32_t flags;
     const double *tables;            // RS1 lane tables (RS1_TABLE_DOUBLES doubles)
@@ -349,13 +351,56 @@ struct ScanArgs {
     double *x_plus, *x_minus;
     // scan state; nothing needs initialising before the launch.  Counts are (plus << 32) | minus.
     unsigned long long *warp_pref;   // [n_tiles][kPrefWords] exclusive prefix of every warp chunk inside its count range, then the tile total
-    unsigned long long *cta_tot;     // [2][gridDim.x] range totals, double-buffered by wave parity
-    unsigned int *tickets;           // [n_waves] emit-phase dispensers of the dynamic tiles
+    unsigned long long *cta_tot;     // [gridDim.x] range totals
+    unsigned int *tickets;           // [0] emit-phase dispenser of the dynamic tiles, [1] CTAs done with the segment counts
     unsigned long long *seg_counts;  // [2 * seg_stride] out: plus[0..n_seg) then, from seg_stride on, minus[0..n_seg);
                                      // slots n_seg .. seg_stride-1 are zeroed (fixed-size block of a sharded scan's all-gather)
     const uint32_t *seg_first_tile, *seg_tile_count;   // [n_seg]
     uint32_t n_seg, seg_stride;
+    // Sharded scan, fused exchange (world > 1): the segment counts also go -- plain stores over NVLink --
+    // into every rank's gather buffer, followed by a flag; the kernel returns once the blocks of all ranks
+    // have landed in its own buffer.  The all-gather of the counts hides behind the emit phase.
+    uint32_t world, rank, epoch;     // world <= 1: no exchange
+    unsigned long long *peer_gather[kMaxPeers];   // rank p's buffer of this epoch's parity: [world][2 * seg_stride]
+    unsigned int *peer_flags[kMaxPeers];          // rank p's flags of this epoch's parity: [world], flag[r] = epoch once r's block is in
+    unsigned int *xchg_error;        // set if a peer's block did not arrive in time
+    unsigned long long xchg_timeout_ns;
 };
+
+// every rank's block is in my gather buffer (or the timeout struck): spun by the first `world` threads of one CTA
+__device__ __forceinline__ void xchg_wait(const ScanArgs &a) {
+    if (threadIdx.x < a.world) {
+        volatile unsigned int *flag = a.peer_flags[a.rank] + threadIdx.x;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (*flag != a.epoch) {
+            __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > a.xchg_timeout_ns) {
+                atomicExch(a.xchg_error, 1u + threadIdx.x);
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+}
+
+// this rank's block is complete in every peer's buffer: raise the flags (one thread)
+__device__ __forceinline__ void xchg_publish(const ScanArgs &a) {
+    __threadfence_system();
+    for (uint32_t p = 0; p < a.world; ++p) *reinterpret_cast<volatile unsigned int *>(a.peer_flags[p] + a.rank) = a.epoch;
+}
+
+// A rank whose shard has no tile still takes part in the exchange.
+__global__ void k_exchange_empty(const ScanArgs a) {
+    for (uint32_t sg = threadIdx.x; sg < 2 * a.seg_stride; sg += blockDim.x) {
+        a.seg_counts[sg] = 0ull;
+        for (uint32_t p = 0; p < a.world; ++p) a.peer_gather[p][(size_t)a.rank * 2 * a.seg_stride + sg] = 0ull;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && a.world > 1) xchg_publish(a);
+    if (a.world > 1) xchg_wait(a);
+}
 
 // optional phase timeline (tools/phase_timeline.py): 8 x u64 per CTA, or NULL
 __device__ unsigned long long *g_dbg_times = nullptr;
@@ -484,7 +529,7 @@ __device__ __forceinline__ void emit_strand(const ScanArgs &a, const double *__r
 struct __align__(16) Ring {
     unsigned long long pref[kStages][kPrefWords];   // bulk-copy destination (emit phase)
     unsigned long long full[kCountStages];          // mbarriers (the emit phase uses the first kStages)
-    unsigned long long pre;                         // first emit tile of a wave, fetched before the grid barrier
+    unsigned long long pre;                         // first emit tile, fetched before the grid barrier
     unsigned long long rbase[kStages];              // global prefix of the count range of the staged tile (emit phase)
     uint32_t tile[kCountStages];                    // staged tile, or kNoTile: the sequence has ended
     uint32_t done[kCountStages];                    // warps finished with the slot (count phase)
@@ -559,43 +604,47 @@ k_scan_score(const ScanArgs a) {
     }
 
     auto record = [&](uint32_t tile) { return a.records + (size_t)tile * kRecWords; };
-    unsigned long long wave_base = 0;
-    uint32_t wave = 0;
-    for (uint32_t w_lo = 0; w_lo < a.n_tiles; w_lo += a.wave_tiles, ++wave) {
-        const uint32_t w_hi = min(a.n_tiles, w_lo + a.wave_tiles);
-        const uint32_t nt = w_hi - w_lo;
-        const uint32_t k = (nt + G - 1) / G;                       // tiles per count range (<= kMaxRange)
+    const uint32_t nt = a.n_tiles;
+    const uint32_t k = (nt + G - 1) / G;                           // tiles per count range
 
-        // ================================================= count phase: tiles [r_lo, r_lo + n_mine)
-        const uint32_t r_lo = min(w_hi, w_lo + cta * k), n_mine = min(w_hi, r_lo + k) - r_lo;
-        auto pam_stage = [&](int s) { return s_dyn + (size_t)s * kPamBytes; };
-        auto produce_count = [&](uint32_t n) {            // n < n_mine
-            const int s = n % kCountStages;
-            *reinterpret_cast<volatile uint32_t *>(&ring.tile[s]) = n;    // which tile of the range the slot is (being) filled with
-            mbar_expect(&ring.full[s], kPamBytes);
-            bulk_copy(pam_stage(s), a.pam + (size_t)(r_lo + n) * kPamBytes, kPamBytes, &ring.full[s]);
-        };
-        if (cta == 0 && tid == 0) a.tickets[wave] = 0;             // read after the grid barrier
-        ring_reset(ring, wave == 0, true);
-        dbg_stamp(1);
-        if (tid == 0)
-            for (uint32_t n = 0; n < (uint32_t)kCountStages && n < n_mine; ++n) produce_count(n);
-        // Tile n of the range goes to warp n % 8, which counts all of it and then refills the slot
-        // with tile n + 6: no hand-over between warps, ~250 instructions per tile instead of 8 x 80.
-        // A warp only visits its own tiles, so it may find the slot several refills behind; the
-        // parity of an mbarrier cannot tell those apart, the slot's tile number can.
-        for (uint32_t n = warp; n < n_mine; n += kWarps) {
+    // ================================================= count phase: tiles [r_lo, r_lo + n_mine)
+    const uint32_t r_lo = min(nt, cta * k), n_mine = min(nt, r_lo + k) - r_lo;
+    auto pam_stage = [&](int s) { return s_dyn + (size_t)s * kPamBytes; };
+    auto produce_count = [&](uint32_t n) {            // n < n_mine
+        const int s = n % kCountStages;
+        *reinterpret_cast<volatile uint32_t *>(&ring.tile[s]) = n;    // which tile of the range the slot is (being) filled with
+        mbar_expect(&ring.full[s], kPamBytes);
+        bulk_copy(pam_stage(s), a.pam + (size_t)(r_lo + n) * kPamBytes, kPamBytes, &ring.full[s]);
+    };
+    if (cta == 0 && tid == 0) {                                    // read after the grid barrier
+        a.tickets[0] = 0;
+        a.tickets[1] = 0;
+    }
+    ring_reset(ring, true, true);
+    dbg_stamp(1);
+    if (tid == 0)
+        for (uint32_t n = 0; n < (uint32_t)kCountStages && n < n_mine; ++n) produce_count(n);
+    // Tile n of the range goes to warp n % 8, which counts all of it and then refills the slot
+    // with tile n + 6: no hand-over between warps, ~250 instructions per tile instead of 8 x 80.
+    // A warp only visits its own tiles, so it may find the slot several refills behind; the
+    // parity of an mbarrier cannot tell those apart, the slot's tile number can.
+    // The range is walked in batches of kMaxRange tiles: their (tile, chunk) counts are scanned
+    // together and the running prefix of the range carries over.
+    unsigned long long range_run = 0;
+    for (uint32_t b_lo = 0;; b_lo += kMaxRange) {
+        const uint32_t b_n = min(n_mine - min(n_mine, b_lo), (uint32_t)kMaxRange);
+        for (uint32_t n = b_lo + warp; n < b_lo + b_n; n += kWarps) {
             const int s = n % kCountStages;
             while (*reinterpret_cast<volatile uint32_t *>(&ring.tile[s]) != n) __nanosleep(32);
             mbar_wait(&ring.full[s], (n / kCountStages) & 1u);
-            warp_count_tile(pam_stage(s), l, lane, s_cnt[n]);
+            warp_count_tile(pam_stage(s), l, lane, s_cnt[n - b_lo]);
             __syncwarp();
             if (lane == 0 && n + kCountStages < n_mine) produce_count(n + kCountStages);
         }
         __syncthreads();
-        {   // exclusive scan over the (tile, warp) counts of the range: thread tid owns tile tid / 8, warp tid % 8
+        {   // exclusive scan over the (tile, warp) counts of the batch: thread tid owns tile tid / 8, warp tid % 8
             const uint32_t j = tid / kWarps, wq = tid % kWarps;
-            const unsigned long long mine = j < n_mine ? unpack_counts(s_cnt[j][wq]) : 0ull;
+            const unsigned long long mine = j < b_n ? unpack_counts(s_cnt[j][wq]) : 0ull;
             unsigned long long incl = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -604,185 +653,204 @@ k_scan_score(const ScanArgs a) {
             }
             if (lane == 31) s_scan[warp] = incl;
             __syncthreads();
-            unsigned long long before = 0, total = 0;
+            unsigned long long before = range_run, total = 0;
 #pragma unroll
             for (int q = 0; q < kWarps; ++q) {
                 const unsigned long long x = s_scan[q];
                 if (q < warp) before += x;
                 total += x;
             }
-            if (j < n_mine) {
-                unsigned long long *pf = a.warp_pref + (size_t)(r_lo + j) * kPrefWords;
+            if (j < b_n) {
+                unsigned long long *pf = a.warp_pref + (size_t)(r_lo + b_lo + j) * kPrefWords;
                 pf[wq] = before + incl - mine;
                 if (wq == kWarps - 1) pf[kWarps] = before + incl;      // prefix at the end of the tile
                 asm volatile("fence.proxy.async.global;" ::: "memory");   // read back by bulk copies after the grid barrier
             }
-            if (tid == 0) a.cta_tot[(wave & 1u) * G + cta] = total;
+            range_run += total;
+            __syncthreads();                                       // s_cnt and s_scan are free for the next batch
         }
-        // The first emit tile of this CTA is known (static share): its record is fetched across the
-        // grid barrier -- the count ring is idle now -- and its prefix block, which another CTA may
-        // have written, right after the barrier.
-        const uint32_t ns = (uint32_t)((unsigned long long)nt * a.static_eighths / 8 / G);
-        const bool pre = ns > 0;
-        const uint32_t t_pre = w_lo + cta;
-        if (pre && tid == 0) {
-            mbar_expect(&ring.pre, kRecBytes + kPrefWords * 8);
-            bulk_copy(stage(0), record(t_pre), kRecBytes, &ring.pre);
-        }
-        dbg_stamp(2);
-        grid.sync();
-        dbg_stamp(3);
-        if (pre && tid == 0) bulk_copy(ring.pref[0], a.warp_pref + (size_t)t_pre * kPrefWords, kPrefWords * 8, &ring.pre);
-
-        // ================================================= exclusive scan of the range totals
-        unsigned long long wave_total;
-        {
-            unsigned long long v[4] = {0, 0, 0, 0}, mine = 0;     // thread owns ranges 4*tid .. 4*tid+3
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t i = 4u * tid + q;
-                if (i < G) v[q] = a.cta_tot[(wave & 1u) * G + i];
-                mine += v[q];
-            }
-            unsigned long long incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long x = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += x;
-            }
-            if (lane == 31) s_scan[warp] = incl;
-            __syncthreads();
-            unsigned long long before = 0, total = 0;
-#pragma unroll
-            for (int q = 0; q < kWarps; ++q) {
-                const unsigned long long x = s_scan[q];
-                if (q < warp) before += x;
-                total += x;
-            }
-            unsigned long long run = wave_base + before + incl - mine;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t i = 4u * tid + q;
-                if (i < G) s_rangepref[i] = run;
-                run += v[q];
-            }
-            wave_total = total;
-        }
-
-        // ================================================= emit phase
-        // The first ns * G tiles of the wave are dealt round-robin (tile known without a
-        // round trip); the rest go through the ticket counter, which evens out what the
-        // data-dependent emit work left unbalanced.
-        const uint32_t dyn_lo = w_lo + ns * G, n_dyn = w_hi - dyn_lo;
-        unsigned int *const ticket = a.tickets + wave;
-        auto produce_emit = [&](uint32_t n, int s) {     // one thread: stage tile number n of this CTA into slot s
-            uint32_t t;
-            if (n < ns) {
-                t = w_lo + n * G + cta;
-            } else {
-                const uint32_t q = atomicAdd(ticket, 1u);
-                t = q < n_dyn ? dyn_lo + q : kNoTile;
-            }
-            ring.tile[s] = t;
-            if (t != kNoTile) {
-                ring.rbase[s] = s_rangepref[(t - w_lo) / k];
-                mbar_expect(&ring.full[s], kRecBytes + kPrefWords * 8);
-                bulk_copy(stage(s), record(t), kRecBytes, &ring.full[s]);
-                bulk_copy(ring.pref[s], a.warp_pref + (size_t)t * kPrefWords, kPrefWords * 8, &ring.full[s]);
-            } else {
-                mbar_arrive(&ring.full[s]);
-            }
-        };
-        ring_reset(ring, false, false);                            // also publishes s_rangepref
-        dbg_stamp(4);
-        if (kScore && wave == 0) mbar_wait(&s_tabbar, 0);
-        // per-segment candidate counts of this wave: prefix at the end of the segment's last
-        // tile minus prefix at the start of its first one (segments are dealt to threads)
-        for (uint32_t sg = cta * kThreads + tid; sg < a.seg_stride; sg += G * kThreads) {
-            if (sg >= a.n_seg) {                                                        // padding of the all-gather block
-                a.seg_counts[sg] = 0ull;
-                a.seg_counts[a.seg_stride + sg] = 0ull;
-                continue;
-            }
-            const uint32_t f = a.seg_first_tile ? a.seg_first_tile[sg] : 0u;            // NULL: one segment = all tiles
-            const uint32_t c = a.seg_tile_count ? a.seg_tile_count[sg] : a.n_tiles;
-            const uint32_t lo_t = max(f, w_lo), hi_t = min(f + c, w_hi);       // tiles of the segment in this wave
-            unsigned long long cnt = 0;
-            if (lo_t < hi_t)
-                cnt = s_rangepref[(hi_t - 1 - w_lo) / k] + a.warp_pref[(size_t)(hi_t - 1) * kPrefWords + kWarps] -
-                      (s_rangepref[(lo_t - w_lo) / k] + a.warp_pref[(size_t)lo_t * kPrefWords]);
-            const unsigned long long plus = cnt >> 32, minus = cnt & 0xFFFFFFFFull;
-            a.seg_counts[sg] = (wave ? a.seg_counts[sg] : 0ull) + plus;
-            a.seg_counts[a.seg_stride + sg] = (wave ? a.seg_counts[a.seg_stride + sg] : 0ull) + minus;
-        }
-        if (tid == 0) {
-            if (pre) mbar_arrive(&ring.full[0]);                   // tile 0 came through ring.pre: skip that phase of slot 0
-            else produce_emit(0, 0);
-        }
-        uint16_t *const list_p = s_list, *const list_m = s_list + kListCap;
-        for (uint32_t n = 0;; ++n) {
-            const int s = n % kStages;
-            // next tile of this CTA: its copies land while this tile is emitted (slot s^1 was
-            // released by the barrier that ended tile n - 1)
-            if (tid == 0) produce_emit(n + 1, s ^ 1);
-            const bool first_pre = pre && n == 0;
-            if (first_pre) mbar_wait(&ring.pre, 0u);
-            else mbar_wait(&ring.full[s], (n / kStages) & 1u);
-            if (!first_pre && ring.tile[s] == kNoTile) break;
-            const uint4 *rec = stage(s);
-            const uint4 d = rec[0];
-            const TileDesc td = {d.x, d.y, d.z, d.w};
-            const unsigned long long tile_pref = ring.pref[s][0];
-            const unsigned long long base = (first_pre ? s_rangepref[(t_pre - w_lo) / k] : ring.rbase[s]) + tile_pref;
-            const unsigned long long off = ring.pref[s][warp] - tile_pref;          // hits of the tile before my warp chunk
-            const unsigned long long tot = ring.pref[s][kWarps] - tile_pref;
-            const uint32_t np = (uint32_t)(tot >> 32), nm = (uint32_t)tot;
-            const uint32_t base_p = (uint32_t)(base >> 32), base_m = (uint32_t)base;
-            const uint32_t wordA = 64 * warp + lane;
-            const Hits h = tile_hits(rec, td, l, wordA);
-            // ---- warp scan of the per-word counts: the A words of the chunk precede its B words
-            const uint32_t cA = __popc(h.pA) | (__popc(h.mA) << 16), cB = __popc(h.pB) | (__popc(h.mB) << 16);
-            uint32_t iA = cA, iB = cB;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t vA = __shfl_up_sync(0xFFFFFFFFu, iA, o), vB = __shfl_up_sync(0xFFFFFFFFu, iB, o);
-                if (lane >= o) {
-                    iA += vA;
-                    iB += vB;
-                }
-            }
-            const uint32_t totA = __shfl_sync(0xFFFFFFFFu, iA, 31);
-            // rank (inside the tile, per strand) of the first hit of my words
-            const uint32_t xA = iA - cA, xB = totA + iB - cB;
-            const uint32_t op = (uint32_t)(off >> 32), om = (uint32_t)off;
-            const uint32_t epA = op + (xA & 0xFFFFu), emA = om + (xA >> 16), epB = op + (xB & 0xFFFFu), emB = om + (xB >> 16);
-            if (np <= (uint32_t)kListCap && nm <= (uint32_t)kListCap) {
-                list_hits(list_p + epA, h.pA, 32u * wordA + kWinBiasPlus);
-                list_hits(list_p + epB, h.pB, 32u * (wordA + 32) + kWinBiasPlus);
-                list_hits(list_m + emA, h.mA, 32u * wordA + kWinBiasMinus);
-                list_hits(list_m + emB, h.mB, 32u * (wordA + 32) + kWinBiasMinus);
-                __syncthreads();
-                emit_strand<kScore, false>(a, s_tab, rec, list_p, np, base_p, td.t_start, td.L, tid);
-                emit_strand<kScore, true>(a, s_tab, rec, list_m, nm, base_m, td.t_start, td.L, tid ^ (kThreads / 2));
-            } else {                                               // dense tile: windows of kListCap ranks
-                for (uint32_t lo = 0; lo < np || lo < nm; lo += kListCap) {
-                    const uint32_t cp = np > lo ? min(np - lo, (uint32_t)kListCap) : 0u;
-                    const uint32_t cm = nm > lo ? min(nm - lo, (uint32_t)kListCap) : 0u;
-                    if (lo) __syncthreads();
-                    list_hits_window(list_p, h.pA, epA, 32u * wordA + kWinBiasPlus, lo);
-                    list_hits_window(list_p, h.pB, epB, 32u * (wordA + 32) + kWinBiasPlus, lo);
-                    list_hits_window(list_m, h.mA, emA, 32u * wordA + kWinBiasMinus, lo);
-                    list_hits_window(list_m, h.mB, emB, 32u * (wordA + 32) + kWinBiasMinus, lo);
-                    __syncthreads();
-                    emit_strand<kScore, false>(a, s_tab, rec, list_p, cp, base_p + lo, td.t_start, td.L, tid);
-                    emit_strand<kScore, true>(a, s_tab, rec, list_m, cm, base_m + lo, td.t_start, td.L, tid);
-                }
-            }
-            __syncthreads();                                       // slot s and the lists are free again
-        }
-        dbg_stamp(5);
-        wave_base += wave_total;
+        if (b_lo + kMaxRange >= n_mine) break;
     }
+    if (tid == 0) a.cta_tot[cta] = range_run;
+    // The first emit tile of this CTA is known (static share): its record is fetched across the
+    // grid barrier -- the count ring is idle now -- and its prefix block, which another CTA may
+    // have written, right after the barrier.
+    const uint32_t ns = (uint32_t)((unsigned long long)nt * a.static_eighths / 8 / G);
+    const bool pre = ns > 0;
+    const uint32_t t_pre = cta;
+    if (pre && tid == 0) {
+        mbar_expect(&ring.pre, kRecBytes + kPrefWords * 8);
+        bulk_copy(stage(0), record(t_pre), kRecBytes, &ring.pre);
+    }
+    dbg_stamp(2);
+    grid.sync();
+    dbg_stamp(3);
+    if (pre && tid == 0) bulk_copy(ring.pref[0], a.warp_pref + (size_t)t_pre * kPrefWords, kPrefWords * 8, &ring.pre);
+
+    // ================================================= exclusive scan of the range totals
+    {
+        unsigned long long v[4] = {0, 0, 0, 0}, mine = 0;     // thread owns ranges 4*tid .. 4*tid+3
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t i = 4u * tid + q;
+            if (i < G) v[q] = a.cta_tot[i];
+            mine += v[q];
+        }
+        unsigned long long incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long x = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += x;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        unsigned long long before = 0;
+#pragma unroll
+        for (int q = 0; q < kWarps; ++q) {
+            const unsigned long long x = s_scan[q];
+            if (q < warp) before += x;
+        }
+        unsigned long long run = before + incl - mine;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t i = 4u * tid + q;
+            if (i < G) s_rangepref[i] = run;
+            run += v[q];
+        }
+    }
+
+    // ================================================= emit phase
+    // The first ns * G tiles are dealt round-robin (tile known without a round trip); the rest go
+    // through the ticket counter, which evens out what the data-dependent emit work left unbalanced.
+    const uint32_t dyn_lo = ns * G, n_dyn = nt - dyn_lo;
+    unsigned int *const ticket = a.tickets;
+    auto produce_emit = [&](uint32_t n, int s) {     // one thread: stage tile number n of this CTA into slot s
+        uint32_t t;
+        if (n < ns) {
+            t = n * G + cta;
+        } else {
+            const uint32_t q = atomicAdd(ticket, 1u);
+            t = q < n_dyn ? dyn_lo + q : kNoTile;
+        }
+        ring.tile[s] = t;
+        if (t != kNoTile) {
+            ring.rbase[s] = s_rangepref[t / k];
+            mbar_expect(&ring.full[s], kRecBytes + kPrefWords * 8);
+            bulk_copy(stage(s), record(t), kRecBytes, &ring.full[s]);
+            bulk_copy(ring.pref[s], a.warp_pref + (size_t)t * kPrefWords, kPrefWords * 8, &ring.full[s]);
+        } else {
+            mbar_arrive(&ring.full[s]);
+        }
+    };
+    ring_reset(ring, false, false);                            // also publishes s_rangepref
+    dbg_stamp(4);
+    if (kScore) mbar_wait(&s_tabbar, 0);
+    // per-segment candidate counts: prefix at the end of the segment's last tile minus prefix at the
+    // start of its first one (segments are dealt to threads).  In a sharded scan the counts go to
+    // every rank's gather buffer as well, and the last CTA through raises this rank's flags there.
+    {
+        const bool xchg = a.world > 1;
+        for (uint32_t sg = cta * kThreads + tid; sg < a.seg_stride; sg += G * kThreads) {
+            unsigned long long plus = 0, minus = 0;
+            if (sg < a.n_seg) {                                                         // beyond: padding of the all-gather block
+                const uint32_t f = a.seg_first_tile ? a.seg_first_tile[sg] : 0u;        // NULL: one segment = all tiles
+                const uint32_t c = a.seg_tile_count ? a.seg_tile_count[sg] : a.n_tiles;
+                if (c) {
+                    const unsigned long long cnt = s_rangepref[(f + c - 1) / k] + a.warp_pref[(size_t)(f + c - 1) * kPrefWords + kWarps] -
+                                                   (s_rangepref[f / k] + a.warp_pref[(size_t)f * kPrefWords]);
+                    plus = cnt >> 32;
+                    minus = cnt & 0xFFFFFFFFull;
+                }
+            }
+            a.seg_counts[sg] = plus;
+            a.seg_counts[a.seg_stride + sg] = minus;
+            if (xchg) {
+                const size_t at = (size_t)a.rank * 2 * a.seg_stride + sg;
+                for (uint32_t p = 0; p < a.world; ++p) {
+                    a.peer_gather[p][at] = plus;
+                    a.peer_gather[p][at + a.seg_stride] = minus;
+                }
+            }
+        }
+        if (xchg && cta * kThreads < a.seg_stride) {           // this CTA wrote counts
+            __threadfence_system();
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t writers = min(G, (a.seg_stride + kThreads - 1) / kThreads);
+                __threadfence_system();                        // cumulative: the CTA's stores, observed through the barrier
+                if (atomicAdd(a.tickets + 1, 1u) == writers - 1) xchg_publish(a);
+            }
+        }
+    }
+    if (tid == 0) {
+        if (pre) mbar_arrive(&ring.full[0]);                   // tile 0 came through ring.pre: skip that phase of slot 0
+        else produce_emit(0, 0);
+    }
+    uint16_t *const list_p = s_list, *const list_m = s_list + kListCap;
+    for (uint32_t n = 0;; ++n) {
+        const int s = n % kStages;
+        // next tile of this CTA: its copies land while this tile is emitted (slot s^1 was
+        // released by the barrier that ended tile n - 1)
+        if (tid == 0) produce_emit(n + 1, s ^ 1);
+        const bool first_pre = pre && n == 0;
+        if (first_pre) mbar_wait(&ring.pre, 0u);
+        else mbar_wait(&ring.full[s], (n / kStages) & 1u);
+        if (!first_pre && ring.tile[s] == kNoTile) break;
+        const uint4 *rec = stage(s);
+        const uint4 d = rec[0];
+        const TileDesc td = {d.x, d.y, d.z, d.w};
+        const unsigned long long tile_pref = ring.pref[s][0];
+        const unsigned long long base = (first_pre ? s_rangepref[t_pre / k] : ring.rbase[s]) + tile_pref;
+        const unsigned long long off = ring.pref[s][warp] - tile_pref;          // hits of the tile before my warp chunk
+        const unsigned long long tot = ring.pref[s][kWarps] - tile_pref;
+        const uint32_t np = (uint32_t)(tot >> 32), nm = (uint32_t)tot;
+        const uint32_t base_p = (uint32_t)(base >> 32), base_m = (uint32_t)base;
+        const uint32_t wordA = 64 * warp + lane;
+        const Hits h = tile_hits(rec, td, l, wordA);
+        // ---- warp scan of the per-word counts: the A words of the chunk precede its B words
+        const uint32_t cA = __popc(h.pA) | (__popc(h.mA) << 16), cB = __popc(h.pB) | (__popc(h.mB) << 16);
+        uint32_t iA = cA, iB = cB;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t vA = __shfl_up_sync(0xFFFFFFFFu, iA, o), vB = __shfl_up_sync(0xFFFFFFFFu, iB, o);
+            if (lane >= o) {
+                iA += vA;
+                iB += vB;
+            }
+        }
+        const uint32_t totA = __shfl_sync(0xFFFFFFFFu, iA, 31);
+        // rank (inside the tile, per strand) of the first hit of my words
+        const uint32_t xA = iA - cA, xB = totA + iB - cB;
+        const uint32_t op = (uint32_t)(off >> 32), om = (uint32_t)off;
+        const uint32_t epA = op + (xA & 0xFFFFu), emA = om + (xA >> 16), epB = op + (xB & 0xFFFFu), emB = om + (xB >> 16);
+        if (np <= (uint32_t)kListCap && nm <= (uint32_t)kListCap) {
+            list_hits(list_p + epA, h.pA, 32u * wordA + kWinBiasPlus);
+            list_hits(list_p + epB, h.pB, 32u * (wordA + 32) + kWinBiasPlus);
+            list_hits(list_m + emA, h.mA, 32u * wordA + kWinBiasMinus);
+            list_hits(list_m + emB, h.mB, 32u * (wordA + 32) + kWinBiasMinus);
+            __syncthreads();
+            emit_strand<kScore, false>(a, s_tab, rec, list_p, np, base_p, td.t_start, td.L, tid);
+            emit_strand<kScore, true>(a, s_tab, rec, list_m, nm, base_m, td.t_start, td.L, tid ^ (kThreads / 2));
+        } else {                                               // dense tile: windows of kListCap ranks
+            for (uint32_t lo = 0; lo < np || lo < nm; lo += kListCap) {
+                const uint32_t cp = np > lo ? min(np - lo, (uint32_t)kListCap) : 0u;
+                const uint32_t cm = nm > lo ? min(nm - lo, (uint32_t)kListCap) : 0u;
+                if (lo) __syncthreads();
+                list_hits_window(list_p, h.pA, epA, 32u * wordA + kWinBiasPlus, lo);
+                list_hits_window(list_p, h.pB, epB, 32u * (wordA + 32) + kWinBiasPlus, lo);
+                list_hits_window(list_m, h.mA, emA, 32u * wordA + kWinBiasMinus, lo);
+                list_hits_window(list_m, h.mB, emB, 32u * (wordA + 32) + kWinBiasMinus, lo);
+                __syncthreads();
+                emit_strand<kScore, false>(a, s_tab, rec, list_p, cp, base_p + lo, td.t_start, td.L, tid);
+                emit_strand<kScore, true>(a, s_tab, rec, list_m, cm, base_m + lo, td.t_start, td.L, tid);
+            }
+        }
+        __syncthreads();                                       // slot s and the lists are free again
+    }
+    dbg_stamp(5);
+    // sharded scan: the counts of every rank are in this rank's buffer before the kernel -- and the
+    // copy to the host behind it -- ends (they were sent a whole emit phase ago)
+    if (a.world > 1 && cta == 0) xchg_wait(a);
 }
 
 // CRP_SCAN_LOGISTIC: x -> 1 / (1 + np.exp(x)) over a finished stream, numpy's digits (npexp.cuh)

@@ -106,6 +106,18 @@ def comm_info():
     return r.value, w.value
 
 
+def comm_set_exchange(mode):
+    """'fused' (the scan kernel exchanges the counts itself over peer memory) or 'nccl'; on every rank."""
+    check(lib.crp_comm_set_exchange({"fused": 0, "nccl": 1}[mode]))
+
+
+def comm_exchange_info():
+    """(fused?, why not) of the sharded scans of this communicator"""
+    f, why = C.c_int(0), C.c_char_p()
+    check(lib.crp_comm_exchange_info(C.byref(f), C.byref(why)))
+    return bool(f.value), (why.value or b"").decode()
+
+
 def comm_barrier():
     check(lib.crp_comm_barrier())
 

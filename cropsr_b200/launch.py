@@ -56,35 +56,66 @@ class Rendezvous:
         if self.world == 1:
             return
         addr = addr or os.environ.get("MASTER_ADDR", "127.0.0.1")
-        port = int(port if port is not None else os.environ.get("MASTER_PORT", "29500"))
+        if addr == "localhost":
+            addr = "127.0.0.1"
+        base = int(port if port is not None else os.environ.get("MASTER_PORT", "29500"))
+        # MASTER_PORT itself may be taken: torchrun's agent keeps its own store there.  Rank 0 listens on
+        # the first free port of a fixed sequence derived from it; the others walk the same sequence and
+        # keep the first listener that answers the handshake (so a foreign service on one of the ports,
+        # or a rank 0 that is not up yet, only costs a retry).
+        ports = [base] if port is not None else [1024 + (base + 997 + 61 * i) % 60000 for i in range(16)]
+        hello = ("cropsr-rdv", base, self.world, os.environ.get("TORCHELASTIC_RUN_ID", ""))
         if self.rank == 0:
-            srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
-            srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
-            srv.bind((addr if addr not in ("localhost",) else "127.0.0.1", port))
-            srv.listen(self.world)
+            srv = None
+            for p in ports:
+                try:
+                    srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+                    srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+                    srv.bind((addr, p))
+                    break
+                except OSError:
+                    srv.close()
+                    srv = None
+            if srv is None:
+                raise OSError(f"rendezvous: none of the ports {ports} is free")
+            srv.listen(self.world + 8)
             srv.settimeout(timeout)
             got = {}
             while len(got) < self.world - 1:
                 conn, _ = srv.accept()
                 conn.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
                 conn.settimeout(timeout)
-                r = _recv(conn)
-                got[int(r)] = conn
+                try:
+                    msg = _recv(conn)
+                    if not (isinstance(msg, tuple) and msg[:-1] == hello):
+                        raise ValueError("not a rank of this job")
+                    _send(conn, hello)
+                    got[int(msg[-1])] = conn
+                except Exception:
+                    conn.close()
             srv.close()
             self.peers = [got[r] for r in range(1, self.world)]
         else:
             deadline = time.time() + timeout
-            while True:
-                try:
-                    s = socket.create_connection((addr, port), timeout=5.0)
-                    break
-                except OSError:
+            s = None
+            while s is None:
+                for p in ports:
+                    try:
+                        c = socket.create_connection((addr, p), timeout=2.0)
+                        c.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+                        c.settimeout(10.0)
+                        _send(c, hello + (self.rank,))
+                        if _recv(c) == hello:
+                            s = c
+                            break
+                        c.close()
+                    except Exception:
+                        pass
+                if s is None:
                     if time.time() > deadline:
-                        raise
+                        raise TimeoutError("rendezvous: rank 0 did not answer")
                     time.sleep(0.05)
-            s.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
             s.settimeout(timeout)
-            _send(s, self.rank)
             self.sock = s
 
     def all_gather(self, obj):

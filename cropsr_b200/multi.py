@@ -86,7 +86,9 @@ def _rank_body(rank, world, port, device, tok_shm_name, tok_off, tok_len, guide_
             n = len(got["pos"])
             pos[row0:row0 + n] = got["pos"]
             x[row0:row0 + n] = got["x"] if scored else np.nan
-    timing = rdv.all_gather({"rank": rank, "device": device, **res.timing_detail(), **genome.timing(),
+    fused, why = engine.comm_exchange_info()
+    timing = rdv.all_gather({"rank": rank, "device": device, "fused_exchange": fused, "exchange_note": why,
+                             **res.timing_detail(), **genome.timing(),
                              "positions": int(sum(b - a for _, a, b in mine))})
     res.free()
     genome.free()

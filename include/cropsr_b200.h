@@ -97,6 +97,10 @@ int crp_flush_l2(void);
 int crp_comm_unique_id(uint8_t *id /* [CRP_COMM_ID_BYTES] */);
 int crp_comm_init(int rank, int world, const uint8_t *id);
 int crp_comm_info(int *rank, int *world);           /* 0 / 1 without a communicator */
+/* Exchange of crp_scan_score_sharded: 0 = fused into the kernel when possible (default), 1 = NCCL
+ * all-gather.  Set it on every rank.  crp_comm_exchange_info says what a sharded scan will do. */
+int crp_comm_set_exchange(int mode);
+int crp_comm_exchange_info(int *fused, const char **why);
 /* Device-wide synchronize, then an all-reduce of one word over all ranks, waited for. */
 int crp_comm_barrier(void);
 /* Element-wise max / sum of n host doubles over all ranks, in place (timings, totals). */
@@ -172,10 +176,16 @@ int crp_genome_free(crp_genome *g);
 int crp_scan_score(crp_genome *g, int guide_len, uint32_t flags, crp_result **res);
 /* The same scan on one shard of a genome that is spread over the ranks of crp_comm_init: the
  * kernel writes this shard's per-segment counts as a block of 2 * slots words
- * {plus[0..slots), minus[0..slots)} (slots >= the segments of every rank; unused slots are 0) and
- * an ncclAllGather on the same stream, right behind the kernel, hands every rank the blocks of
- * all ranks.  crp_result_timing then reports kernel + collective, crp_result_timing_detail the
- * kernel alone as well.  Collective: every rank must call it, with the same slots. */
+ * {plus[0..slots), minus[0..slots)} (slots >= the segments of every rank; unused slots are 0),
+ * and every rank ends up with the blocks of all ranks -- the one exchange step of the path.
+ *   fused exchange (default when every rank could map its peers' buffers through CUDA IPC):
+ *     the kernel itself stores its block into every rank's gather buffer over NVLink as soon as
+ *     its count phase is through, raises a flag there, and returns once all blocks have landed
+ *     in its own buffer: the all-gather rides behind the emit phase and costs no launch;
+ *   NCCL exchange (crp_comm_set_exchange(1), CRP_COMM_EXCHANGE=nccl, or no peer mapping):
+ *     an ncclAllGather on the same stream, right behind the kernel.
+ * crp_result_timing reports kernel + exchange either way, crp_result_timing_detail the kernel
+ * alone as well.  Collective: every rank must call it, with the same slots. */
 int crp_scan_score_sharded(crp_genome *g, int guide_len, uint32_t flags, uint32_t slots, crp_result **res);
 /* counts[(rank * 2 + strand) * slots + segment] of the scan above, strand 0 = '+'. */
 int crp_result_gathered_counts(const crp_result *res, uint64_t *counts /* [world][2][slots] */);

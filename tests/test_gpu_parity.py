@@ -233,37 +233,33 @@ def test_full_size_properties(eng):
     g.free()
 
 
-def test_multi_wave_scan_matches_oracle(eng, monkeypatch):
-    """Several count/emit waves (grid barrier between them, per-wave tickets, segment counts
-    accumulated across waves): force 2-tile waves on inputs of 3-7 tiles."""
-    monkeypatch.setenv("CRP_WAVE_TILES", "2")
-    _check_against_oracle(eng, synthetic_fasta(21, [100000, 40000], gc=0.5, lower_frac=0.2), 20)
-    monkeypatch.setenv("CRP_WAVE_TILES", "1")
-    _check_against_oracle(eng, synthetic_fasta(22, [50000], gc=0.6, lower_frac=0.0), 20)
-    monkeypatch.setenv("CRP_STATIC_EIGHTHS", "8")
-    _check_against_oracle(eng, synthetic_fasta(23, [90000], gc=0.5), 20)
-    monkeypatch.setenv("CRP_STATIC_EIGHTHS", "0")
-    _check_against_oracle(eng, synthetic_fasta(23, [90000], gc=0.5), 20)
+def test_static_and_ticketed_tile_dealing_match_oracle(eng, monkeypatch):
+    """The emit phase deals part of the tiles round-robin and the rest through a ticket counter: all
+    static, all ticketed, and the default split give the same streams."""
+    for eighths in ("8", "0", "4"):
+        monkeypatch.setenv("CRP_STATIC_EIGHTHS", eighths)
+        _check_against_oracle(eng, synthetic_fasta(23, [90000, 40000], gc=0.5, lower_frac=0.2), 20)
 
 
 def test_long_count_ranges_and_prefetched_first_tile(eng, monkeypatch):
-    """With few CTAs every CTA counts a long range of tiles (the 6-slot ring of PAM records is
-    refilled several times, by different warps) and its first emit tile is fetched across the
-    grid barrier; on a full-size genome that is the normal case, here 3 and 7 CTAs force it on
-    ~100 tiles.  Also with two waves."""
+    """With few CTAs every CTA counts a long range of tiles: the 6-slot ring of PAM records is
+    refilled many times, by different warps, and ranges longer than 32 tiles are walked in batches
+    with a running prefix (on a multi-Gbp genome that is the normal case: 237 tiles per CTA on the
+    maize-scale config); the first emit tile is fetched across the grid barrier.  3, 7 and 1 CTAs
+    force it on ~100 tiles (1 CTA: four batches, the ring goes round sixteen times)."""
     text = synthetic_fasta(31, [900000, 650000, 37], gc=0.45, lower_frac=0.15, n_frac=0.001)
     monkeypatch.setenv("CRP_SCAN_GRID", "3")
     _check_against_oracle(eng, text, 20)
     monkeypatch.setenv("CRP_SCAN_GRID", "7")
-    monkeypatch.setenv("CRP_WAVE_TILES", "60")
     _check_against_oracle(eng, text, 20)
     monkeypatch.setenv("CRP_STATIC_EIGHTHS", "8")
     _check_against_oracle(eng, text, 20)
-    # one CTA: count ranges of 32 tiles (the ring of 6 PAM slots goes round five times), four waves
-    monkeypatch.delenv("CRP_WAVE_TILES")
     monkeypatch.setenv("CRP_SCAN_GRID", "1")
     monkeypatch.setenv("CRP_STATIC_EIGHTHS", "4")
     _check_against_oracle(eng, text, 20)
+    monkeypatch.setenv("CRP_SCAN_GRID", "2")
+    monkeypatch.setenv("CRP_STATIC_EIGHTHS", "0")
+    _check_against_oracle(eng, synthetic_fasta(32, [1100000], gc=0.5, lower_frac=0.1), 20)     # 68 tiles: 34 per CTA, 32 + 2
 
 
 def test_pipelined_call_equals_plain_scan(eng):
@@ -581,14 +577,16 @@ def test_host_rescorer_equals_crp_rescore(eng):
         genome.free()
 
 
+@pytest.mark.parametrize("exchange", ["fused", "nccl"])
 @pytest.mark.parametrize("n_dev", [2, 3, 8])
-def test_multi_gpu_cli_writes_the_reference_csv(n_dev, manifest, eng, tmp_path):
+def test_multi_gpu_cli_writes_the_reference_csv(n_dev, exchange, manifest, eng, tmp_path, monkeypatch):
     """CROPSR.py --devices 0-(n-1): one process per GPU, contiguous shards, the NCCL all-gather of the
     per-segment counts inside the library, rows placed in reference order -- the CSV must be the
     unmodified reference's, byte for byte.  Needs n GPUs on the box (gpurun --gpus n)."""
     from cropsr_b200 import pipeline
     if eng.device_count() < n_dev:
         pytest.skip(f"needs {n_dev} GPUs")
+    monkeypatch.setenv("CRP_COMM_EXCHANGE", exchange)      # read by crp_comm_init in every rank (workers inherit it)
     for name in ("multi3", "sample", "mid50k_t5", "multi3_c20", "edge_fmt", "empty_records", "single_candidate"):
         case = manifest["cases"][name]
         out = tmp_path / f"{name}.csv"
@@ -598,6 +596,10 @@ def test_multi_gpu_cli_writes_the_reference_csv(n_dev, manifest, eng, tmp_path):
                                   chunk_rows=case.get("chunk"), devices=list(range(n_dev)))
         assert out.read_bytes().decode() == golden_csv(name), name
         assert len(stats["ranks"]) == n_dev
+        if exchange == "nccl":
+            assert not any(r["fused_exchange"] for r in stats["ranks"])
+        else:       # fused wherever the peers could be mapped; the note says why not otherwise
+            assert all(r["fused_exchange"] or r["exchange_note"] for r in stats["ranks"]), stats["ranks"]
 
 
 def _gpu_table_digest(eng, workload, limit=None):
