@@ -1,6 +1,7 @@
 """One genome on several GPUs of one box: one process per GPU, contiguous tile-aligned shards
-(shard.plan), ONE exchange step -- the NCCL all-gather of the per-segment candidate counts that
-crp_scan_score_sharded queues behind its kernel -- and rows written in the reference's order.
+(shard.plan), ONE exchange step -- the all-gather of the per-segment candidate counts that
+crp_scan_score_sharded performs (fused into the scan kernel over peer memory, or an NCCL
+all-gather behind it) -- and rows written in the reference's order.
 
 The reference has no counterpart (CROPSR.py:409 loops over the chromosomes in one process); what
 is preserved is its output order: token by token, '+' hits by ascending t, then '-' hits
@@ -55,6 +56,7 @@ def _rank_body(rank, world, port, device, tok_shm_name, tok_off, tok_len, guide_
     for k, a, b in mine:
         genome.add_segment(k, buf[tok_off[k]:tok_off[k] + tok_len[k]], a, b)
     genome.commit()
+    engine.comm_barrier()                                          # shards differ in size: start the collective scan together
     res = genome.scan_sharded(slots, guide_len, flags)
     gathered = res.gathered_counts()                               # [world, 2, slots]: the all-gather's result
     counts = [(gathered[r, 0, :len(plans[r])], gathered[r, 1, :len(plans[r])]) for r in range(world)]
@@ -94,7 +96,7 @@ def _rank_body(rank, world, port, device, tok_shm_name, tok_off, tok_len, guide_
     genome.free()
     rdv.barrier()                                                  # every rank's rows are in place
     if rank:
-        del pos, x, buf
+        del pos, x, buf, got
         pos_shm.close()
         x_shm.close()
         tok_shm.close()
@@ -149,9 +151,12 @@ class MultiScanOutput:
         self._pos = self._x = None
         for shm in self._shm:
             try:
-                shm.close()
-                shm.unlink()
+                shm.unlink()                    # the name goes first: a view someone still holds only delays the unmap
             except Exception:
+                pass
+            try:
+                shm.close()
+            except BufferError:
                 pass
         self._shm = ()
 

@@ -296,6 +296,7 @@ def run_cas9(fasta, gff, output="data.csv", guide_len=20, verbose=False, blas_th
         write_side_output(side_output, tokens, scan, gff_frame, flank, formatted_path, annotation_info)
     stats = {"tokens": len(tokens), "candidates": len(table), "rows": rows_written,
              "scan_ms": scan.scan_ms(), **scan.timing()}
+    t_plus = x_plus = t_minus = x_minus = None          # views into the scan's row arrays
     scan.free()
     if verbose:
         out(f"The output file has been generated at {output}")
