@@ -194,6 +194,9 @@ class Shard:
                 t = buf.array
             self.host_tokens[k] = t
         self.my_bases = sum(b - a for _, a, b in self.mine)
+        if self.my_bases >= (1 << 32) - (1 << 20):
+            raise SystemExit(f"{workload}: {self.my_bases} positions per GPU exceed one genome handle; run it on more GPUs "
+                             "(the product path spreads such genomes over several handles, pipeline.scan_token_bytes)")
         self.genome = self.build()
 
     def build(self):

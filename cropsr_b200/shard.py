@@ -7,44 +7,61 @@ the library stages the halo around every segment itself.  The only exchange is
 an all-gather of per-segment, per-strand candidate counts, from which every
 rank derives the global position of its candidates in reference order
 (token order; inside a token all '+' by ascending t, then all '-').
-Pure index arithmetic -- unit-tested on the CPU (tests/test_shard.py) and
-under gloo with world_size 2.
+Pure index arithmetic -- unit-tested on the CPU (tests/test_host_logic.py) and
+under gloo with world_size 2 and 3 (tests/test_multi_rank_gloo.py).
 """
 from .engine import TILE
 
 
 def plan(token_lengths, world_size, granule=TILE):
     """-> per rank: list of (token_id, begin, end) segments, in genome order.
-    Rank r owns the positions [r*share, (r+1)*share) of the concatenated genome,
-    with boundaries moved to multiples of `granule` inside a token."""
+    Every rank gets one contiguous run of the genome; the runs are balanced by TILES, not by
+    positions (a token's last tile is scanned whole even when it is half empty, so 10,000 short
+    scaffolds weigh more than one chromosome of the same length), and boundaries inside a token
+    sit on multiples of `granule`."""
+    padded = [(n + granule - 1) // granule * granule for n in token_lengths]
     total = sum(token_lengths)
-    starts = []
-    acc = 0
-    for n in token_lengths:
+    total_padded = sum(padded)
+    starts, pstarts = [], []
+    acc = pacc = 0
+    for n, pn in zip(token_lengths, padded):
         starts.append(acc)
+        pstarts.append(pacc)
         acc += n
-    # cut points in concatenated coordinates, snapped down to a granule inside their token
+        pacc += pn
+    # cut points in padded coordinates, snapped down to a granule, mapped back to real positions
     cuts = [0]
+    k = 0
     for r in range(1, world_size):
-        target = total * r // world_size
-        k = 0
-        while k + 1 < len(token_lengths) and starts[k + 1] <= target:
+        target = total_padded * r // world_size
+        while k + 1 < len(token_lengths) and pstarts[k + 1] <= target:
             k += 1
+        cut = 0
         if token_lengths:
-            inside = target - starts[k]
+            inside = target - pstarts[k]
             inside -= inside % granule
-            target = starts[k] + inside
-        cuts.append(max(target, cuts[-1]))
+            cut = starts[k] + min(inside, token_lengths[k])
+        cuts.append(max(cut, cuts[-1]))
     cuts.append(total)
-    out = []
-    for r in range(world_size):
-        lo, hi = cuts[r], cuts[r + 1]
-        segs = []
-        for k, n in enumerate(token_lengths):
-            a, b = max(lo, starts[k]), min(hi, starts[k] + n)
-            if a < b or (n == 0 and lo <= starts[k] < hi) :
-                segs.append((k, a - starts[k], b - starts[k]))
-        out.append(segs)
+    out = [[] for _ in range(world_size)]
+    r = 0
+    for k, n in enumerate(token_lengths):
+        s, e = starts[k], starts[k] + n
+        if n == 0:                                   # an empty token goes to the rank whose run holds its position
+            while r + 1 < world_size and cuts[r + 1] <= s and cuts[r + 1] < total:
+                r += 1
+            out[r].append((k, 0, 0))
+            continue
+        while r + 1 < world_size and cuts[r + 1] <= s:
+            r += 1
+        q = r
+        while True:                                  # the token may span several ranks
+            a, b = max(cuts[q], s), min(cuts[q + 1], e)
+            if a < b:
+                out[q].append((k, a - s, b - s))
+            if cuts[q + 1] >= e or q + 1 >= world_size:
+                break
+            q += 1
     return out
 
 

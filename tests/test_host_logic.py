@@ -323,3 +323,28 @@ def test_id_stream_draws_ahead_what_get_id_would_draw(built_lib):
         st.next(11)
     st.close()                                   # drains: the state is the one after all six draws
     assert np.array_equal(np.random.randint(0, 1000, 4), after_want)
+
+
+def test_shard_plan_tiles_the_genome_and_balances_tiles(built_lib):
+    """shard.plan: every position of every token in exactly one segment, segments in genome order,
+    cuts on granule multiples, ranks balanced by TILES (20,000 scaffolds weigh their padded length)."""
+    import random
+    from cropsr_b200 import shard
+    random.seed(1)
+    for _ in range(3000):
+        lengths = [random.choice([0, 1, 5, 127, 128, 129, 1000, 5000]) for _ in range(random.randint(0, 12))]
+        world, granule = random.randint(1, 9), 128
+        plans = shard.plan(lengths, world, granule)
+        assert len(plans) == world
+        pos = [0] * len(lengths)
+        seen, last = set(), -1
+        for k, a, b in (seg for segs in plans for seg in segs):
+            assert k >= last and a == pos[k] and b <= lengths[k] and a % granule == 0
+            last, pos[k] = k, b
+            seen.add(k)
+        assert pos == lengths and seen == set(range(len(lengths)))
+        tiles = [sum(-(-(b - a) // granule) for _, a, b in p) for p in plans]
+        assert max(tiles, default=0) <= -(-sum(-(-n // granule) for n in lengths) // world) + 2 + len(lengths)
+    big = [80_000_000] * 6 + [random.randint(10_000, 500_000) for _ in range(4000)]
+    tiles = [sum(-(-(b - a) // shard.TILE) for _, a, b in p) for p in shard.plan(big, 8)]
+    assert max(tiles) - min(tiles) <= 2
