@@ -1526,6 +1526,129 @@ int crp_result_extras(const crp_result *res, uint32_t segment, char strand, uint
     return rc;
 }
 
+/* The same for ALL segments of one strand stream in one call: one launch per segment queued back to
+ * back, one copy per output array, one wait -- a genome of 20,000 scaffolds costs 20,000 launches, not
+ * 120,000 host round trips. */
+int crp_result_extras_strand(const crp_result *res, char strand, uint32_t flank, uint8_t *gc, uint8_t *flags,
+                             uint8_t *run, uint32_t *cut, uint32_t *flank_lo, uint32_t *flank_hi) {
+    if (!res) return fail(CRP_ERR_ARG, "res is NULL");
+    if (int rc = need_ctx()) return rc;
+    if (strand != '+' && strand != '-') return fail(CRP_ERR_ARG, "strand must be '+' or '-'");
+    if (res->guide_len != 20) return fail(CRP_ERR_STATE, "extras are defined for guide_len 20 (30-base windows) only");
+    const int s = strand == '+' ? 0 : 1;
+    const uint64_t n = s == 0 ? res->n_plus : res->n_minus;
+    if (n == 0) return 0;
+    const crp_genome *g = res->g;
+    const std::vector<uint64_t> &cnt = s == 0 ? res->seg_plus : res->seg_minus;
+    cudaStream_t st = res->st;
+    uint8_t *d8 = nullptr;
+    uint32_t *d32 = nullptr;
+    CUDA_TRY(dev_alloc(&d8, 3 * n, st));
+    if (dev_alloc(&d32, 3 * n * sizeof(uint32_t), st) != cudaSuccess) {
+        dev_free(d8, st);
+        return fail(CRP_ERR_NOMEM, "cudaMalloc failed");
+    }
+    uint64_t first = 0;
+    for (size_t sgi = 0; sgi < cnt.size(); ++sgi) {
+        const uint64_t m = cnt[sgi];
+        if (m) {
+            const Segment &sg = g->segs[sgi];
+            ExtrasArgs a;
+            a.records = g->records;
+            a.pos = res->pos[s] + first;
+            a.n = m;
+            a.first_tile = sg.first_tile;
+            a.seg_begin = (uint32_t)sg.begin;
+            a.L = (uint32_t)sg.token_len;
+            a.flank = flank;
+            a.minus = s;
+            a.gc = d8 + first;
+            a.flags = d8 + n + first;
+            a.run = d8 + 2 * n + first;
+            a.cut = d32 + first;
+            a.flank_lo = d32 + n + first;
+            a.flank_hi = d32 + 2 * n + first;
+            k_extras<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(a);
+            g_ctx.launches++;
+        }
+        first += m;
+    }
+    int rc = 0;
+    auto back = [&](void *dst, const void *src, size_t bytes) {
+        if (dst && !rc && cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            rc = fail(CRP_ERR_CUDA, "D2H of extras failed");
+    };
+    back(gc, d8, n);
+    back(flags, d8 + n, n);
+    back(run, d8 + 2 * n, n);
+    back(cut, d32, n * 4);
+    back(flank_lo, d32 + n, n * 4);
+    back(flank_hi, d32 + 2 * n, n * 4);
+    if (!rc && cudaStreamSynchronize(st) != cudaSuccess)
+        rc = fail(CRP_ERR_CUDA, "extras kernels failed: %s", cudaGetErrorString(cudaGetLastError()));
+    dev_free(d8, st);
+    dev_free(d32, st);
+    return rc;
+}
+
+/* Annotation of a whole strand stream: the intervals of segment s are [iv_offset[s], iv_offset[s + 1]) of
+ * start / end (each segment's run sorted by start); feature[i] is an index into that segment's run, or -1. */
+int crp_result_annotate_strand(const crp_result *res, char strand, const uint64_t *iv_offset, const uint32_t *start,
+                               const uint32_t *end, int32_t *feature) {
+    if (!res) return fail(CRP_ERR_ARG, "res is NULL");
+    if (int rc = need_ctx()) return rc;
+    if (strand != '+' && strand != '-') return fail(CRP_ERR_ARG, "strand must be '+' or '-'");
+    const int s = strand == '+' ? 0 : 1;
+    const uint64_t n = s == 0 ? res->n_plus : res->n_minus;
+    if (n == 0) return 0;
+    if (!feature || !iv_offset) return fail(CRP_ERR_ARG, "NULL argument");
+    const std::vector<uint64_t> &cnt = s == 0 ? res->seg_plus : res->seg_minus;
+    const uint64_t n_iv = iv_offset[cnt.size()];
+    if (n_iv && (!start || !end)) return fail(CRP_ERR_ARG, "NULL interval arrays");
+    std::vector<uint32_t> host(3 * (size_t)n_iv + 1);
+    for (size_t sgi = 0; sgi < cnt.size(); ++sgi) {
+        uint32_t running = 0;
+        if (iv_offset[sgi + 1] < iv_offset[sgi]) return fail(CRP_ERR_ARG, "iv_offset must not decrease");
+        for (uint64_t j = iv_offset[sgi]; j < iv_offset[sgi + 1]; ++j) {
+            if (j > iv_offset[sgi] && start[j] < start[j - 1]) return fail(CRP_ERR_ARG, "intervals must be sorted by start");
+            if (end[j] < start[j]) return fail(CRP_ERR_ARG, "interval %llu has end < start", (unsigned long long)j);
+            running = end[j] > running ? end[j] : running;
+            host[j] = start[j];
+            host[n_iv + j] = end[j];
+            host[2 * (size_t)n_iv + j] = running;
+        }
+    }
+    cudaStream_t st = res->st;
+    uint32_t *d_iv = nullptr;
+    int32_t *d_f = nullptr;
+    CUDA_TRY(dev_alloc(&d_iv, host.size() * sizeof(uint32_t), st));
+    if (dev_alloc(&d_f, n * sizeof(int32_t), st) != cudaSuccess) {
+        dev_free(d_iv, st);
+        return fail(CRP_ERR_NOMEM, "cudaMalloc failed");
+    }
+    int rc = 0;
+    if (cudaMemcpyAsync(d_iv, host.data(), host.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st) != cudaSuccess)
+        rc = fail(CRP_ERR_CUDA, "H2D of intervals failed");
+    uint64_t first = 0;
+    for (size_t sgi = 0; sgi < cnt.size() && !rc; ++sgi) {
+        const uint64_t m = cnt[sgi];
+        if (m) {
+            const uint64_t o = iv_offset[sgi];
+            k_annotate<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(res->pos[s] + first, m, s, d_iv + o, d_iv + n_iv + o,
+                                                                   d_iv + 2 * (size_t)n_iv + o,
+                                                                   (uint32_t)(iv_offset[sgi + 1] - o), d_f + first);
+            g_ctx.launches++;
+        }
+        first += m;
+    }
+    if (!rc && (cudaMemcpyAsync(feature, d_f, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaStreamSynchronize(st) != cudaSuccess))
+        rc = fail(CRP_ERR_CUDA, "annotate failed: %s", cudaGetErrorString(cudaGetLastError()));
+    dev_free(d_iv, st);
+    dev_free(d_f, st);
+    return rc;
+}
+
 int crp_primer_windows(const crp_genome *g, uint64_t n, const uint32_t *segment, const uint32_t *lo, const uint32_t *hi,
                        const crp_primer_params *prm, uint32_t *n_fwd, uint32_t *n_rev, uint64_t *n_pairs,
                        uint16_t *first, uint8_t *status) {

@@ -467,6 +467,29 @@ class ScanResult:
                                     ptr(out["run"]), ptr(out["cut"]), ptr(out["flank_lo"]), ptr(out["flank_hi"])))
         return out
 
+    def extras_strand(self, strand, flank=200):
+        """extras() of every candidate of one strand stream (all segments), in stream order"""
+        n = int(self.n_plus if strand == "+" else self.n_minus)
+        out = {k: np.empty(n, np.uint8) for k in ("gc", "flags", "run")}
+        out.update({k: np.empty(n, np.uint32) for k in ("cut", "flank_lo", "flank_hi")})
+        ptr = lambda a: a.ctypes.data if len(a) else None
+        check(lib.crp_result_extras_strand(self._h, strand.encode(), int(flank), ptr(out["gc"]), ptr(out["flags"]),
+                                           ptr(out["run"]), ptr(out["cut"]), ptr(out["flank_lo"]), ptr(out["flank_hi"])))
+        return out
+
+    def annotate_strand(self, strand, iv_offset, start, end):
+        """annotate() of a whole strand stream: intervals of segment s are [iv_offset[s], iv_offset[s+1])"""
+        iv_offset = np.ascontiguousarray(iv_offset, dtype=np.uint64)
+        start = np.ascontiguousarray(start, dtype=np.uint32)
+        end = np.ascontiguousarray(end, dtype=np.uint32)
+        n = int(self.n_plus if strand == "+" else self.n_minus)
+        out = np.empty(n, np.int32)
+        if n:
+            check(lib.crp_result_annotate_strand(self._h, strand.encode(), iv_offset.ctypes.data,
+                                                 start.ctypes.data if len(start) else None,
+                                                 end.ctypes.data if len(end) else None, out.ctypes.data))
+        return out
+
     def annotate(self, seg, strand, start, end):
         """Index of the innermost interval [start, end] (inclusive token coordinates,
         sorted by start) containing each candidate's cut site, -1 if none."""

@@ -193,21 +193,33 @@ def write_side_output(path, tokens, scan, gff_frame, flank, formatted_path, anno
     with open(path, "w", newline="") as f:
         csv.writer(f, delimiter="\t").writerow(columns)
     # GFF rows are looked up per DISTINCT feature, then spread over the candidates: whole columns,
-    # one strand of one token at a time, no Python work per candidate
+    # no Python work per candidate.  The device is asked once per strand of a genome handle -- every
+    # segment's extras / annotation / primer windows in one call each -- so 20,000 scaffolds cost a
+    # handful of host round trips; the rows are then put back into the reference's order
+    # (token by token, '+' then '-').
     gff_feature = gff_frame["feature"].to_numpy(dtype=object)
     gff_attr = gff_frame["attributes"].to_numpy(dtype=object)
-    for k, key in enumerate(tokens.keys()):
-        iv = ivs[k]
-        genome, result, seg = scan.locate(k)
-        for strand in "+-":
-            pos = result.fetch_segment(seg, strand, want=("pos",))["pos"]
-            n = len(pos)
-            if n == 0:
-                continue
-            ex = result.extras(seg, strand, flank)
-            feat = result.annotate(seg, strand, iv["start"], iv["end"])
-            pr = primers.design_windows(genome, np.full(n, seg, np.uint32), ex["flank_lo"], ex["flank_hi"])
-            rows = np.where(feat >= 0, iv["row"][np.maximum(feat, 0)] if len(iv["row"]) else -1, -1)
+    keys = list(tokens.keys())
+    for genome, result, first, cnt in scan.parts:
+        part_ivs = ivs[first:first + cnt]
+        iv_off = np.concatenate(([0], np.cumsum([len(iv["start"]) for iv in part_ivs]))).astype(np.uint64)
+        iv_start = np.concatenate([iv["start"] for iv in part_ivs]) if cnt else np.empty(0, np.uint32)
+        iv_end = np.concatenate([iv["end"] for iv in part_ivs]) if cnt else np.empty(0, np.uint32)
+        iv_row = np.concatenate([np.asarray(iv["row"], dtype=np.int64) for iv in part_ivs]) if cnt else np.empty(0, np.int64)
+        cols = {}
+        for strand, seg_cnt in (("+", result.seg_plus), ("-", result.seg_minus)):
+            seg_cnt = seg_cnt.astype(np.int64)
+            n = int(seg_cnt.sum())
+            seg_of = np.repeat(np.arange(cnt, dtype=np.int64), seg_cnt)
+            pos = result.fetch(strand, want=("pos",))["pos"]
+            ex = result.extras_strand(strand, flank)
+            feat = result.annotate_strand(strand, iv_off, iv_start, iv_end)
+            pr = primers.design_windows(genome, seg_of.astype(np.uint32), ex["flank_lo"], ex["flank_hi"])
+            if n and len(iv_row):
+                at = np.minimum(np.maximum(feat, 0) + iv_off[seg_of].astype(np.int64), len(iv_row) - 1)
+                rows = np.where(feat >= 0, iv_row[at], -1)
+            else:
+                rows = np.full(n, -1, dtype=np.int64)
             ft = np.full(n, "", dtype=object)
             fa = np.full(n, "", dtype=object)
             ai = np.full(n, "", dtype=object)
@@ -219,22 +231,25 @@ def write_side_output(path, tokens, scan, gff_frame, flank, formatted_path, anno
                 ai[hit] = np.array([annotate.lookup_annotation_info(info, a) for a in gff_attr[uniq]], dtype=object)[inv]
             fl = ex["flags"].astype(np.int64)
             ok = pr["status"] == 0
-            first = pr["first"].astype(np.int64)
-            has_pair = ok & (first[:, 0] != 0xFFFF)
+            firstp = pr["first"].astype(np.int64)
+            has_pair = ok & (firstp[:, 0] != 0xFFFF) if n else np.zeros(0, bool)
             pair = np.full(n, "", dtype=object)
             if has_pair.any():
-                fp = first[has_pair]
-                pair[has_pair] = [f"{a}+{b}/{c}+{d}" for a, b, c, d in fp.tolist()]
+                pair[has_pair] = [f"{a}+{b}/{c}+{d}" for a, b, c, d in firstp[has_pair].tolist()]
             blank_unless_ok = lambda a: np.where(ok, a.astype(np.int64).astype(str).astype(object), "")
-            frame = pd.DataFrame({
-                "chromosome": key[1:], "strand": strand, "pam_pos": pos.astype(np.int64), "cutsite": ex["cut"].astype(np.int64),
+            chrom = np.array([k[1:] for k in keys[first:first + cnt]], dtype=object)[seg_of] if n else np.empty(0, object)
+            cols[strand] = (seg_of, pd.DataFrame({
+                "chromosome": chrom, "strand": strand, "pam_pos": pos.astype(np.int64), "cutsite": ex["cut"].astype(np.int64),
                 "gc": ex["gc"].astype(np.int64), "poly_t": fl & 1, "homopolymer": (fl >> 1) & 1, "low_gc": (fl >> 2) & 1,
                 "unscored_base": (fl >> 3) & 1, "longest_run": ex["run"].astype(np.int64),
                 "flank_start": ex["flank_lo"].astype(np.int64), "flank_end": ex["flank_hi"].astype(np.int64),
                 "feature_type": ft, "feature_attributes": fa, "fwd_primers": blank_unless_ok(pr["n_fwd"]),
                 "rev_primers": blank_unless_ok(pr["n_rev"]), "primer_pairs": blank_unless_ok(pr["n_pairs"]),
-                "first_pair": pair, "annotation_info": ai}, columns=columns)
-            frame.to_csv(path, sep="\t", mode="a", header=False, index=False, lineterminator="\r\n")
+                "first_pair": pair, "annotation_info": ai}, columns=columns))
+        # reference order: per token its '+' rows, then its '-' rows -- a stable sort on (token, strand)
+        frame = pd.concat([cols["+"][1], cols["-"][1]], ignore_index=True)
+        order = np.argsort(np.concatenate((2 * cols["+"][0], 2 * cols["-"][0] + 1)), kind="stable")
+        frame.iloc[order].to_csv(path, sep="\t", mode="a", header=False, index=False, lineterminator="\r\n")
 
 
 def run_cas9(fasta, gff, output="data.csv", guide_len=20, verbose=False, blas_threads=1,

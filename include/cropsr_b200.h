@@ -246,11 +246,21 @@ int crp_rescore(const crp_genome *g, uint64_t n, const uint32_t *segment, const 
 int crp_result_extras(const crp_result *res, uint32_t segment, char strand, uint32_t flank,
                       uint8_t *gc, uint8_t *flags, uint8_t *run,
                       uint32_t *cut, uint32_t *flank_lo, uint32_t *flank_hi);
+/* The same for every segment of one strand stream in one call (arrays of crp_result_totals()
+ * entries, stream order): one launch per segment queued back to back, one copy per array, one wait. */
+int crp_result_extras_strand(const crp_result *res, char strand, uint32_t flank,
+                             uint8_t *gc, uint8_t *flags, uint8_t *run,
+                             uint32_t *cut, uint32_t *flank_lo, uint32_t *flank_hi);
 /* feature[i] = index of the innermost interval [start, end] (inclusive, token
  * coordinates, sorted by start) that contains candidate i's cut site, or -1:
  * a binary search per candidate in device memory. */
 int crp_result_annotate(const crp_result *res, uint32_t segment, char strand, uint32_t n_intervals,
                         const uint32_t *start, const uint32_t *end, int32_t *feature);
+
+/* The same for a whole strand stream: the intervals of segment s are [iv_offset[s], iv_offset[s+1])
+ * of start / end (iv_offset has num_segments + 1 entries); feature[i] indexes its segment's run. */
+int crp_result_annotate_strand(const crp_result *res, char strand, const uint64_t *iv_offset,
+                               const uint32_t *start, const uint32_t *end, int32_t *feature);
 
 /* crispr_id characters: replaces get_id() (CROPSR.py:316-318: np.random.choice of 36 characters,
  * [n, 7]) value for value on numpy's legacy MT19937 generator -- the caller passes the state of

@@ -654,3 +654,52 @@ def test_whole_candidate_table_of_larger_configs_equals_oracle_digest(eng, workl
     d = _gpu_table_digest(eng, workload)
     assert (d.tokens, d.candidates) == (want["tokens"], want["candidates"])
     assert d.hexdigest() == want["sha256"]
+
+
+def test_many_scaffolds_cli_and_batched_side_outputs(eng, tmp_path):
+    """configs[4] shape in small through the whole CLI: 1,500 records, most of them shorter than one
+    window, a few with candidates -- the cumulative re-emission (CROPSR.py:407,442) then writes ~10^5 rows.
+    Byte-identical to the oracle; and the whole-strand side-output calls (one per strand instead of one
+    per segment) return what the per-segment calls return."""
+    import io
+    from cropsr_b200 import ingest, pipeline
+    rng = np.random.default_rng(91)
+    lengths = [int(x) for x in rng.integers(5, 29, size=1500)]
+    for k in rng.choice(1500, size=30, replace=False):
+        lengths[int(k)] = int(rng.integers(150, 400))
+    text = synthetic_fasta(92, lengths, gc=0.5, lower_frac=0.2, n_frac=0.0, width=60)
+    fa = tmp_path / "scaffolds.fa"
+    with open(fa, "w", newline="") as f:
+        f.write(text)
+    out = tmp_path / "out.csv"
+    np.random.seed(5)
+    stats = pipeline.run_cas9(str(fa), fixture_path("sample_genome.gff"), str(out), 20, False, 1, str(tmp_path / "time.txt"),
+                              out=lambda *a: None)
+    np.random.seed(5)
+    want = oracle.run_to_string(text, 20, "model", 1)
+    assert out.read_bytes().decode() == want
+    assert stats["tokens"] == 1500 and stats["rows"] > 20 * stats["candidates"]
+    # whole-strand calls == per-segment calls
+    tokens = ingest.fasta_text_to_tokens(text)
+    genome, result, _ = pipeline.scan_tokens(tokens, 20)
+    try:
+        n_seg = len(tokens)
+        ivs = [(np.sort(rng.integers(0, max(len(t), 1), size=3)).astype(np.uint32)) for t in tokens.values()]
+        iv_off = np.arange(0, 3 * n_seg + 1, 3, dtype=np.uint64)
+        start = np.concatenate(ivs)
+        end = start + np.uint32(40)
+        for strand in "+-":
+            whole = result.extras_strand(strand, 200)
+            feat = result.annotate_strand(strand, iv_off, start, end)
+            off = result.off_plus if strand == "+" else result.off_minus
+            for seg in range(n_seg):
+                a, b = int(off[seg]), int(off[seg + 1])
+                if a == b:
+                    continue
+                one = result.extras(seg, strand, 200)
+                for key in one:
+                    assert np.array_equal(whole[key][a:b], one[key]), (seg, strand, key)
+                assert np.array_equal(feat[a:b], result.annotate(seg, strand, start[3 * seg:3 * seg + 3], end[3 * seg:3 * seg + 3]))
+    finally:
+        result.free()
+        genome.free()
