@@ -194,27 +194,59 @@ class Shard:
                 t = buf.array
             self.host_tokens[k] = t
         self.my_bases = sum(b - a for _, a, b in self.mine)
-        if self.my_bases >= (1 << 32) - (1 << 20):
-            raise SystemExit(f"{workload}: {self.my_bases} positions per GPU exceed one genome handle; run it on more GPUs "
-                             "(the product path spreads such genomes over several handles, pipeline.scan_token_bytes)")
-        self.genome = self.build()
+        # one genome handle addresses 2^32 positions: a bigger shard (10 Gbp on one GPU) becomes several
+        # handles scanned back to back, exactly as the product path does (pipeline.scan_token_bytes)
+        self.groups, acc = [[]], 0
+        for seg in self.mine:
+            n = seg[2] - seg[1]
+            if self.groups[-1] and acc + n > (1 << 31):
+                self.groups.append([])
+                acc = 0
+            self.groups[-1].append(seg)
+            acc += n
+        if len(self.groups) > 1 and world > 1:
+            raise SystemExit(f"{workload}: {self.my_bases} positions per GPU need several genome handles; the sharded "
+                             "scan of this benchmark takes one per rank -- run it on more GPUs")
+        self.genomes = [self.build(g) for g in self.groups]
+        self.genome = self.genomes[0]
 
-    def build(self):
+    def build(self, group=None):
         g = self.engine.Genome()
-        for k, a, b in self.mine:
+        for k, a, b in (self.mine if group is None else group):
             g.add_segment(k, self.host_tokens[k], a, b)
         return g.commit()
 
     def scan(self):
         if self.world > 1:
             return self.genome.scan_sharded(self.slots, 20)
-        return self.genome.scan(20)
+        if len(self.genomes) == 1:
+            return self.genome.scan(20)
+        return _ManyResults([g.scan(20) for g in self.genomes])
 
     def free(self):
-        self.genome.free()
+        for g in self.genomes:
+            g.free()
         for b in self._pinned:
             b.free()
         self._pinned, self.host_tokens = [], {}
+
+
+class _ManyResults:
+    """the scans of the several genome handles of one oversized shard, timed as one step"""
+
+    def __init__(self, results):
+        self.results = results
+        self.n_plus = sum(r.n_plus for r in results)
+        self.n_minus = sum(r.n_minus for r in results)
+
+    def timing_detail(self):
+        ds = [r.timing_detail() for r in self.results]
+        return {"kernel_ms": sum(d["kernel_ms"] for d in ds), "total_ms": sum(d["total_ms"] for d in ds),
+                "launches": sum(d["launches"] for d in ds) - len(ds) + 1}
+
+    def free(self):
+        for r in self.results:
+            r.free()
 
 
 def time_scans(engine, sh, steps, warmup, sampler_index=None):
@@ -324,7 +356,7 @@ def main():
                 "what": "concurrent pinned H2D + D2H cudaMemcpyAsync of exactly the e2e byte counts on every rank, no kernels"}
     if arena is not None:
         arena.free()
-    g = sh.build()                   # a warm commit (the first one of a process pays lazy module loading)
+    g = sh.build(sh.groups[0])       # a warm commit (the first one of a process pays lazy module loading)
     ingest_timing = g.timing()
     g.free()
 
@@ -428,7 +460,7 @@ def time_scans_local(engine, sh, steps, warmup):
     for i in range(warmup + steps):
         engine.flush_l2()
         engine.device_synchronize()
-        res = sh.genome.scan(20)
+        res = sh.scan() if sh.world == 1 else sh.genome.scan(20)
         if i >= warmup:
             d = res.timing_detail()
             total_ms.append(d["total_ms"])

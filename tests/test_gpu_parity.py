@@ -587,7 +587,10 @@ def test_multi_gpu_cli_writes_the_reference_csv(n_dev, exchange, manifest, eng, 
     if eng.device_count() < n_dev:
         pytest.skip(f"needs {n_dev} GPUs")
     monkeypatch.setenv("CRP_COMM_EXCHANGE", exchange)      # read by crp_comm_init in every rank (workers inherit it)
-    for name in ("multi3", "sample", "mid50k_t5", "multi3_c20", "edge_fmt", "empty_records", "single_candidate"):
+    names = ("multi3", "sample", "mid50k_t5", "multi3_c20", "edge_fmt", "empty_records", "single_candidate")
+    if n_dev > 3:           # every case spawns n_dev processes (CUDA context + NCCL init each): keep the big boxes short
+        names = ("multi3", "sample", "empty_records")
+    for name in names:
         case = manifest["cases"][name]
         out = tmp_path / f"{name}.csv"
         np.random.seed(case["seed"])
