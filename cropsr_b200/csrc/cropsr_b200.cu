@@ -1139,7 +1139,10 @@ static int scan_enqueue(crp_genome *g, int guide_len, uint32_t flags, crp_result
 }
 
 // Wait for the scan, read the counts; run it again with exact capacity if the guess was short.
-static int scan_finish(crp_genome *g, crp_result *r) {
+static int scan_finish(crp_genome *g, crp_result *r, cudaStream_t post = nullptr) {
+    // post: the stream the caller will read the rows on (crp_scan_segments: its row-copy stream).  The
+    // optional logistic pass goes there -- the genome's own stream may already hold the H2D, pack and
+    // scan of later segments, and a pass queued behind them would hold this segment's rows back.
     const uint32_t n_seg = (uint32_t)g->segs.size();
     for (int attempt = 0; attempt < 2; ++attempt) {
         if (cudaError_t e = cudaEventSynchronize(r->ev[2]))   // not the stream: it may already hold later segments
@@ -1183,12 +1186,12 @@ static int scan_finish(crp_genome *g, crp_result *r) {
         for (int s = 0; s < 2; ++s)
             if (n[s]) {
                 const uint64_t want = (n[s] + 255) / 256, cap = (uint64_t)g_ctx.sm_count * 16;
-                k_logistic<<<(unsigned)(want < cap ? want : cap), 256, 0, r->st>>>(r->x[s], n[s]);
+                k_logistic<<<(unsigned)(want < cap ? want : cap), 256, 0, post ? post : r->st>>>(r->x[s], n[s]);
                 g_ctx.launches++;
             }
         CUDA_TRY(cudaGetLastError());
-        // whoever reads the streams from another stream (crp_scan_segments) orders itself after this event
-        CUDA_TRY(cudaEventRecord(r->ev[2], r->st));
+        // whoever reads the streams from yet another stream orders itself after this event
+        CUDA_TRY(cudaEventRecord(r->ev[2], post ? post : r->st));
     }
     return 0;
 }
@@ -1385,71 +1388,92 @@ int crp_scan_segments(uint32_t n_segments, const crp_segment_desc *segments, int
     if (!g_ctx.lanes[0])
         for (int i = 0; i < kLanes; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.lanes[i], cudaStreamNonBlocking));
     Trace tr("scan_segments");
-    std::vector<crp_genome *> gs(n_segments, nullptr);
-    std::vector<crp_result *> rs(n_segments, nullptr);
-    int rc = 0;
-    uint64_t off[2] = {0, 0};
-    float ms = 0.f;
-    bool overflow = false;
-    // Segments are enqueued AHEAD of the one whose counts the host waits for (its rows can only be
-    // placed once the counts of every earlier segment are known): up to kAheadBytes of tokens, at
-    // least two segments, so that the host-to-device copy engine always has the next token queued.
-    // The rows leave on a stream of their own: a lane may already hold later segments.
-    constexpr uint64_t kAheadBytes = 512ull << 20;
-    if (!g_ctx.lane_out) CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.lane_out, cudaStreamNonBlocking));
-    auto finish = [&](uint32_t k) -> int {
-        if (int e = scan_finish(gs[k], rs[k])) return e;
-        n_plus[k] = rs[k]->n_plus;
-        n_minus[k] = rs[k]->n_minus;
-        ms += rs[k]->ms_scan;
-        if (off[0] + rs[k]->n_plus > capacity || off[1] + rs[k]->n_minus > capacity) {
-            overflow = true;        // keep counting so that the caller learns the capacity it needs
-        } else {
-            // the rows leave on lane_out: after everything scan_finish queued on the lane (the logistic pass)
-            if (cudaError_t e = cudaStreamWaitEvent(g_ctx.lane_out, rs[k]->ev[2], 0))
-                return fail(CRP_ERR_CUDA, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
-            if (int e = fetch_enqueue(rs[k], 0, 0, rs[k]->n_plus, pos_plus ? pos_plus + off[0] : nullptr,
-                                      scored && packed_plus ? packed_plus + off[0] : nullptr,
-                                      scored && x_plus ? x_plus + off[0] : nullptr, g_ctx.lane_out)) return e;
-            if (int e = fetch_enqueue(rs[k], 1, 0, rs[k]->n_minus, pos_minus ? pos_minus + off[1] : nullptr,
-                                      scored && packed_minus ? packed_minus + off[1] : nullptr,
-                                      scored && x_minus ? x_minus + off[1] : nullptr, g_ctx.lane_out)) return e;
-        }
-        off[0] += rs[k]->n_plus;
-        off[1] += rs[k]->n_minus;
-        return 0;
-    };
-    auto enqueue = [&](uint32_t k) -> int {
-        const crp_segment_desc &sd = segments[k];
-        if (int e = crp_genome_new(&gs[k])) return e;
-        gs[k]->st = g_ctx.lanes[k % kLanes];
-        if (int e = crp_genome_add_segment(gs[k], sd.token_id, sd.token, sd.token_len, sd.begin, sd.end)) return e;
-        if (int e = commit_enqueue(gs[k])) return e;
-        return scan_enqueue(gs[k], guide_len, flags, &rs[k]);
-    };
+    // Consecutive small segments share one genome handle -- one commit, one scan, one copy per stream
+    // for the whole group -- so a genome of 20,000 scaffolds costs a few hundred launches, not 20,000
+    // commits and scans; a segment of kGroupBytes or more is a group of its own.
+    constexpr uint64_t kGroupBytes = 16ull << 20;
     auto seg_bytes = [&](uint32_t k) -> uint64_t {
         const uint64_t end = segments[k].end ? segments[k].end : segments[k].token_len;
         return end > segments[k].begin ? end - segments[k].begin : 0;
     };
+    struct Group {
+        uint32_t first, count;
+        uint64_t bytes;
+    };
+    std::vector<Group> groups;
+    for (uint32_t k = 0; k < n_segments; ++k) {
+        const uint64_t nb = seg_bytes(k);
+        if (groups.empty() || groups.back().bytes + nb > kGroupBytes || groups.back().count >= 4096)
+            groups.push_back(Group{k, 0, 0});
+        groups.back().count++;
+        groups.back().bytes += nb;
+    }
+    const uint32_t n_groups = (uint32_t)groups.size();
+    std::vector<crp_genome *> gs(n_groups, nullptr);
+    std::vector<crp_result *> rs(n_groups, nullptr);
+    int rc = 0;
+    uint64_t off[2] = {0, 0};
+    float ms = 0.f;
+    bool overflow = false;
+    // Groups are enqueued AHEAD of the one whose counts the host waits for (its rows can only be
+    // placed once the counts of every earlier group are known): up to kAheadBytes of tokens, at
+    // least two groups, so that the host-to-device copy engine always has the next token queued.
+    // The rows leave on a stream of their own: a lane may already hold later groups.
+    constexpr uint64_t kAheadBytes = 512ull << 20;
+    if (!g_ctx.lane_out) CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.lane_out, cudaStreamNonBlocking));
+    auto finish = [&](uint32_t q) -> int {
+        if (int e = scan_finish(gs[q], rs[q], g_ctx.lane_out)) return e;
+        for (uint32_t j = 0; j < groups[q].count; ++j) {
+            n_plus[groups[q].first + j] = rs[q]->seg_plus[j];
+            n_minus[groups[q].first + j] = rs[q]->seg_minus[j];
+        }
+        ms += rs[q]->ms_scan;
+        if (off[0] + rs[q]->n_plus > capacity || off[1] + rs[q]->n_minus > capacity) {
+            overflow = true;        // keep counting so that the caller learns the capacity it needs
+        } else {
+            // the rows leave on lane_out: after everything scan_finish queued (the logistic pass)
+            if (cudaError_t e = cudaStreamWaitEvent(g_ctx.lane_out, rs[q]->ev[2], 0))
+                return fail(CRP_ERR_CUDA, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
+            if (int e = fetch_enqueue(rs[q], 0, 0, rs[q]->n_plus, pos_plus ? pos_plus + off[0] : nullptr,
+                                      scored && packed_plus ? packed_plus + off[0] : nullptr,
+                                      scored && x_plus ? x_plus + off[0] : nullptr, g_ctx.lane_out)) return e;
+            if (int e = fetch_enqueue(rs[q], 1, 0, rs[q]->n_minus, pos_minus ? pos_minus + off[1] : nullptr,
+                                      scored && packed_minus ? packed_minus + off[1] : nullptr,
+                                      scored && x_minus ? x_minus + off[1] : nullptr, g_ctx.lane_out)) return e;
+        }
+        off[0] += rs[q]->n_plus;
+        off[1] += rs[q]->n_minus;
+        return 0;
+    };
+    auto enqueue = [&](uint32_t q) -> int {
+        if (int e = crp_genome_new(&gs[q])) return e;
+        gs[q]->st = g_ctx.lanes[q % kLanes];
+        for (uint32_t j = 0; j < groups[q].count; ++j) {
+            const crp_segment_desc &sd = segments[groups[q].first + j];
+            if (int e = crp_genome_add_segment(gs[q], sd.token_id, sd.token, sd.token_len, sd.begin, sd.end)) return e;
+        }
+        if (int e = commit_enqueue(gs[q])) return e;
+        return scan_enqueue(gs[q], guide_len, flags, &rs[q]);
+    };
     uint32_t next_enq = 0;
     uint64_t ahead = 0;
-    for (uint32_t k = 0; k < n_segments && !rc; ++k) {
-        while (!rc && next_enq < n_segments && (next_enq < k + 2 || ahead + seg_bytes(next_enq) <= kAheadBytes)) {
+    for (uint32_t q = 0; q < n_groups && !rc; ++q) {
+        while (!rc && next_enq < n_groups && (next_enq < q + 2 || ahead + groups[next_enq].bytes <= kAheadBytes)) {
             rc = enqueue(next_enq);
-            ahead += seg_bytes(next_enq);
+            ahead += groups[next_enq].bytes;
             ++next_enq;
         }
         tr.lap("enqueue");
-        if (!rc) rc = finish(k);
-        ahead -= seg_bytes(k);
+        if (!rc) rc = finish(q);
+        ahead -= groups[q].bytes;
         tr.lap("finish");
     }
     for (int i = 0; i < kLanes; ++i) cudaStreamSynchronize(g_ctx.lanes[i]);
     cudaStreamSynchronize(g_ctx.lane_out);
     tr.lap("drain");
-    for (uint32_t k = 0; k < n_segments; ++k) {
-        crp_result_free(rs[k]);
-        crp_genome_free(gs[k]);
+    for (uint32_t q = 0; q < n_groups; ++q) {
+        crp_result_free(rs[q]);
+        crp_genome_free(gs[q]);
     }
     tr.lap("free");
     if (ms_device) *ms_device = ms;

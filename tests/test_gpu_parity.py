@@ -706,3 +706,31 @@ def test_many_scaffolds_cli_and_batched_side_outputs(eng, tmp_path):
     finally:
         result.free()
         genome.free()
+
+
+def test_pipelined_call_groups_small_segments(eng):
+    """crp_scan_segments puts consecutive small segments into one genome handle (one commit + one scan
+    per group): 5,000 short records and two long ones, counts per segment and rows in segment order
+    equal the plain scan's."""
+    from cropsr_b200 import engine, ingest
+    rng = np.random.default_rng(17)
+    lengths = [int(x) for x in rng.integers(1, 700, size=5000)]
+    lengths[777] = 400000
+    lengths[3100] = 18 << 20          # a group of its own (>= 16 MiB)
+    text = synthetic_fasta(18, lengths, gc=0.5, lower_frac=0.1, n_frac=0.0)
+    toks = [np.frombuffer(v.encode(), np.uint8) for v in ingest.fasta_text_to_tokens(text).values()]
+    arena, n_plus, n_minus, _ = engine.scan_segments([(k, t, 0, None) for k, t in enumerate(toks)], 20)
+    g = engine.Genome()
+    for t in toks:
+        g.add_token(t)
+    r = g.commit().scan(20)
+    try:
+        assert np.array_equal(n_plus, r.seg_plus) and np.array_equal(n_minus, r.seg_minus)
+        for strand, n in (("+", r.n_plus), ("-", r.n_minus)):
+            want = r.fetch(strand)
+            for name in ("pos", "packed", "x"):
+                assert np.array_equal(arena.arrays[strand][name][:n], want[name]), (strand, name)
+    finally:
+        arena.free()
+        r.free()
+        g.free()
