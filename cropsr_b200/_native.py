@@ -67,6 +67,7 @@ SIGNATURES = {
     "crp_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "crp_abi_version": (C.c_int, []),
     "crp_tile_size": (C.c_int, []),
+    "crp_checked_build": (C.c_int, []),
     "crp_host_alloc": (C.c_int, [_vpp, C.c_uint64]),
     "crp_host_free": (C.c_int, [C.c_void_p]),
     "crp_genome_new": (C.c_int, [_vpp]),

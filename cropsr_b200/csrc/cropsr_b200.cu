@@ -60,6 +60,7 @@ struct Context {
     cudaStream_t lane_out = nullptr;                       // its device-to-host row copies
     std::atomic<uint64_t> launches{0};
     double *d_tables = nullptr;        // RS1 lane tables in device memory
+    unsigned int *d_fault = nullptr;   // CRP_CHECKED builds: first violated kernel invariant
 };
 static Context g_ctx;
 
@@ -224,7 +225,7 @@ static void *pinned_get(size_t bytes) {
         }
     const size_t want = bytes < 4096 ? 4096 : bytes;
     void *p = nullptr;
-    if (cudaHostAlloc(&p, want + sizeof(size_t) * 2, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    if (cudaHostAlloc(&p, want + sizeof(size_t) * 2, cudaHostAllocMapped) != cudaSuccess) return nullptr;   // kernels may store into it
     *reinterpret_cast<size_t *>(p) = want;
     return reinterpret_cast<char *>(p) + sizeof(size_t) * 2;
 }
@@ -324,6 +325,15 @@ int crp_abi_version(void) { return CRP_ABI_VERSION; }
 
 int crp_tile_size(void) { return kTile; }
 
+/* 1 if this build carries the kernel's self-checks (make checked, -DCRP_CHECKED) */
+int crp_checked_build(void) {
+#ifdef CRP_CHECKED
+    return 1;
+#else
+    return 0;
+#endif
+}
+
 const char *crp_last_error(void) { return g_err; }
 
 /* debug hook of tools/phase_timeline.py: device buffer of 8 x u64 per CTA, or NULL */
@@ -358,6 +368,10 @@ int crp_init(int device) {
         CUDA_TRY(cudaMalloc(&g_ctx.d_tables, tab.size() * sizeof(double)));
         CUDA_TRY(cudaMemcpy(g_ctx.d_tables, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
+#ifdef CRP_CHECKED
+    CUDA_TRY(cudaMalloc(&g_ctx.d_fault, sizeof(unsigned int)));
+    CUDA_TRY(cudaMemset(g_ctx.d_fault, 0, sizeof(unsigned int)));
+#endif
     g_ctx.device = device;
     g_ctx.sm_count = prop.multiProcessorCount;
     g_ctx.launches = 0;
@@ -381,6 +395,8 @@ int crp_shutdown(void) {
         if (l) cudaStreamDestroy(l);
     if (g_ctx.lane_out) cudaStreamDestroy(g_ctx.lane_out);
     cudaFree(g_ctx.d_tables);
+    if (g_ctx.d_fault) cudaFree(g_ctx.d_fault);
+    g_ctx.d_fault = nullptr;
     g_ctx.ready = false;
     g_ctx.device = -1;
     g_ctx.stream = nullptr;
@@ -1029,6 +1045,8 @@ static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p) {
     a.seg_stride = r->stride;
     a.seg_first_tile = g->d_seg_first;      // NULL for a single-segment genome
     a.seg_tile_count = g->d_seg_count;
+    a.seg_counts_host = r->h_counts;        // mapped pinned memory: the kernel stores the counts there itself
+    a.fault = g_ctx.d_fault;
     a.world = 1;
     a.rank = 0;
     a.epoch = 0;
@@ -1065,6 +1083,7 @@ static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p) {
         CUDA_TRY(cudaGetLastError());
     } else if (r->stride) {
         CUDA_TRY(cudaMemsetAsync(r->d_counts, 0, 2 * (size_t)r->stride * sizeof(unsigned long long), st));
+        memset(r->h_counts, 0, 2 * (size_t)r->stride * sizeof(unsigned long long));
     }
     if (r->ev_kernel) CUDA_TRY(cudaEventRecord(r->ev_kernel, st));
     if (r->d_gather && !r->fused) {
@@ -1073,9 +1092,7 @@ static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p) {
         if (int rc = comm_allgather_u64(r->d_counts, r->d_gather, 2 * (size_t)r->stride, st)) return rc;
     }
     CUDA_TRY(cudaEventRecord(r->ev[1], st));
-    if (r->stride)
-        CUDA_TRY(cudaMemcpyAsync(r->h_counts, r->d_counts, 2 * (size_t)r->stride * sizeof(unsigned long long),
-                                 cudaMemcpyDeviceToHost, st));
+    // (the per-segment counts are already in r->h_counts: the kernel stored them into mapped host memory)
     if (r->h_gather && gathered)
         CUDA_TRY(cudaMemcpyAsync(r->h_gather, gathered, (size_t)g_comm.world * 2 * r->stride * sizeof(unsigned long long),
                                  cudaMemcpyDeviceToHost, st));
@@ -1164,6 +1181,16 @@ static int scan_finish(crp_genome *g, crp_result *r, cudaStream_t post = nullptr
             r->ms_kernel += ms;
             r->n_launches++;
         }
+#ifdef CRP_CHECKED
+        {
+            unsigned int fault = 0;
+            cudaMemcpy(&fault, g_ctx.d_fault, sizeof fault, cudaMemcpyDeviceToHost);
+            if (fault) {
+                cudaMemset(g_ctx.d_fault, 0, sizeof fault);
+                return fail(CRP_ERR_STATE, "checked build: kernel invariant %u violated (scan.cuh:%u)", fault & 0xFFu, fault >> 8);
+            }
+        }
+#endif
         if (r->fused && *r->h_xchg_error)
             return fail(CRP_ERR_CUDA, "sharded scan: the counts of rank %u did not arrive (peer not scanning?)", *r->h_xchg_error - 1);
         const uint64_t need = r->n_plus > r->n_minus ? r->n_plus : r->n_minus;

@@ -355,6 +355,10 @@ struct ScanArgs {
     unsigned int *tickets;           // [0] emit-phase dispenser of the dynamic tiles, [1] CTAs done with the segment counts
     unsigned long long *seg_counts;  // [2 * seg_stride] out: plus[0..n_seg) then, from seg_stride on, minus[0..n_seg);
                                      // slots n_seg .. seg_stride-1 are zeroed (fixed-size block of a sharded scan's all-gather)
+    unsigned long long *seg_counts_host;   // the same block again in mapped pinned host memory (or NULL): the host reads its
+                                           // counts when the kernel's event has fired, without a copy that would queue behind
+                                           // the row copies of earlier segments on the device-to-host engine
+    unsigned int *fault;                   // CRP_CHECKED builds: first violated invariant (code | line << 8), else untouched
     const uint32_t *seg_first_tile, *seg_tile_count;   // [n_seg]
     uint32_t n_seg, seg_stride;
     // Sharded scan, fused exchange (world > 1): the segment counts also go -- plain stores over NVLink --
@@ -366,6 +370,22 @@ struct ScanArgs {
     unsigned int *xchg_error;        // set if a peer's block did not arrive in time
     unsigned long long xchg_timeout_ns;
 };
+
+// CRP_CHECKED builds (make checked): the kernel verifies its own invariants -- indices into the hit
+// lists, the staged record, the count ring and the output streams, and that the emit phase finds in
+// every warp chunk exactly the hits the count phase counted there -- and records the first violation
+// in *fault instead of trapping (the context stays usable; the host turns it into CRP_ERR_STATE).
+// This pool's compute-sanitizer is closed, so this is how out-of-bounds and ordering bugs are hunted.
+#ifdef CRP_CHECKED
+#define CRP_CHECK(a, cond, code)                                                            \
+    do {                                                                                    \
+        if (!(cond) && (a).fault) atomicCAS((a).fault, 0u, (unsigned)(code) | ((unsigned)__LINE__ << 8)); \
+    } while (0)
+#else
+#define CRP_CHECK(a, cond, code) \
+    do {                         \
+    } while (0)
+#endif
 
 // every rank's block is in my gather buffer (or the timeout struck): spun by the first `world` threads of one CTA
 __device__ __forceinline__ void xchg_wait(const ScanArgs &a) {
@@ -395,6 +415,7 @@ __device__ __forceinline__ void xchg_publish(const ScanArgs &a) {
 __global__ void k_exchange_empty(const ScanArgs a) {
     for (uint32_t sg = threadIdx.x; sg < 2 * a.seg_stride; sg += blockDim.x) {
         a.seg_counts[sg] = 0ull;
+        if (a.seg_counts_host) a.seg_counts_host[sg] = 0ull;
         for (uint32_t p = 0; p < a.world; ++p) a.peer_gather[p][(size_t)a.rank * 2 * a.seg_stride + sg] = 0ull;
     }
     __syncthreads();
@@ -514,6 +535,10 @@ __device__ __forceinline__ void emit_strand(const ScanArgs &a, const double *__r
     for (uint32_t i = slot; i < count; i += kThreads) {
         const uint32_t ws = list[i], t = t_start - (kMinus ? kWinBiasMinus : kWinBiasPlus) + ws;
         const uint32_t row = row0 + i;
+        CRP_CHECK(a, i < (uint32_t)kListCap, 1);                                 // inside the hit list
+        CRP_CHECK(a, ws >= (kMinus ? kWinBiasMinus : kWinBiasPlus) && 2u + (ws >> 5) < (uint32_t)kRecWords, 2);   // window inside the record
+        CRP_CHECK(a, row < cap && t < L, 3);                                     // inside the stream, inside the token
+        CRP_CHECK(a, i == 0 || list[i - 1] < ws, 4);                             // positions ascend
         __stcs(pos + row, t);
         if (kScore) {
             const Window w = extract_window<kMinus>(rec, ws, t, L);
@@ -637,6 +662,8 @@ k_scan_score(const ScanArgs a) {
             const int s = n % kCountStages;
             while (*reinterpret_cast<volatile uint32_t *>(&ring.tile[s]) != n) __nanosleep(32);
             mbar_wait(&ring.full[s], (n / kCountStages) & 1u);
+            CRP_CHECK(a, n - b_lo < (uint32_t)kMaxRange && r_lo + n < nt, 5);
+            CRP_CHECK(a, *reinterpret_cast<const uint32_t *>(pam_stage(s)) == reinterpret_cast<const uint32_t *>(a.pam + (size_t)(r_lo + n) * kPamBytes)[0], 6);   // the slot holds tile n's record
             warp_count_tile(pam_stage(s), l, lane, s_cnt[n - b_lo]);
             __syncwarp();
             if (lane == 0 && n + kCountStages < n_mine) produce_count(n + kCountStages);
@@ -734,6 +761,7 @@ k_scan_score(const ScanArgs a) {
         }
         ring.tile[s] = t;
         if (t != kNoTile) {
+            CRP_CHECK(a, t < nt && t / k < G, 11);
             ring.rbase[s] = s_rangepref[t / k];
             mbar_expect(&ring.full[s], kRecBytes + kPrefWords * 8);
             bulk_copy(stage(s), record(t), kRecBytes, &ring.full[s]);
@@ -764,7 +792,12 @@ k_scan_score(const ScanArgs a) {
             }
             a.seg_counts[sg] = plus;
             a.seg_counts[a.seg_stride + sg] = minus;
+            if (a.seg_counts_host) {
+                a.seg_counts_host[sg] = plus;
+                a.seg_counts_host[a.seg_stride + sg] = minus;
+            }
             if (xchg) {
+                CRP_CHECK(a, (size_t)(a.rank + 1) * 2 * a.seg_stride <= (size_t)kMaxPeers * 2 * 32768, 12);
                 const size_t at = (size_t)a.rank * 2 * a.seg_stride + sg;
                 for (uint32_t p = 0; p < a.world; ++p) {
                     a.peer_gather[p][at] = plus;
@@ -823,6 +856,17 @@ k_scan_score(const ScanArgs a) {
         const uint32_t xA = iA - cA, xB = totA + iB - cB;
         const uint32_t op = (uint32_t)(off >> 32), om = (uint32_t)off;
         const uint32_t epA = op + (xA & 0xFFFFu), emA = om + (xA >> 16), epB = op + (xB & 0xFFFFu), emB = om + (xB >> 16);
+#ifdef CRP_CHECKED
+        {
+            const uint32_t mine = totA + __shfl_sync(0xFFFFFFFFu, iB, 31);       // hits of my warp chunk, (plus | minus << 16)
+            const unsigned long long nxt = ring.pref[s][warp + 1] - ring.pref[s][warp];
+            CRP_CHECK(a, (uint32_t)(nxt >> 32) == (mine & 0xFFFFu) && (uint32_t)nxt == (mine >> 16), 7);   // count phase == emit phase
+            CRP_CHECK(a, ring.tile[s] == kNoTile || first_pre || ring.tile[s] < nt, 8);
+            CRP_CHECK(a, (unsigned long long)base_p + np <= 0xFFFFFFFFull && (unsigned long long)base_m + nm <= 0xFFFFFFFFull, 9);
+            if (np <= (uint32_t)kListCap && nm <= (uint32_t)kListCap)
+                CRP_CHECK(a, epA + __popc(h.pA) <= np && epB + __popc(h.pB) <= np && emA + __popc(h.mA) <= nm && emB + __popc(h.mB) <= nm, 10);
+        }
+#endif
         if (np <= (uint32_t)kListCap && nm <= (uint32_t)kListCap) {
             list_hits(list_p + epA, h.pA, 32u * wordA + kWinBiasPlus);
             list_hits(list_p + epB, h.pB, 32u * (wordA + 32) + kWinBiasPlus);

@@ -76,6 +76,10 @@ int crp_abi_version(void);
 /* Positions per scan tile: segment boundaries chosen by the host should be
  * multiples of this (any multiple of 128 is accepted). */
 int crp_tile_size(void);
+/* 1 for the self-checking build (make -C cropsr_b200/csrc checked: libcropsr_b200_checked.so):
+ * k_scan_score verifies its own index and ordering invariants and a violated one fails the scan
+ * with CRP_ERR_STATE naming it.  Slower; for tests (compute-sanitizer is not available everywhere). */
+int crp_checked_build(void);
 
 /* Wait for everything this library has queued on the device. */
 int crp_device_synchronize(void);

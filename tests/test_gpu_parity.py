@@ -734,3 +734,28 @@ def test_pipelined_call_groups_small_segments(eng):
         arena.free()
         r.free()
         g.free()
+
+
+def test_checked_build_sees_no_violated_invariant(eng):
+    """libcropsr_b200_checked.so (make checked, -DCRP_CHECKED): k_scan_score verifies its own invariants --
+    hit-list, record, ring and stream indices, ascending positions, and that the emit phase finds in every
+    warp chunk exactly the hits the count phase counted -- and a violated one fails the scan.  The small
+    cases with the most edges (tile borders, dense tiles, long count ranges with 1-7 CTAs, static / ticketed
+    dealing, the edge fixtures, many scaffolds) run under it in a subprocess.  (compute-sanitizer is closed
+    on the GPU pool this was developed on: profiles/README.md.)"""
+    import subprocess, sys
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    lib = os.path.join(root, "cropsr_b200", "libcropsr_b200_checked.so")
+    if not os.path.exists(lib):
+        pytest.skip("checked library not built (make -C cropsr_b200/csrc checked)")
+    if os.environ.get("CROPSR_B200_LIB"):
+        return                      # already inside such a subprocess
+    env = dict(os.environ, CROPSR_B200_LIB=lib)
+    probe = subprocess.run([sys.executable, "-c", "from cropsr_b200 import _native as N; print(N.lib.crp_checked_build())"],
+                           cwd=root, env=env, capture_output=True, text=True, timeout=120)
+    assert probe.stdout.strip() == "1", probe.stderr[-1000:]
+    sel = ("test_tile_boundaries or test_long_count_ranges or test_static_and_ticketed or test_many_scaffolds_match or "
+           "test_random_fastas or test_sharded_scan or test_pipelined or (test_candidate_streams and (edge or multi3 or mid50k))")
+    out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_parity.py", "-k", sel],
+                         cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
