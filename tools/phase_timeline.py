@@ -9,7 +9,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import torch
+import torch  # device buffer only
 import bench
 from cropsr_b200 import engine, _native
 
@@ -34,7 +34,7 @@ T = buf.cpu().numpy().reshape(-1, 8)
 T = T[T[:, 0] > 0]
 t0 = T[:, 0].min()
 rel = (T - t0) / 1000.0
-names = ["start", "count_begin", "count_end", "grid_sync_end", "emit_begin", "emit_end", "range_scan_end", "first_tile"]
+names = ["start", "count_begin", "count_end", "grid_sync_end", "emit_begin", "emit_end"]
 print(f"scan {ms * 1e3:.1f} us (events), {len(T)} CTAs; microseconds since the first CTA started")
 for k, n in enumerate(names):
     c = rel[:, k]
