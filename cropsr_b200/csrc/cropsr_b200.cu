@@ -1415,22 +1415,44 @@ int crp_scan_segments(uint32_t n_segments, const crp_segment_desc *segments, int
     if (!g_ctx.lanes[0])
         for (int i = 0; i < kLanes; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.lanes[i], cudaStreamNonBlocking));
     Trace tr("scan_segments");
-    // Consecutive small segments share one genome handle -- one commit, one scan, one copy per stream
-    // for the whole group -- so a genome of 20,000 scaffolds costs a few hundred launches, not 20,000
-    // commits and scans; a segment of kGroupBytes or more is a group of its own.
-    constexpr uint64_t kGroupBytes = 16ull << 20;
-    auto seg_bytes = [&](uint32_t k) -> uint64_t {
-        const uint64_t end = segments[k].end ? segments[k].end : segments[k].token_len;
-        return end > segments[k].begin ? end - segments[k].begin : 0;
+    // The unit of the pipeline is a GROUP of ~8 M positions: a long segment is cut into pieces of that
+    // size (tile-aligned; the scan of the first piece starts after 8 MB of the token have arrived, and
+    // the rows that are still on the device when the last copy-in ends are those of one piece, not of a
+    // chromosome), and consecutive small segments share one group -- one commit, one scan, one copy per
+    // stream -- so a genome of 20,000 scaffolds costs a few hundred launches, not 20,000 commits and scans.
+    uint64_t piece_bytes = 8ull << 20;
+    if (const char *e = getenv("CRP_PIECE_POSITIONS")) {
+        const unsigned long long v = strtoull(e, nullptr, 10);
+        if (v >= (unsigned long long)kTile) piece_bytes = v / kTile * kTile;
+    }
+    struct Piece {
+        uint32_t seg;              // index of the caller's segment
+        uint64_t begin, end;
     };
+    std::vector<Piece> pieces;
+    for (uint32_t k = 0; k < n_segments; ++k) {
+        const uint64_t end = segments[k].end ? segments[k].end : segments[k].token_len;
+        uint64_t b0 = segments[k].begin;
+        n_plus[k] = n_minus[k] = 0;
+        if (end <= b0) {
+            pieces.push_back(Piece{k, b0, end});
+            continue;
+        }
+        while (b0 < end) {
+            uint64_t e0 = b0 + piece_bytes;
+            if (e0 + piece_bytes / 4 >= end) e0 = end;       // no crumb at the end
+            pieces.push_back(Piece{k, b0, e0});
+            b0 = e0;
+        }
+    }
     struct Group {
-        uint32_t first, count;
+        uint32_t first, count;     // pieces
         uint64_t bytes;
     };
     std::vector<Group> groups;
-    for (uint32_t k = 0; k < n_segments; ++k) {
-        const uint64_t nb = seg_bytes(k);
-        if (groups.empty() || groups.back().bytes + nb > kGroupBytes || groups.back().count >= 4096)
+    for (uint32_t k = 0; k < (uint32_t)pieces.size(); ++k) {
+        const uint64_t nb = pieces[k].end > pieces[k].begin ? pieces[k].end - pieces[k].begin : 0;
+        if (groups.empty() || groups.back().bytes + nb > piece_bytes + piece_bytes / 4 || groups.back().count >= 4096)
             groups.push_back(Group{k, 0, 0});
         groups.back().count++;
         groups.back().bytes += nb;
@@ -1451,8 +1473,8 @@ int crp_scan_segments(uint32_t n_segments, const crp_segment_desc *segments, int
     auto finish = [&](uint32_t q) -> int {
         if (int e = scan_finish(gs[q], rs[q], g_ctx.lane_out)) return e;
         for (uint32_t j = 0; j < groups[q].count; ++j) {
-            n_plus[groups[q].first + j] = rs[q]->seg_plus[j];
-            n_minus[groups[q].first + j] = rs[q]->seg_minus[j];
+            n_plus[pieces[groups[q].first + j].seg] += rs[q]->seg_plus[j];
+            n_minus[pieces[groups[q].first + j].seg] += rs[q]->seg_minus[j];
         }
         ms += rs[q]->ms_scan;
         if (off[0] + rs[q]->n_plus > capacity || off[1] + rs[q]->n_minus > capacity) {
@@ -1476,8 +1498,9 @@ int crp_scan_segments(uint32_t n_segments, const crp_segment_desc *segments, int
         if (int e = crp_genome_new(&gs[q])) return e;
         gs[q]->st = g_ctx.lanes[q % kLanes];
         for (uint32_t j = 0; j < groups[q].count; ++j) {
-            const crp_segment_desc &sd = segments[groups[q].first + j];
-            if (int e = crp_genome_add_segment(gs[q], sd.token_id, sd.token, sd.token_len, sd.begin, sd.end)) return e;
+            const Piece &pc = pieces[groups[q].first + j];
+            const crp_segment_desc &sd = segments[pc.seg];
+            if (int e = crp_genome_add_segment(gs[q], sd.token_id, sd.token, sd.token_len, pc.begin, pc.end)) return e;
         }
         if (int e = commit_enqueue(gs[q])) return e;
         return scan_enqueue(gs[q], guide_len, flags, &rs[q]);
