@@ -161,17 +161,39 @@ template <typename T>
 static cudaError_t dev_alloc(T **ptr, size_t bytes, cudaStream_t st) {
     std::lock_guard<std::mutex> lock(g_mem_mu);
     const size_t want = (bytes ? bytes : 16) + 255 & ~(size_t)255;
-    size_t best = g_dev_free.size();
+    // best fit among the idle blocks whose last user has FINISHED: a block that is still in use on another
+    // stream would chain this stream behind that one (the copy-in of pipeline group k + 1 behind the pack
+    // kernel of group k: a bubble on the copy engine per group); such a block is only taken when nothing
+    // else fits and the driver has no memory left (below)
+    size_t best = g_dev_free.size(), busy = g_dev_free.size();
     for (size_t i = 0; i < g_dev_free.size(); ++i) {
         const size_t b = g_dev_free[i].bytes;
-        if (b >= want && b - want <= want / 8 + 4096 && (best == g_dev_free.size() || b < g_dev_free[best].bytes)) best = i;
+        if (b < want || b - want > want / 8 + 4096) continue;
+        if (cudaEventQuery(g_dev_free[i].ev) == cudaSuccess) {
+            best = i;                                          // first fit: one query per allocation in the steady state
+            break;
+        } else {
+            cudaGetLastError();                                // cudaErrorNotReady is not an error here
+            if (busy == g_dev_free.size() || b < g_dev_free[busy].bytes) busy = i;
+        }
     }
     DevBlock blk;
     if (best < g_dev_free.size()) {
         blk = g_dev_free[best];
         g_dev_free.erase(g_dev_free.begin() + best);
+    } else if (cudaMalloc(&blk.ptr, want) == cudaSuccess) {
+        blk.bytes = want;
+        if (cudaError_t e = cudaEventCreateWithFlags(&blk.ev, cudaEventDisableTiming)) {
+            cudaFree(blk.ptr);
+            return e;
+        }
+    } else if (busy < g_dev_free.size()) {
+        cudaGetLastError();
+        blk = g_dev_free[busy];
+        g_dev_free.erase(g_dev_free.begin() + busy);
         if (cudaError_t e = cudaStreamWaitEvent(st, blk.ev, 0)) return e;
     } else {
+        cudaGetLastError();
         blk.bytes = want;
         if (cudaMalloc(&blk.ptr, want) != cudaSuccess) {        // out of memory: give the idle blocks back first
             cudaGetLastError();
@@ -1415,12 +1437,14 @@ int crp_scan_segments(uint32_t n_segments, const crp_segment_desc *segments, int
     if (!g_ctx.lanes[0])
         for (int i = 0; i < kLanes; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.lanes[i], cudaStreamNonBlocking));
     Trace tr("scan_segments");
-    // The unit of the pipeline is a GROUP of ~8 M positions: a long segment is cut into pieces of that
-    // size (tile-aligned; the scan of the first piece starts after 8 MB of the token have arrived, and
-    // the rows that are still on the device when the last copy-in ends are those of one piece, not of a
-    // chromosome), and consecutive small segments share one group -- one commit, one scan, one copy per
+    // The unit of the pipeline is a GROUP of up to ~32 M positions: a longer segment is cut into pieces of
+    // that size (tile-aligned: a 300 Mbp chromosome does not hold the scan back until all of it has
+    // arrived), and consecutive small segments share one group -- one commit, one scan, one copy per
     // stream -- so a genome of 20,000 scaffolds costs a few hundred launches, not 20,000 commits and scans.
-    uint64_t piece_bytes = 8ull << 20;
+    // Measured on the 135 Mbp config (5 chromosomes of 21-34 Mbp): 32 M -> 3.29 ms, 16 M -> 3.73 ms,
+    // 8 M -> 4.3 ms, 2 M -> 7.1 ms per call: every group costs two logistic launches and four row copies
+    // on the copy-out stream (~25 us of engine latency), which finer groups multiply.
+    uint64_t piece_bytes = 32ull << 20;
     if (const char *e = getenv("CRP_PIECE_POSITIONS")) {
         const unsigned long long v = strtoull(e, nullptr, 10);
         if (v >= (unsigned long long)kTile) piece_bytes = v / kTile * kTile;
