@@ -448,6 +448,7 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             os.sched_setaffinity(0, cpus_before)          # the CPU baseline may use every core of the host
             line["cpu_baseline"] = reference_sample(workload, 20.0)[0]
+        line["perf_report"] = engine.perf_report()
         print(json.dumps(line))
     engine.comm_barrier()
     engine.comm_shutdown()

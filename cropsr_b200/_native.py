@@ -107,6 +107,7 @@ SIGNATURES = {
     "crp_genome_timing": (C.c_int, [C.c_void_p, _f32p, _f32p]),
     "crp_result_timing": (C.c_int, [C.c_void_p, _f32p]),
     "crp_launch_count": (C.c_int, [_u64p]),
+    "crp_perf_report": (C.c_int, [C.c_void_p, C.c_uint64, _u64p]),
     "crp_debug_set_times": (C.c_int, [C.c_void_p]),
     "crp_device_synchronize": (C.c_int, []),
     "crp_flush_l2": (C.c_int, []),

@@ -64,6 +64,14 @@ struct Context {
 };
 static Context g_ctx;
 
+// counters behind crp_perf_report
+struct Perf {
+    std::atomic<uint64_t> commits{0}, scans{0}, sharded_scans{0}, fused_exchanges{0}, capacity_reruns{0};
+    std::atomic<uint64_t> positions{0}, candidates{0}, h2d_bytes{0}, d2h_bytes{0}, cache_hits{0}, cache_misses{0};
+    double ms_h2d = 0, ms_pack = 0, ms_scan = 0, ms_kernel = 0;     // sums over finished commits / scans
+};
+static Perf g_perf;
+
 // ------------------------------------------------------------------ host objects
 struct Segment {
     uint32_t token_id;
@@ -181,7 +189,9 @@ static cudaError_t dev_alloc(T **ptr, size_t bytes, cudaStream_t st) {
     if (best < g_dev_free.size()) {
         blk = g_dev_free[best];
         g_dev_free.erase(g_dev_free.begin() + best);
+        g_perf.cache_hits++;
     } else if (cudaMalloc(&blk.ptr, want) == cudaSuccess) {
+        g_perf.cache_misses++;
         blk.bytes = want;
         if (cudaError_t e = cudaEventCreateWithFlags(&blk.ev, cudaEventDisableTiming)) {
             cudaFree(blk.ptr);
@@ -426,6 +436,39 @@ int crp_shutdown(void) {
     g_ctx.lane_out = nullptr;
     g_ctx.d_tables = nullptr;
     g_ctx.launches = 0;
+    return 0;
+}
+
+/* JSON object with the library's counters since crp_init (perf report) */
+int crp_perf_report(char *buf, uint64_t capacity, uint64_t *needed) {
+    char tmp[1536];
+    size_t live = 0, idle = 0, live_bytes = 0, idle_bytes = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_mem_mu);
+        live = g_dev_live.size();
+        idle = g_dev_free.size();
+        for (const DevBlock &b : g_dev_live) live_bytes += b.bytes;
+        for (const DevBlock &b : g_dev_free) idle_bytes += b.bytes;
+    }
+    const int n = snprintf(
+        tmp, sizeof tmp,
+        "{\"abi\": %d, \"checked_build\": %d, \"device\": %d, \"sm_count\": %d, \"kernel_launches\": %llu, "
+        "\"commits\": %llu, \"scans\": %llu, \"sharded_scans\": %llu, \"fused_exchanges\": %llu, \"capacity_reruns\": %llu, "
+        "\"positions_packed\": %llu, \"candidates\": %llu, \"h2d_token_bytes\": %llu, \"d2h_row_bytes\": %llu, "
+        "\"ms_h2d\": %.4f, \"ms_pack\": %.4f, \"ms_scan\": %.4f, \"ms_scan_kernels\": %.4f, "
+        "\"comm\": {\"rank\": %d, \"world\": %d, \"fused_exchange\": %s}, "
+        "\"block_cache\": {\"live_blocks\": %zu, \"live_bytes\": %zu, \"idle_blocks\": %zu, \"idle_bytes\": %zu, \"hits\": %llu, \"misses\": %llu}}",
+        CRP_ABI_VERSION, crp_checked_build(), g_ctx.device, g_ctx.sm_count, (unsigned long long)g_ctx.launches.load(),
+        (unsigned long long)g_perf.commits.load(), (unsigned long long)g_perf.scans.load(),
+        (unsigned long long)g_perf.sharded_scans.load(), (unsigned long long)g_perf.fused_exchanges.load(),
+        (unsigned long long)g_perf.capacity_reruns.load(), (unsigned long long)g_perf.positions.load(),
+        (unsigned long long)g_perf.candidates.load(), (unsigned long long)g_perf.h2d_bytes.load(),
+        (unsigned long long)g_perf.d2h_bytes.load(), g_perf.ms_h2d, g_perf.ms_pack, g_perf.ms_scan, g_perf.ms_kernel,
+        g_comm.comm ? g_comm.rank : 0, g_comm.comm ? g_comm.world : 1, g_comm.comm && g_comm.fused && g_comm.mode == 0 ? "true" : "false",
+        live, live_bytes, idle, idle_bytes, (unsigned long long)g_perf.cache_hits.load(), (unsigned long long)g_perf.cache_misses.load());
+    if (needed) *needed = (uint64_t)n + 1;
+    if (!buf || capacity < (uint64_t)n + 1) return fail(CRP_ERR_RANGE, "perf report needs %d bytes", n + 1);
+    memcpy(buf, tmp, (size_t)n + 1);
     return 0;
 }
 
@@ -841,6 +884,9 @@ static int commit_enqueue(crp_genome *g) {
         return fail(CRP_ERR_RANGE, "shard of %llu positions exceeds the 32-bit candidate count range",
                     (unsigned long long)g->n_positions);
     g->n_tiles = (uint32_t)n_tiles;
+    g_perf.commits++;
+    g_perf.positions += g->n_positions;
+    g_perf.h2d_bytes += ascii_bytes;
 
     uint8_t *d_ascii = nullptr;
     PackDesc *d_descs = nullptr;
@@ -949,6 +995,8 @@ int crp_genome_commit(crp_genome *g) {
     tr.lap("sync");
     CUDA_TRY(cudaEventElapsedTime(&g->ms_h2d, g->ev[0], g->ev[1]));
     CUDA_TRY(cudaEventElapsedTime(&g->ms_pack, g->ev[1], g->ev[2]));
+    g_perf.ms_h2d += g->ms_h2d;
+    g_perf.ms_pack += g->ms_pack;
     for (Segment &s : g->segs) s.token = nullptr;   // host tokens may be released now
     if (g->h_bad && *g->h_bad)
         return fail(CRP_ERR_FORMAT, "a FASTA record is not plain fixed-width text; use the host ingest for this file");
@@ -1230,6 +1278,13 @@ static int scan_finish(crp_genome *g, crp_result *r, cudaStream_t post = nullptr
         if (int rc = plan_scan(g, r->scored, &plan)) return rc;
         if (int rc = launch_scan(g, r, plan)) return rc;
     }
+    g_perf.scans++;
+    if (r->stride != (uint32_t)g->segs.size() || r->h_gather) g_perf.sharded_scans++;
+    if (r->epoch && g_comm.fused && g_comm.mode == 0) g_perf.fused_exchanges++;
+    g_perf.capacity_reruns += r->n_launches - 1;
+    g_perf.candidates += r->n_plus + r->n_minus;
+    g_perf.ms_scan += r->ms_scan;
+    g_perf.ms_kernel += r->ms_kernel;
     if (r->scored && (r->flags & CRP_SCAN_LOGISTIC)) {
         const uint64_t n[2] = {r->n_plus, r->n_minus};
         for (int s = 0; s < 2; ++s)
@@ -1366,6 +1421,7 @@ int crp_result_device_counts(const crp_result *res, void **dev_ptr) {
 static int fetch_enqueue(const crp_result *res, int s, uint64_t first, uint64_t count, uint32_t *pos, uint64_t *packed,
                          double *x, cudaStream_t st = nullptr) {
     if (!st) st = res->st;
+    g_perf.d2h_bytes += count * ((pos ? 4 : 0) + (packed ? 8 : 0) + (x ? 8 : 0));
     if (count) {
         if (pos) CUDA_TRY(cudaMemcpyAsync(pos, res->pos[s] + first, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         if (packed)

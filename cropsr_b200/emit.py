@@ -95,13 +95,6 @@ class IdStream:
             self.thread = None
 
 
-def ids_to_strings(ids):
-    ids = np.ascontiguousarray(ids)
-    if ids.size == 0:
-        return []
-    return ids.view("<U7").ravel().tolist()
-
-
 def apply_cutsite(start_pos, end_pos, crispr_sys):
     """CROPSR.py:155-158."""
     if crispr_sys == "cas9":
@@ -283,33 +276,6 @@ def slice_scores(table, genome, start, count, blas_threads=1):
         return 1 / (1 + np.exp(x)), scored
 
 
-def slice_rows(table, ids, scores, scored, start, count):
-    """Row tuples of one emitted slice (CROPSR.py:463-469)."""
-    l = table.guide_len
-    rows = []
-    tok_i = table.tok[start:start + count].tolist()
-    minus = table.minus[start:start + count].tolist()
-    ts = table.t[start:start + count].tolist()
-    sc = scores.tolist()
-    ok = scored.tolist()
-    for k in range(count):
-        t = ts[k]
-        token = table.tokens[tok_i[k]]
-        short, long_ = guide_strings(token, t, minus[k], l)
-        if minus[k]:
-            first, second, strand = t + 3 + l, t + 3, "-"
-        else:
-            first, second, strand = t - l, t, "+"
-        rid = ids[start - k - 1]
-        chrom = table.chroms[tok_i[k]]
-        if ok[k]:
-            rows.append((rid, "cas9", short, long_, chrom, first, second,
-                         apply_cutsite(first, second, "cas9"), strand, sc[k], "", "completed"))
-        else:
-            rows.append((rid, "cas9", short, long_, chrom, first, second, strand, -1, "", "completed"))
-    return rows
-
-
 def id_bytes_of(ids):
     """get_id()'s (size, 7) '<U1' array as (size, 7) ASCII bytes for the row formatter."""
     return np.ascontiguousarray(ids).view(np.uint32).astype(np.uint8)
@@ -317,7 +283,7 @@ def id_bytes_of(ids):
 
 def format_rows(table, ids, scores, scored, start, count, n_threads=0, buffer=0):
     """CSV bytes of one emitted slice through the library's multi-threaded row formatter
-    (csrc/emit_csv.cpp) -- byte-identical to csv.writer().writerows(slice_rows(...))."""
+    (csrc/emit_csv.cpp) -- byte-identical to csv.writer().writerows() of the reference's row tuples (tests/helpers.py slice_rows)."""
     import ctypes as C
     from ._native import lib, check
     if count == 0:

@@ -70,6 +70,15 @@ def device_count():
     return n.value
 
 
+def perf_report():
+    """dict of the library's counters since init (crp_perf_report)"""
+    import json
+    buf = C.create_string_buffer(4096)
+    need = C.c_uint64(0)
+    check(lib.crp_perf_report(buf, len(buf), C.byref(need)))
+    return json.loads(buf.value.decode())
+
+
 def launch_count():
     n = C.c_uint64(0)
     check(lib.crp_launch_count(C.byref(n)))

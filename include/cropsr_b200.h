@@ -339,6 +339,10 @@ int crp_result_timing(const crp_result *res, float *ms_scan);
 /* ms_kernels: the scan kernels alone; ms_total = ms_scan above; n_launches: 1, or 2 if the first
  * capacity guess (1/8 candidate per position and strand) was too small and the scan ran again. */
 int crp_result_timing_detail(const crp_result *res, float *ms_kernels, float *ms_total, uint32_t *n_launches);
+/* The library's counters since crp_init as one JSON object (launches, commits, scans, sharded scans,
+ * fused exchanges, capacity reruns, positions, candidates, bytes over the link, summed event times,
+ * communicator, block cache).  CRP_ERR_RANGE (and *needed) if buf is too small. */
+int crp_perf_report(char *buf, uint64_t capacity, uint64_t *needed);
 /* Number of kernel launches issued by this library since crp_init. */
 int crp_launch_count(uint64_t *n);
 /* Profiling hook (tools/phase_timeline.py): device buffer of 8 x uint64 per CTA that k_scan_score

@@ -60,3 +60,41 @@ def synthetic_fasta(seed, lengths, gc=0.45, lower_frac=0.15, n_frac=0.001, width
         lines = "\n".join(body[j:j + width] for j in range(0, n, width))
         out.append(f">chr{k + 1}\n{lines}")
     return "\n".join(out) + ("\n" if trailing_newline else "")
+
+
+# ---- Python mirrors of the reference's row tuples: what the library's C row formatter (crp_format_rows) is compared with
+def ids_to_strings(ids):
+    ids = np.ascontiguousarray(ids)
+    if ids.size == 0:
+        return []
+    return ids.view("<U7").ravel().tolist()
+
+
+def slice_rows(table, ids, scores, scored, start, count):
+    """Row tuples of one emitted slice (CROPSR.py:463-469)."""
+    from cropsr_b200 import emit
+    l = table.guide_len
+    rows = []
+    tok_i = table.tok[start:start + count].tolist()
+    minus = table.minus[start:start + count].tolist()
+    ts = table.t[start:start + count].tolist()
+    sc = scores.tolist()
+    ok = scored.tolist()
+    for k in range(count):
+        t = ts[k]
+        token = table.tokens[tok_i[k]]
+        short, long_ = emit.guide_strings(token, t, minus[k], l)
+        if minus[k]:
+            first, second, strand = t + 3 + l, t + 3, "-"
+        else:
+            first, second, strand = t - l, t, "+"
+        rid = ids[start - k - 1]
+        chrom = table.chroms[tok_i[k]]
+        if ok[k]:
+            rows.append((rid, "cas9", short, long_, chrom, first, second,
+                         emit.apply_cutsite(first, second, "cas9"), strand, sc[k], "", "completed"))
+        else:
+            rows.append((rid, "cas9", short, long_, chrom, first, second, strand, -1, "", "completed"))
+    return rows
+
+

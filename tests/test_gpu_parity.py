@@ -759,3 +759,19 @@ def test_checked_build_sees_no_violated_invariant(eng):
     out = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu_parity.py", "-k", sel],
                          cwd=root, env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+
+
+def test_perf_report_counts_what_ran(eng):
+    from cropsr_b200 import ingest, pipeline
+    before = eng.perf_report()
+    tokens = ingest.fasta_text_to_tokens(synthetic_fasta(61, [50000, 20000], gc=0.5))
+    genome, result, _ = pipeline.scan_tokens(tokens, 20)
+    n = result.n_plus + result.n_minus
+    result.fetch("+")
+    result.free()
+    genome.free()
+    after = eng.perf_report()
+    assert after["commits"] == before["commits"] + 1 and after["scans"] == before["scans"] + 1
+    assert after["candidates"] == before["candidates"] + n
+    assert after["positions_packed"] == before["positions_packed"] + sum(len(t) for t in tokens.values())
+    assert after["kernel_launches"] >= before["kernel_launches"] + 2 and after["d2h_row_bytes"] > before["d2h_row_bytes"]

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import cropsr_oracle as oracle
-from helpers import GOLDEN, ROOT, fixture_text
+from helpers import GOLDEN, ROOT, fixture_text, ids_to_strings, slice_rows
 
 
 def test_library_loads_and_exports_header_symbols(built_lib):
@@ -86,7 +86,7 @@ def test_blas_row_classes_match_oracle_model(built_lib):
 def test_ids_reproduce_reference_rng(built_lib):
     from cropsr_b200 import emit
     np.random.seed(3)
-    a = emit.ids_to_strings(emit.get_id(1000))
+    a = ids_to_strings(emit.get_id(1000))
     np.random.seed(3)
     b = oracle.make_ids(1000)
     assert a == b and len(a[0]) == 7
@@ -185,7 +185,7 @@ def test_c_row_formatter_equals_python_csv_writer(built_lib, fasta, guide_len, m
     scores[~scored] = np.nan
     for start, count in ((0, n), (n // 3, n - n // 3), (n - 1, 1)):
         want = io.StringIO(newline="")
-        csv.writer(want).writerows(emit.slice_rows(table, emit.ids_to_strings(ids), scores[start:start + count],
+        csv.writer(want).writerows(slice_rows(table, ids_to_strings(ids), scores[start:start + count],
                                                    scored[start:start + count], start, count))
         for threads, budget in ((1, 512 << 20), (3, 512 << 20), (2, 1 << 20)):      # the last one: several calls per slice
             monkeypatch.setattr(emit, "_FORMAT_BUDGET", budget)
