@@ -179,15 +179,18 @@ def scan_on_devices(token_bytes, devices, guide_len=20, flags=0):
                          daemon=True) for r in range(1, world)]
     for p in procs:
         p.start()
+    ok = False
     try:
         _rank_body.parent_buf = parent_buf
         out = _rank_body(0, world, port, devices[0], tok_shm.name, tok_off, tok_len, guide_len, flags)
+        ok = True
     finally:
         _rank_body.parent_buf = None
         for p in procs:
-            p.join(timeout=120)
+            p.join(timeout=120 if ok else 2)       # rank 0 failed: the others wait for it in vain
             if p.is_alive():
                 p.terminate()
+                p.join(timeout=10)
         del view
         tok_shm.close()
         tok_shm.unlink()
