@@ -26,13 +26,11 @@
 #define CRP_CTAS_PER_SM 4
 #endif
 #include "scan.cuh"
-#include "scan_pw.cuh"
 #include "primers.cuh"
 #include "extras.cuh"
 
 #define CRP_ABI_VERSION 7
 
-static constexpr uint32_t kPwMaxWaves = 34;       // control words per genome: 32 waves double past any tile count, + 1 + spare
 static constexpr size_t kScanSmemFixed = (size_t)kStages * kRecBytes + 2 * (size_t)kListCap * sizeof(uint16_t);
 
 // ------------------------------------------------------------------ errors
@@ -98,7 +96,6 @@ struct crp_genome {
     unsigned char *pam = nullptr;      // n_tiles PAM records (count phase of the scan)
     uint32_t n_tiles = 0;
     uint32_t *d_seg_first = nullptr, *d_seg_count = nullptr;
-    PwCtl *d_pw_ctl = nullptr;         // control words of k_scan_pw: zero between launches (the kernel cleans up after itself)
     float ms_h2d = 0.f, ms_pack = 0.f;
     uint8_t *d_ascii = nullptr;                // ASCII tokens, kept after the pack only for device-ingested FASTA records
     bool fasta = false;
@@ -117,9 +114,6 @@ struct crp_result {
     bool fused = false;                        // counts exchanged by the kernel itself (peer stores), not by NCCL
     uint32_t epoch = 0;
     unsigned int *h_xchg_error = nullptr;      // pinned
-    unsigned int *h_pw_error = nullptr;        // pinned, mapped: k_scan_pw reports a flag that never came up
-    bool pw = false;                           // scanned by k_scan_pw (count folded into the emit phase)
-    uint32_t pw_waves = 0, pw_grid = 0;
     float ms_kernel = 0.f;
     int guide_len = 0;
     uint32_t flags = 0;
@@ -907,11 +901,6 @@ static int commit_enqueue(crp_genome *g) {
         return fail(CRP_ERR_NOMEM, "cudaMalloc of %llu record bytes + %llu staging bytes failed",
                     (unsigned long long)rec_bytes, (unsigned long long)ascii_bytes);
     }
-    if (dev_alloc(&g->d_pw_ctl, kPwMaxWaves * sizeof(PwCtl), st) != cudaSuccess) {
-        cudaGetLastError();
-        return fail(CRP_ERR_NOMEM, "cudaMalloc of the scan control words failed");
-    }
-    CUDA_TRY(cudaMemsetAsync(g->d_pw_ctl, 0, kPwMaxWaves * sizeof(PwCtl), st));
     for (int i = 0; i < 3; ++i)
         if (!g->ev[i]) CUDA_TRY(cudaEventCreate(&g->ev[i]));
     CUDA_TRY(cudaEventRecord(g->ev[0], st));
@@ -1030,7 +1019,6 @@ int crp_genome_free(crp_genome *g) {
     pinned_put(g->h_bad);
     dev_free(g->d_seg_first, st);
     dev_free(g->d_seg_count, st);
-    dev_free(g->d_pw_ctl, st);
     for (cudaEvent_t e : g->ev)
         if (e) cudaEventDestroy(e);
     delete g;
@@ -1071,31 +1059,16 @@ struct ScanPlan {
     const void *fn;
     unsigned grid, threads;
     size_t smem;
-    bool pw;
-    uint32_t waves;
 };
-
-// CRP_SCAN_PW=0 selects k_scan_score (count phase, grid barrier, emit phase); default k_scan_pw
-static bool use_pw() {
-    const char *e = getenv("CRP_SCAN_PW");
-    return !(e && e[0] == '0');
-}
 
 static int plan_scan(const crp_genome *g, bool scored, ScanPlan *p) {
     p->threads = kThreads;
-    p->pw = use_pw();
-    p->waves = 0;
+    p->fn = scored ? (const void *)k_scan_score<true> : (const void *)k_scan_score<false>;
     const unsigned grid_max = (unsigned)g_ctx.sm_count * CRP_CTAS_PER_SM;
-    if (p->pw) {
-        p->fn = scored ? (const void *)k_scan_pw<true> : (const void *)k_scan_pw<false>;
-        p->smem = kScanSmemFixed;
-    } else {
-        p->fn = scored ? (const void *)k_scan_score<true> : (const void *)k_scan_score<false>;
-        p->smem = kScanSmemFixed + (size_t)grid_max * sizeof(unsigned long long);
-        if (p->smem < (size_t)kCountStages * kPamBytes) p->smem = (size_t)kCountStages * kPamBytes;   // the count ring reuses all of it
-    }
-    static int per_sm_cache[4] = {0, 0, 0, 0};  // occupancy of the four instantiations, queried once
-    int &per_sm = per_sm_cache[(scored ? 1 : 0) + (p->pw ? 2 : 0)];
+    p->smem = kScanSmemFixed + (size_t)grid_max * sizeof(unsigned long long);
+    if (p->smem < (size_t)kCountStages * kPamBytes) p->smem = (size_t)kCountStages * kPamBytes;   // the count ring reuses all of it
+    static int per_sm_cache[2] = {0, 0};       // occupancy of the two instantiations, queried once
+    int &per_sm = per_sm_cache[scored ? 1 : 0];
     if (per_sm == 0) {
         CUDA_TRY(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p->fn, kThreads, p->smem));
@@ -1111,11 +1084,6 @@ static int plan_scan(const crp_genome *g, bool scored, ScanPlan *p) {
     if (grid > g->n_tiles) grid = g->n_tiles;
     if (grid < 1) grid = 1;
     p->grid = (unsigned)grid;
-    if (p->pw) {                                // waves double: wave w holds grid * 2^w tiles
-        uint32_t w = 0;
-        while (w < 31 && (uint64_t)grid * ((1ull << w) - 1) < g->n_tiles) ++w;
-        p->waves = w ? w : 1;
-    }
     return 0;
 }
 
@@ -1173,22 +1141,9 @@ static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p) {
         }
         gathered = xchg_gather(g_comm.xchg, r->epoch & 1u, a.world, r->stride);
     }
-    PwArgs pa;
-    pa.s = a;
-    if (p.pw) {
-        pa.ctl = g->d_pw_ctl;
-        pa.wave_tot = s64 + (size_t)g->n_tiles * kPrefWords;
-        pa.range_base = pa.wave_tot + (size_t)p.waves * p.grid;
-        pa.grand = pa.range_base + (size_t)p.waves * p.grid;
-        pa.n_waves = p.waves;
-        pa.timeout_ns = 5ull * 1000 * 1000 * 1000;
-        if (const char *e = getenv("CRP_PW_TIMEOUT_MS")) pa.timeout_ns = strtoull(e, nullptr, 10) * 1000000ull;
-        pa.error = r->h_pw_error;
-        if (p.waves + 1 > kPwMaxWaves) return fail(CRP_ERR_RANGE, "too many waves");
-    }
     CUDA_TRY(cudaEventRecord(r->ev[0], st));
     if (g->n_tiles) {
-        void *params[] = {p.pw ? (void *)&pa : (void *)&a};
+        void *params[] = {(void *)&a};
         CUDA_TRY(cudaLaunchCooperativeKernel(p.fn, dim3(p.grid), dim3(p.threads), params, p.smem, st));
         g_ctx.launches++;
         CUDA_TRY(cudaGetLastError());
@@ -1235,20 +1190,9 @@ static int scan_enqueue(crp_genome *g, int guide_len, uint32_t flags, crp_result
     ScanPlan plan = {};
     if ((rc = plan_scan(g, r->scored, &plan))) return bail(rc);
     r->stride = slots ? slots : n_seg;
-    // state: prefix blocks | k_scan_score: range totals / k_scan_pw: per wave range totals, range bases, grand totals |
-    //        segment counts | two counters
-    r->pw = plan.pw;
-    r->pw_waves = plan.waves;
-    r->pw_grid = plan.grid;
-    const size_t mid_words = plan.pw ? (size_t)plan.waves * (2 * (size_t)plan.grid + 1) : (size_t)plan.grid;
-    r->zero_offset = ((size_t)g->n_tiles * kPrefWords + mid_words) * sizeof(unsigned long long);
+    r->zero_offset = ((size_t)g->n_tiles * kPrefWords + (size_t)plan.grid) * sizeof(unsigned long long);
     r->state_bytes = r->zero_offset + 2 * (size_t)r->stride * sizeof(unsigned long long) +
                      4 * sizeof(unsigned int);
-    if (plan.pw) {
-        r->h_pw_error = static_cast<unsigned int *>(pinned_get(sizeof(unsigned int)));
-        if (!r->h_pw_error) return bail(fail(CRP_ERR_NOMEM, "cudaHostAlloc failed"));
-        *r->h_pw_error = 0;
-    }
     if (dev_alloc(&r->state, r->state_bytes, r->st) != cudaSuccess)
         return bail(fail(CRP_ERR_NOMEM, "cudaMalloc of scan state failed"));
     r->d_counts = reinterpret_cast<unsigned long long *>(r->state + r->zero_offset);
@@ -1317,10 +1261,6 @@ static int scan_finish(crp_genome *g, crp_result *r, cudaStream_t post = nullptr
             }
         }
 #endif
-        if (r->h_pw_error && *r->h_pw_error) {
-            cudaMemsetAsync(g->d_pw_ctl, 0, kPwMaxWaves * sizeof(PwCtl), r->st);     // the launch did not clean up after itself
-            return fail(CRP_ERR_CUDA, "scan kernel: a wave's flag did not come up in time (code %u)", *r->h_pw_error);
-        }
         if (r->fused && *r->h_xchg_error)
             return fail(CRP_ERR_CUDA, "sharded scan: the counts of rank %u did not arrive (peer not scanning?)", *r->h_xchg_error - 1);
         const uint64_t need = r->n_plus > r->n_minus ? r->n_plus : r->n_minus;
@@ -1530,7 +1470,6 @@ int crp_result_free(crp_result *r) {
     pinned_put(r->h_counts);
     pinned_put(r->h_gather);
     pinned_put(r->h_xchg_error);
-    pinned_put(r->h_pw_error);
     if (r->ev_kernel) cudaEventDestroy(r->ev_kernel);
     for (cudaEvent_t e : r->ev)
         if (e) cudaEventDestroy(e);

@@ -34,10 +34,12 @@ T = buf.cpu().numpy().reshape(-1, 8)
 T = T[T[:, 0] > 0]
 t0 = T[:, 0].min()
 rel = (T - t0) / 1000.0
-names = ["start", "count_begin", "count_end", "grid_sync_end", "emit_begin", "emit_end"]
+names = ["start", "count_begin", "count_end", "grid_sync_end", "emit_begin", "emit_end", "slot6", "slot7"]
 print(f"scan {ms * 1e3:.1f} us (events), {len(T)} CTAs; microseconds since the first CTA started")
 for k, n in enumerate(names):
     c = rel[:, k]
+    if not np.isfinite(c).all() or abs(c).max() > 1e7:
+        continue
     print(f"{n:>14}: min {c.min():7.1f}  p50 {np.median(c):7.1f}  p90 {np.percentile(c, 90):7.1f}  max {c.max():7.1f}")
 d = rel[:, 5] - rel[:, 4]
 print(f"emit duration per CTA: min {d.min():.1f} p50 {np.median(d):.1f} max {d.max():.1f}")
