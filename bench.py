@@ -322,6 +322,8 @@ def main():
     ms = float(engine.comm_max([t["ms"]])[0])                      # the slowest rank sets the step
     value = n_bases_total / (ms * 1e-3) / 1e9
     n_cand_total = int(engine.comm_sum([t["candidates"]])[0])
+    per_rank = rdv.all_gather({"rank": rank, "tiles": sum(-(-(b - a) // engine.TILE) for _, a, b in sh.mine),
+                               "candidates": t["candidates"], "kernel_ms": t["kernel_ms"], "step_ms": t["ms"]})
 
     # ---- end to end from host buffers (pinned in, pinned out), through the pipelined C-ABI call:
     # per segment H2D -> pack -> scan+score+logistic -> D2H of (pos, score), then the count exchange
@@ -384,6 +386,7 @@ def main():
         }
         if world > 1:
             line["collective_ms"] = t["ms"] - t["kernel_ms"]
+            line["per_rank"] = per_rank         # what sets the step: equal tiles, unequal candidates (soft-masked repeats carry none)
     # ---- N > 1: the same steps with the other exchange (the default is the fused one when peers map)
     if world > 1:
         fused, why = engine.comm_exchange_info()
