@@ -374,6 +374,7 @@ def main():
                                      "inside the timed events" if world > 1 else "none (1 GPU)",
                        "l2": "flushed between steps (512 MiB memset)", "host_numa_node": numa_node},
             "e2e": {"value": n_bases_total / (e2e * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": e2e,
+                    "ms_each_step_this_rank": [round(v, 3) for v in e2e_ms],
                     "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
                     "rows": "pos u32 + score f64 (CRP_SCAN_LOGISTIC) per candidate; the packed 30-mer stays on the device",
                     "link_ceiling": link},
