@@ -839,39 +839,55 @@ k_scan_score(const ScanArgs a) {
         const uint32_t np = (uint32_t)(tot >> 32), nm = (uint32_t)tot;
         const uint32_t base_p = (uint32_t)(base >> 32), base_m = (uint32_t)base;
         const uint32_t wordA = 64 * warp + lane;
-        const Hits h = tile_hits(rec, td, l, wordA);
-        // ---- warp scan of the per-word counts: the A words of the chunk precede its B words
-        const uint32_t cA = __popc(h.pA) | (__popc(h.mA) << 16), cB = __popc(h.pB) | (__popc(h.mB) << 16);
-        uint32_t iA = cA, iB = cB;
+        // A warp whose 2,048-position chunk holds no hit on either strand -- a soft-masked block, an N run:
+        // half of all chunks on the 50-60 % lower-case configs -- skips its whole front end; the count
+        // phase has already said so (prefix block).  Warp-uniform.
+        const bool busy = ring.pref[s][warp + 1] != ring.pref[s][warp];
+        Hits h = {0u, 0u, 0u, 0u};
+        uint32_t epA = 0, emA = 0, epB = 0, emB = 0;
+        if (busy) {
+            h = tile_hits(rec, td, l, wordA);
+            // ---- warp scan of the per-word counts: the A words of the chunk precede its B words
+            const uint32_t cA = __popc(h.pA) | (__popc(h.mA) << 16), cB = __popc(h.pB) | (__popc(h.mB) << 16);
+            uint32_t iA = cA, iB = cB;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t vA = __shfl_up_sync(0xFFFFFFFFu, iA, o), vB = __shfl_up_sync(0xFFFFFFFFu, iB, o);
-            if (lane >= o) {
-                iA += vA;
-                iB += vB;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t vA = __shfl_up_sync(0xFFFFFFFFu, iA, o), vB = __shfl_up_sync(0xFFFFFFFFu, iB, o);
+                if (lane >= o) {
+                    iA += vA;
+                    iB += vB;
+                }
             }
-        }
-        const uint32_t totA = __shfl_sync(0xFFFFFFFFu, iA, 31);
-        // rank (inside the tile, per strand) of the first hit of my words
-        const uint32_t xA = iA - cA, xB = totA + iB - cB;
-        const uint32_t op = (uint32_t)(off >> 32), om = (uint32_t)off;
-        const uint32_t epA = op + (xA & 0xFFFFu), emA = om + (xA >> 16), epB = op + (xB & 0xFFFFu), emB = om + (xB >> 16);
+            const uint32_t totA = __shfl_sync(0xFFFFFFFFu, iA, 31);
+            // rank (inside the tile, per strand) of the first hit of my words
+            const uint32_t xA = iA - cA, xB = totA + iB - cB;
+            const uint32_t op = (uint32_t)(off >> 32), om = (uint32_t)off;
+            epA = op + (xA & 0xFFFFu), emA = om + (xA >> 16), epB = op + (xB & 0xFFFFu), emB = om + (xB >> 16);
 #ifdef CRP_CHECKED
-        {
-            const uint32_t mine = totA + __shfl_sync(0xFFFFFFFFu, iB, 31);       // hits of my warp chunk, (plus | minus << 16)
-            const unsigned long long nxt = ring.pref[s][warp + 1] - ring.pref[s][warp];
-            CRP_CHECK(a, (uint32_t)(nxt >> 32) == (mine & 0xFFFFu) && (uint32_t)nxt == (mine >> 16), 7);   // count phase == emit phase
-            CRP_CHECK(a, ring.tile[s] == kNoTile || first_pre || ring.tile[s] < nt, 8);
-            CRP_CHECK(a, (unsigned long long)base_p + np <= 0xFFFFFFFFull && (unsigned long long)base_m + nm <= 0xFFFFFFFFull, 9);
-            if (np <= (uint32_t)kListCap && nm <= (uint32_t)kListCap)
-                CRP_CHECK(a, epA + __popc(h.pA) <= np && epB + __popc(h.pB) <= np && emA + __popc(h.mA) <= nm && emB + __popc(h.mB) <= nm, 10);
+            {
+                const uint32_t mine = totA + __shfl_sync(0xFFFFFFFFu, iB, 31);       // hits of my warp chunk, (plus | minus << 16)
+                const unsigned long long nxt = ring.pref[s][warp + 1] - ring.pref[s][warp];
+                CRP_CHECK(a, (uint32_t)(nxt >> 32) == (mine & 0xFFFFu) && (uint32_t)nxt == (mine >> 16), 7);   // count phase == emit phase
+                if (np <= (uint32_t)kListCap && nm <= (uint32_t)kListCap)
+                    CRP_CHECK(a, epA + __popc(h.pA) <= np && epB + __popc(h.pB) <= np && emA + __popc(h.mA) <= nm && emB + __popc(h.mB) <= nm, 10);
+            }
+#endif
         }
+#ifdef CRP_CHECKED
+        else {                                                 // the count phase said "no hit here": verify
+            const Hits hh = tile_hits(rec, td, l, wordA);
+            CRP_CHECK(a, (hh.pA | hh.pB | hh.mA | hh.mB) == 0u, 13);
+        }
+        CRP_CHECK(a, ring.tile[s] == kNoTile || first_pre || ring.tile[s] < nt, 8);
+        CRP_CHECK(a, (unsigned long long)base_p + np <= 0xFFFFFFFFull && (unsigned long long)base_m + nm <= 0xFFFFFFFFull, 9);
 #endif
         if (np <= (uint32_t)kListCap && nm <= (uint32_t)kListCap) {
-            list_hits(list_p + epA, h.pA, 32u * wordA + kWinBiasPlus);
-            list_hits(list_p + epB, h.pB, 32u * (wordA + 32) + kWinBiasPlus);
-            list_hits(list_m + emA, h.mA, 32u * wordA + kWinBiasMinus);
-            list_hits(list_m + emB, h.mB, 32u * (wordA + 32) + kWinBiasMinus);
+            if (busy) {
+                list_hits(list_p + epA, h.pA, 32u * wordA + kWinBiasPlus);
+                list_hits(list_p + epB, h.pB, 32u * (wordA + 32) + kWinBiasPlus);
+                list_hits(list_m + emA, h.mA, 32u * wordA + kWinBiasMinus);
+                list_hits(list_m + emB, h.mB, 32u * (wordA + 32) + kWinBiasMinus);
+            }
             __syncthreads();
             emit_strand<kScore, false>(a, s_tab, rec, list_p, np, base_p, td.t_start, td.L, tid);
             emit_strand<kScore, true>(a, s_tab, rec, list_m, nm, base_m, td.t_start, td.L, tid ^ (kThreads / 2));
@@ -880,10 +896,12 @@ k_scan_score(const ScanArgs a) {
                 const uint32_t cp = np > lo ? min(np - lo, (uint32_t)kListCap) : 0u;
                 const uint32_t cm = nm > lo ? min(nm - lo, (uint32_t)kListCap) : 0u;
                 if (lo) __syncthreads();
-                list_hits_window(list_p, h.pA, epA, 32u * wordA + kWinBiasPlus, lo);
-                list_hits_window(list_p, h.pB, epB, 32u * (wordA + 32) + kWinBiasPlus, lo);
-                list_hits_window(list_m, h.mA, emA, 32u * wordA + kWinBiasMinus, lo);
-                list_hits_window(list_m, h.mB, emB, 32u * (wordA + 32) + kWinBiasMinus, lo);
+                if (busy) {
+                    list_hits_window(list_p, h.pA, epA, 32u * wordA + kWinBiasPlus, lo);
+                    list_hits_window(list_p, h.pB, epB, 32u * (wordA + 32) + kWinBiasPlus, lo);
+                    list_hits_window(list_m, h.mA, emA, 32u * wordA + kWinBiasMinus, lo);
+                    list_hits_window(list_m, h.mB, emB, 32u * (wordA + 32) + kWinBiasMinus, lo);
+                }
                 __syncthreads();
                 emit_strand<kScore, false>(a, s_tab, rec, list_p, cp, base_p + lo, td.t_start, td.L, tid);
                 emit_strand<kScore, true>(a, s_tab, rec, list_m, cm, base_m + lo, td.t_start, td.L, tid);
