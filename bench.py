@@ -330,7 +330,8 @@ def main():
     segs = [(k, sh.host_tokens[k], a, b) for k, a, b in sh.mine]
     want = ("pos", "x")
     arena, e2e_ms, h2d, d2h = None, [], 0, 0
-    for i in range(args.warmup + max(3, args.steps // 2)):
+    e2e_warmup = max(args.warmup, 5)           # the block cache of the pipelined call settles within the first calls
+    for i in range(e2e_warmup + max(3, args.steps // 2)):
         engine.comm_barrier()
         t0 = time.perf_counter()
         arena, n_plus, n_minus, _ = engine.scan_segments(segs, 20, flags=N.CRP_SCAN_LOGISTIC, arena=arena, want=want)
@@ -342,7 +343,7 @@ def main():
                                         for r in range(world)])
         engine.comm_barrier()
         dt = (time.perf_counter() - t0) * 1e3
-        if i >= args.warmup:
+        if i >= e2e_warmup:
             e2e_ms.append(dt)
         h2d = sum(min(b + 32, sh.lengths[k]) - max(a - 32, 0) for k, a, b in sh.mine)
         d2h = 12 * int(n_plus.sum() + n_minus.sum())
