@@ -20,6 +20,7 @@
 #include <charconv>
 #include <string>
 #include <thread>
+#include <mutex>
 #include <vector>
 
 #include "../../include/cropsr_b200.h"
@@ -230,6 +231,8 @@ extern "C" int crp_format_rows(uint64_t n_rows, const char *ids, const uint64_t 
     // every thread formats its rows into its own region of a scratch buffer that lives as long as
     // the library (fresh 100+ MB buffers per call cost more in page faults than the formatting),
     // then the regions are copied, again in parallel, to their final offsets in out
+    static std::mutex scratch_mu;                 // one call at a time per process: concurrent callers queue here
+    std::lock_guard<std::mutex> scratch_lock(scratch_mu);
     static std::vector<char> scratch;
     const size_t row_max = max_row_bytes(j, n_tokens);
     const uint64_t per = (n_rows + nt - 1) / nt;
