@@ -26,7 +26,6 @@
 #define CRP_CTAS_PER_SM 4
 #endif
 #include "scan.cuh"
-#include "scan2.cuh"
 #include "primers.cuh"
 #include "extras.cuh"
 
@@ -125,7 +124,6 @@ struct crp_result {
     unsigned long long *packed[2] = {nullptr, nullptr};
     double *x[2] = {nullptr, nullptr};
     unsigned char *state = nullptr;            // warp_pref | cta_tot | segment counts | tickets, one allocation
-    unsigned char *lists = nullptr;            // k_scan_lists: [n_tiles][4 KB] hit lists written by the count phase
     size_t state_bytes = 0, zero_offset = 0;   // segment counts and tickets start at zero_offset
     unsigned long long *d_counts = nullptr;    // [2*stride], inside state
     std::vector<uint64_t> seg_plus, seg_minus;
@@ -1061,29 +1059,16 @@ struct ScanPlan {
     const void *fn;
     unsigned grid, threads;
     size_t smem;
-    bool lists;                 // k_scan_lists (hit lists built by the count phase) instead of k_scan_score
 };
-
-// CRP_SCAN_LISTS=0 selects k_scan_score (the emit phase compacts the hits itself)
-static bool use_lists() {
-    const char *e = getenv("CRP_SCAN_LISTS");
-    return !(e && e[0] == '0');
-}
 
 static int plan_scan(const crp_genome *g, bool scored, ScanPlan *p) {
     p->threads = kThreads;
-    p->lists = use_lists();
+    p->fn = scored ? (const void *)k_scan_score<true> : (const void *)k_scan_score<false>;
     const unsigned grid_max = (unsigned)g_ctx.sm_count * CRP_CTAS_PER_SM;
-    if (p->lists) {
-        p->fn = scored ? (const void *)k_scan_lists<true> : (const void *)k_scan_lists<false>;
-        p->smem = smem_bytes2(grid_max);
-    } else {
-        p->fn = scored ? (const void *)k_scan_score<true> : (const void *)k_scan_score<false>;
-        p->smem = kScanSmemFixed + (size_t)grid_max * sizeof(unsigned long long);
-        if (p->smem < (size_t)kCountStages * kPamBytes) p->smem = (size_t)kCountStages * kPamBytes;   // the count ring reuses all of it
-    }
-    static int per_sm_cache[4] = {0, 0, 0, 0};  // occupancy of the four instantiations, queried once
-    int &per_sm = per_sm_cache[(scored ? 1 : 0) + (p->lists ? 2 : 0)];
+    p->smem = kScanSmemFixed + (size_t)grid_max * sizeof(unsigned long long);
+    if (p->smem < (size_t)kCountStages * kPamBytes) p->smem = (size_t)kCountStages * kPamBytes;   // the count ring reuses all of it
+    static int per_sm_cache[2] = {0, 0};       // occupancy of the two instantiations, queried once
+    int &per_sm = per_sm_cache[scored ? 1 : 0];
     if (per_sm == 0) {
         CUDA_TRY(cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p->fn, kThreads, p->smem));
@@ -1156,19 +1141,10 @@ static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p) {
         }
         gathered = xchg_gather(g_comm.xchg, r->epoch & 1u, a.world, r->stride);
     }
-    ListArgs la;
-    la.s = a;
-    la.lists = r->lists;
-    if (p.lists && g->n_tiles && !r->lists) {                  // the rerun after a capacity overflow reuses the result
-        if (dev_alloc(&r->lists, (size_t)g->n_tiles * kListBytes + 16, st) != cudaSuccess)
-            return fail(CRP_ERR_NOMEM, "cudaMalloc of the hit lists failed");
-        la.lists = r->lists;
-    }
     CUDA_TRY(cudaEventRecord(r->ev[0], st));
     if (g->n_tiles) {
-        void *params[] = {p.lists ? (void *)&la : (void *)&a};
-        const size_t smem = p.lists ? smem_bytes2(p.grid) : p.smem;
-        CUDA_TRY(cudaLaunchCooperativeKernel(p.fn, dim3(p.grid), dim3(p.threads), params, smem, st));
+        void *params[] = {(void *)&a};
+        CUDA_TRY(cudaLaunchCooperativeKernel(p.fn, dim3(p.grid), dim3(p.threads), params, p.smem, st));
         g_ctx.launches++;
         CUDA_TRY(cudaGetLastError());
     } else if (r->fused) {
@@ -1219,9 +1195,6 @@ static int scan_enqueue(crp_genome *g, int guide_len, uint32_t flags, crp_result
                      4 * sizeof(unsigned int);
     if (dev_alloc(&r->state, r->state_bytes, r->st) != cudaSuccess)
         return bail(fail(CRP_ERR_NOMEM, "cudaMalloc of scan state failed"));
-    if (plan.lists && dev_alloc(&r->lists, (size_t)g->n_tiles * kListBytes + 16, r->st) != cudaSuccess)
-        return bail(fail(CRP_ERR_NOMEM, "cudaMalloc of the hit lists (%llu bytes) failed",
-                         (unsigned long long)g->n_tiles * kListBytes));
     r->d_counts = reinterpret_cast<unsigned long long *>(r->state + r->zero_offset);
     r->h_counts = static_cast<unsigned long long *>(pinned_get((2 * (size_t)r->stride + 1) * sizeof(unsigned long long)));
     if (!r->h_counts) return bail(fail(CRP_ERR_NOMEM, "cudaHostAlloc of the counts failed"));
@@ -1493,7 +1466,6 @@ int crp_result_free(crp_result *r) {
     if (!r) return 0;
     free_streams(r);
     dev_free(r->state, r->st);
-    dev_free(r->lists, r->st);
     dev_free(r->d_gather, r->st);
     pinned_put(r->h_counts);
     pinned_put(r->h_gather);
