@@ -6,7 +6,10 @@ __version__ = "1.11b-b200"
 
 
 def build_parser():
-    p = argparse.ArgumentParser(prog="CROPSR.py")
+    # the usage line is spelled out: with the reference's empty metavars argparse cannot wrap a usage
+    # line of this length (its own consistency assertion fails), and --help would crash
+    p = argparse.ArgumentParser(prog="CROPSR.py", usage="CROPSR.py [-h] -f FASTA [-g GFF] [-p TXT] [-o CSV] [-l 20] [-L 200] --cas9 [-v]\n"
+                                "                 [--device N | --devices 0-7] [--side-output TSV] [--blas-threads N]")
     p.add_argument("-f", "--fasta", metavar="", required=True, dest="f",
                    help="[required] path to input file in FASTA format")
     p.add_argument("-g", "--gff", metavar="", dest="g", help="path to input file in GFF format")

@@ -348,3 +348,16 @@ def test_shard_plan_tiles_the_genome_and_balances_tiles(built_lib):
     big = [80_000_000] * 6 + [random.randint(10_000, 500_000) for _ in range(4000)]
     tiles = [sum(-(-(b - a) // shard.TILE) for _, a, b in p) for p in shard.plan(big, 8)]
     assert max(tiles) - min(tiles) <= 2
+
+
+def test_cli_help_and_missing_system(built_lib, capsys):
+    """--help prints (argparse cannot wrap the auto-generated usage line with the reference's empty metavars);
+    without --cas9 the CLI exits with the reference's message (CROPSR.py:335-336)."""
+    from cropsr_b200 import cli
+    with pytest.raises(SystemExit) as e:
+        cli.main(["--help"])
+    assert e.value.code == 0 and "--cas9" in capsys.readouterr().out
+    with pytest.raises(SystemExit) as e:
+        cli.main(["-f", "x.fa"])
+    assert e.value.code == "Please select at least one CRISPR system: Cas9"
+    assert cli.parse_devices("0-3") == [0, 1, 2, 3] and cli.parse_devices("0,2,5") == [0, 2, 5]
