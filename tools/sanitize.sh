@@ -1,5 +1,7 @@
 #!/bin/bash
 # compute-sanitizer over the scan kernel's small cases (on the GPU box, via gpurun):
+# NOTE: on the GPU pool this repository was developed on, compute-sanitizer is closed (every tool answers with a
+# refusal, profiles/r2_sanitizer_refused/); the script is kept for pools where it runs.  Stand-in: make checked.
 #   bash tools/sanitize.sh            -> gpurun_out/sanitize_{memcheck,synccheck,racecheck,initcheck}.log
 # Cases: smoke() (two segments, lane tables, both strands), the edge_fmt / multi3 golden CLIs, count
 # ranges longer than one batch with 1-7 CTAs (ring refills, running prefix), static / ticketed tile
