@@ -95,6 +95,7 @@ SIGNATURES = {
     "crp_result_extras_strand": (C.c_int, [C.c_void_p, C.c_char, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
     "crp_result_annotate_strand": (C.c_int, [C.c_void_p, C.c_char, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "crp_genome_other_runs": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, _u64p]),
     "crp_primer_windows": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PrimerParams),
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "crp_legacy_ids": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_uint64, C.c_void_p]),

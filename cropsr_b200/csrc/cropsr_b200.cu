@@ -14,6 +14,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <stdlib.h>
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <new>
@@ -1801,6 +1802,84 @@ int crp_result_annotate_strand(const crp_result *res, char strand, const uint64_
     dev_free(d_iv, st);
     dev_free(d_f, st);
     return rc;
+}
+
+/* Runs of bytes that are not A C G T a c g t inside one segment (the gaps of an assembly: N, IUPAC codes,
+ * anything else), at least min_len long: (start, length) in token coordinates, ascending. */
+int crp_genome_other_runs(const crp_genome *g, uint32_t segment, uint32_t min_len, uint64_t capacity, uint32_t *start,
+                          uint32_t *length, uint64_t *n_runs) {
+    if (!g || !n_runs) return fail(CRP_ERR_ARG, "NULL argument");
+    if (int rc = need_ctx()) return rc;
+    if (!g->committed) return fail(CRP_ERR_STATE, "genome is not committed");
+    if (segment >= g->segs.size()) return fail(CRP_ERR_ARG, "segment %u out of range", segment);
+    if (capacity && (!start || !length)) return fail(CRP_ERR_ARG, "NULL output arrays");
+    const Segment &sg = g->segs[segment];
+    *n_runs = 0;
+    if (!sg.n_tiles) return 0;
+    cudaStream_t st = stream_of(g);
+    // boundaries of ALL runs first (the length filter needs both ends); a segment rarely holds more than a few thousand
+    uint32_t cap = 1u << 16;
+    std::vector<uint32_t> hs, he;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        uint32_t *d = nullptr;
+        unsigned int *d_n = nullptr;
+        CUDA_TRY(dev_alloc(&d, 2 * (size_t)cap * sizeof(uint32_t), st));
+        if (dev_alloc(&d_n, 2 * sizeof(unsigned int), st) != cudaSuccess) {
+            dev_free(d, st);
+            return fail(CRP_ERR_NOMEM, "cudaMalloc failed");
+        }
+        RunArgs a;
+        a.records = g->records;
+        a.first_tile = sg.first_tile;
+        a.n_tiles = sg.n_tiles;
+        a.seg_begin = (uint32_t)sg.begin;
+        a.seg_end = (uint32_t)sg.end;
+        a.starts = d;
+        a.ends = d + cap;
+        a.n_starts = d_n;
+        a.n_ends = d_n + 1;
+        a.capacity = cap;
+        unsigned int n[2] = {0, 0};
+        int rc = 0;
+        const uint64_t items = (uint64_t)sg.n_tiles * kTileWords;
+        if (cudaMemsetAsync(d_n, 0, 2 * sizeof(unsigned int), st) != cudaSuccess) rc = fail(CRP_ERR_CUDA, "memset failed");
+        if (!rc) {
+            k_other_runs<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(a);
+            g_ctx.launches++;
+            if (cudaMemcpyAsync(n, d_n, sizeof n, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+                rc = fail(CRP_ERR_CUDA, "run kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        if (!rc && n[0] != n[1]) rc = fail(CRP_ERR_STATE, "run boundaries do not pair up (%u starts, %u ends)", n[0], n[1]);
+        if (!rc && n[0] <= cap) {
+            hs.resize(n[0]);
+            he.resize(n[0]);
+            if (n[0] && (cudaMemcpyAsync(hs.data(), a.starts, n[0] * sizeof(uint32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                         cudaMemcpyAsync(he.data(), a.ends, n[0] * sizeof(uint32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                         cudaStreamSynchronize(st) != cudaSuccess))
+                rc = fail(CRP_ERR_CUDA, "D2H of run boundaries failed");
+        }
+        dev_free(d, st);
+        dev_free(d_n, st);
+        if (rc) return rc;
+        if (n[0] <= cap) break;
+        if (attempt == 1) return fail(CRP_ERR_RANGE, "more than %u runs in one segment", cap);
+        cap = n[0];
+    }
+    std::sort(hs.begin(), hs.end());
+    std::sort(he.begin(), he.end());
+    uint64_t kept = 0;
+    for (size_t i = 0; i < hs.size(); ++i) {
+        const uint32_t len = he[i] - hs[i] + 1;
+        if (len < min_len) continue;
+        if (kept < capacity) {
+            start[kept] = hs[i];
+            length[kept] = len;
+        }
+        ++kept;
+    }
+    *n_runs = kept;
+    if (kept > capacity) return fail(CRP_ERR_RANGE, "%llu runs, room for %llu", (unsigned long long)kept, (unsigned long long)capacity);
+    return 0;
 }
 
 int crp_primer_windows(const crp_genome *g, uint64_t n, const uint32_t *segment, const uint32_t *lo, const uint32_t *hi,

@@ -81,3 +81,52 @@ __global__ void k_annotate(const uint32_t *__restrict__ pos, uint64_t n, int min
         }
     feature[i] = found;
 }
+
+
+// ------------------------------------------------------------------ runs of bytes that are not A C G T a c g t
+// SURVEY.md 8f.2 ("N-run side table"): the gaps of an assembly -- runs of N, IUPAC codes or any other byte --
+// as (start, length) in token coordinates, read off the `other` plane of the tile records.  One thread per
+// tile word: a set bit whose predecessor is clear starts a run, one whose successor is clear ends it; the
+// boundaries go to two unordered lists (runs are disjoint, so the i-th smallest start pairs with the i-th
+// smallest end on the host).  Positions outside the segment never count, and runs are clipped to it.
+struct RunArgs {
+    const uint4 *records;
+    uint32_t first_tile, n_tiles;
+    uint32_t seg_begin, seg_end;        // token positions the segment owns
+    uint32_t *starts, *ends;            // token positions (end = last position of the run)
+    unsigned int *n_starts, *n_ends;    // counters (the lists hold at most `capacity` entries each; the counters keep counting)
+    uint32_t capacity;
+};
+
+__global__ void k_other_runs(const RunArgs a) {
+    const uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= (uint64_t)a.n_tiles * kTileWords) return;
+    const uint32_t tile = (uint32_t)(it / kTileWords), k = (uint32_t)(it % kTileWords);
+    const uint4 *rec = a.records + (size_t)(a.first_tile + tile) * kRecWords;
+    const uint4 d = rec[0];
+    const uint32_t t_start = d.x, n_owned = d.z;                  // owned positions of this tile: [0, n_owned)
+    const uint32_t p0 = 32u * k;                                  // first position of my word inside the tile
+    if (p0 >= n_owned) return;
+    const uint32_t own = n_owned - p0 >= 32u ? 0xFFFFFFFFu : (1u << (n_owned - p0)) - 1u;
+    const uint32_t o = rec[2 + k].w & own;
+    if (!o) return;
+    // neighbours: the bit before my word and the bit after it (halo words at the tile edges), 0 where the
+    // segment starts / ends
+    const uint32_t first = t_start + p0;
+    const uint32_t prev = first > a.seg_begin ? rec[1 + k].w >> 31 : 0u;
+    const uint32_t next = first + 32u < a.seg_end ? rec[3 + k].w & 1u : 0u;
+    uint32_t st = o & ~((o << 1) | prev);
+    uint32_t en = o & ~((o >> 1) | (next << 31));
+    while (st) {
+        const uint32_t b = __ffs(st) - 1;
+        st &= st - 1;
+        const unsigned int slot = atomicAdd(a.n_starts, 1u);
+        if (slot < a.capacity) a.starts[slot] = t_start + p0 + b;
+    }
+    while (en) {
+        const uint32_t b = __ffs(en) - 1;
+        en &= en - 1;
+        const unsigned int slot = atomicAdd(a.n_ends, 1u);
+        if (slot < a.capacity) a.ends[slot] = t_start + p0 + b;
+    }
+}

@@ -387,6 +387,23 @@ class Genome:
                                   cls.ctypes.data, out.ctypes.data))
         return out
 
+    def other_runs(self, segment, min_len=1):
+        """Gap table of one segment: runs of bytes that are not ACGTacgt, at least min_len long.
+        -> (start uint32[], length uint32[]) in token coordinates, ascending."""
+        cap = 4096
+        for _ in range(2):
+            start = np.empty(cap, np.uint32)
+            length = np.empty(cap, np.uint32)
+            n = C.c_uint64(0)
+            rc = lib.crp_genome_other_runs(self._h, int(segment), int(min_len), cap, start.ctypes.data, length.ctypes.data,
+                                           C.byref(n))
+            if rc == -5 and n.value > cap:
+                cap = int(n.value)
+                continue
+            check(rc)
+            return start[:n.value], length[:n.value]
+        raise CropsrError(-5, "gap table: capacity negotiation failed")
+
     def free(self):
         if self._h:
             check(lib.crp_genome_free(self._h))

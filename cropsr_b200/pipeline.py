@@ -252,6 +252,20 @@ def write_side_output(path, tokens, scan, gff_frame, flank, formatted_path, anno
         frame.iloc[order].to_csv(path, sep="\t", mode="a", header=False, index=False, lineterminator="\r\n")
 
 
+def write_gap_table(path, tokens, scan, min_len=10):
+    """Opt-in companion of the side output: the gaps of the assembly -- runs of at least
+    min_len bytes that are not ACGTacgt (N, IUPAC) -- one row per run, token coordinates, read off the packed
+    records on the device (Genome.other_runs / k_other_runs).  Not part of the reference's output."""
+    import csv
+    with open(path, "w", newline="") as f:
+        w = csv.writer(f, delimiter="\t")
+        w.writerow(["chromosome", "start", "length"])
+        for k, key in enumerate(tokens.keys()):
+            genome, _, seg = scan.locate(k)
+            start, length = genome.other_runs(seg, min_len)
+            w.writerows((key[1:], int(a), int(b)) for a, b in zip(start.tolist(), length.tolist()))
+
+
 def run_cas9(fasta, gff, output="data.csv", guide_len=20, verbose=False, blas_threads=1,
              time_path="time.txt", out=print, side_output=None, flank=200, device_ingest=True, annotation_info=None,
              chunk_rows=None, devices=None, handle_limit=None):
@@ -309,6 +323,7 @@ def run_cas9(fasta, gff, output="data.csv", guide_len=20, verbose=False, blas_th
         with open(fasta, "r") as f:
             formatted_path = ingest.needs_formatting(f.read())
         write_side_output(side_output, tokens, scan, gff_frame, flank, formatted_path, annotation_info)
+        write_gap_table(side_output + ".gaps.tsv", tokens, scan)
     stats = {"tokens": len(tokens), "candidates": len(table), "rows": rows_written,
              "scan_ms": scan.scan_ms(), **scan.timing()}
     t_plus = x_plus = t_minus = x_minus = None          # views into the scan's row arrays

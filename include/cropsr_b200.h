@@ -255,6 +255,13 @@ int crp_result_extras(const crp_result *res, uint32_t segment, char strand, uint
 int crp_result_extras_strand(const crp_result *res, char strand, uint32_t flank,
                              uint8_t *gc, uint8_t *flags, uint8_t *run,
                              uint32_t *cut, uint32_t *flank_lo, uint32_t *flank_hi);
+/* Gap table of one segment (opt-in; the reference has nothing like it): maximal runs of
+ * bytes that are not A C G T a c g t -- N, IUPAC codes, anything else; the quote / paren decoration of a
+ * formatted-path token is such a run too -- at least min_len long, read off the packed records on the
+ * device: start[i] (token coordinate) and length[i], ascending.  *n_runs receives the number of runs;
+ * CRP_ERR_RANGE if it exceeds `capacity` (call again with more room). */
+int crp_genome_other_runs(const crp_genome *g, uint32_t segment, uint32_t min_len, uint64_t capacity,
+                          uint32_t *start, uint32_t *length, uint64_t *n_runs);
 /* feature[i] = index of the innermost interval [start, end] (inclusive, token
  * coordinates, sorted by start) that contains candidate i's cut site, or -1:
  * a binary search per candidate in device memory. */

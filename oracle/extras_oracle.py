@@ -53,3 +53,10 @@ def annotate(cuts, start, end):
                 hit = j
         res.append(hit)
     return np.array(res, dtype=np.int32)
+
+
+def other_runs(token, min_len=1):
+    """Gap table: maximal runs of bytes that are not A C G T a c g t, at least min_len long.
+    -> [(start, length)] ascending (UNPINNED BY THE REFERENCE, like everything in this module)."""
+    import re
+    return [(m.start(), m.end() - m.start()) for m in re.finditer(r"[^ACGTacgt]+", token) if m.end() - m.start() >= min_len]

@@ -775,3 +775,49 @@ def test_perf_report_counts_what_ran(eng):
     assert after["candidates"] == before["candidates"] + n
     assert after["positions_packed"] == before["positions_packed"] + sum(len(t) for t in tokens.values())
     assert after["kernel_launches"] >= before["kernel_launches"] + 2 and after["d2h_row_bytes"] > before["d2h_row_bytes"]
+
+
+def test_gap_table_matches_oracle(eng, tmp_path):
+    """Genome.other_runs (k_other_runs: runs of bytes that are not ACGTacgt, read off the `other` plane of the
+    packed records) against the string oracle: N runs across tile edges, at the token ends, IUPAC singletons,
+    the decoration of formatted-path tokens, several segments of one token."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+    import extras_oracle
+    from cropsr_b200 import engine, ingest
+    rng = np.random.default_rng(5)
+    body = bytearray(synthetic_fasta(6, [70000], gc=0.5, lower_frac=0.3, n_frac=0.0005, width=10**9).split("\\n")[1].encode())
+    for lo, n in ((0, 7), (16380, 9), (16384 * 2 - 3, 40), (32768, 1), (40000, 5000), (69990, 10)):
+        body[lo:lo + n] = b"N" * n
+    text = ">g\\n" + "\\n".join(body.decode()[i:i + 80] for i in range(0, len(body), 80)) + "\\n>h\\nNNACGTNN\\n>i\\nACGT\\n"
+    tokens = ingest.fasta_text_to_tokens(text)
+    g = engine.Genome()
+    for tok in tokens.values():
+        g.add_token(tok)
+    g.commit()
+    try:
+        for seg, tok in enumerate(tokens.values()):
+            for min_len in (1, 4, 10):
+                start, length = g.other_runs(seg, min_len)
+                assert list(zip(start.tolist(), length.tolist())) == extras_oracle.other_runs(tok, min_len), (seg, min_len)
+    finally:
+        g.free()
+    # one token cut into tile-aligned segments: the runs of the pieces, clipped at the cuts, tile the token's runs
+    tok = list(tokens.values())[0]
+    g = engine.Genome()
+    cuts = [0, 16384, 49152, len(tok)]
+    for a, b in zip(cuts, cuts[1:]):
+        g.add_segment(0, tok, a, b)
+    g.commit()
+    try:
+        covered = np.zeros(len(tok), bool)
+        for seg in range(3):
+            for a, n in zip(*[x.tolist() for x in g.other_runs(seg, 1)]):
+                assert cuts[seg] <= a and a + n <= cuts[seg + 1] and not covered[a:a + n].any()
+                covered[a:a + n] = True
+        want = np.zeros(len(tok), bool)
+        for a, n in extras_oracle.other_runs(tok, 1):
+            want[a:a + n] = True
+        assert np.array_equal(covered, want)
+    finally:
+        g.free()
