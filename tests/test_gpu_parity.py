@@ -786,10 +786,10 @@ def test_gap_table_matches_oracle(eng, tmp_path):
     import extras_oracle
     from cropsr_b200 import engine, ingest
     rng = np.random.default_rng(5)
-    body = bytearray(synthetic_fasta(6, [70000], gc=0.5, lower_frac=0.3, n_frac=0.0005, width=10**9).split("\\n")[1].encode())
+    body = bytearray(synthetic_fasta(6, [70000], gc=0.5, lower_frac=0.3, n_frac=0.0005, width=10**9).split("\n")[1].encode())
     for lo, n in ((0, 7), (16380, 9), (16384 * 2 - 3, 40), (32768, 1), (40000, 5000), (69990, 10)):
         body[lo:lo + n] = b"N" * n
-    text = ">g\\n" + "\\n".join(body.decode()[i:i + 80] for i in range(0, len(body), 80)) + "\\n>h\\nNNACGTNN\\n>i\\nACGT\\n"
+    text = ">g\n" + "\n".join(body.decode()[i:i + 80] for i in range(0, len(body), 80)) + "\n>h\nNNACGTNN\n>i\nACGT\n"
     tokens = ingest.fasta_text_to_tokens(text)
     g = engine.Genome()
     for tok in tokens.values():
