@@ -108,6 +108,22 @@ def measured_peak():
 
 
 # ---------------------------------------------------------------------------------- CPU arm
+_SAMPLE_CACHE = {}
+
+
+def _reference_sample_files(workload, per, n_rec):
+    """The sample FASTA / GFF of a workload, written once per process (generating five chromosomes costs
+    seconds; the reference arm runs the same sample every step)."""
+    key = (workload, per, n_rec)
+    if key not in _SAMPLE_CACHE:
+        wd = tempfile.mkdtemp(prefix="cropsr_ref_sample_")
+        fa, gff = os.path.join(wd, "sample.fa"), os.path.join(wd, "sample.gff")
+        W.write_fasta(workload, fa, records=range(n_rec), prefix_bases=per)
+        W.write_gff(workload, gff, records=range(n_rec), prefix_bases=per)
+        _SAMPLE_CACHE[key] = (fa, gff)
+    return _SAMPLE_CACHE[key]
+
+
 def reference_sample(workload, seconds_target):
     """One run of the reference's CPU implementation on a bounded MULTI-RECORD sample of the
     workload: the first `per` bases of each of its first (up to) 5 records, written as the same
@@ -119,10 +135,8 @@ def reference_sample(workload, seconds_target):
     n_rec = min(5, len(W.lengths(workload)))
     # ~0.19 Mbp/s in-program on this class of host, cumulative re-emission of earlier records included
     per = int(max(20_000, min(min(W.lengths(workload)[:n_rec]), seconds_target * 0.17e6 / n_rec)))
+    fa, gff = _reference_sample_files(workload, per, n_rec)
     with tempfile.TemporaryDirectory() as wd:
-        fa, gff = os.path.join(wd, "sample.fa"), os.path.join(wd, "sample.gff")
-        W.write_fasta(workload, fa, records=range(n_rec), prefix_bases=per)
-        W.write_gff(workload, gff, records=range(n_rec), prefix_bases=per)
         n_bases = per * n_rec
         what = (f"first {per} bp of each of the first {n_rec} records of the {workload} workload "
                 f"({n_bases} bp, 80-column FASTA + synthetic GFF)")
