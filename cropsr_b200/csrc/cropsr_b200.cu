@@ -32,7 +32,7 @@
 
 #define CRP_ABI_VERSION 7
 
-static constexpr size_t kScanSmemFixed = (size_t)kStages * kRecBytes + 2 * (size_t)kListCap * sizeof(uint16_t);
+static constexpr size_t kScanSmemFixed = (size_t)kStages * kRecBytes + kListBufs * 2 * (size_t)kListCap * sizeof(uint16_t);
 
 // ------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";

@@ -96,7 +96,8 @@ def valid_states(entries):
 GC_MODEL = 0.42                 # base composition of the Monte-Carlo that ranks hash candidates
 SEQUENTIAL_MAX = 3               # lanes with at most this many entries are summed without a table
 SWIZZLE_MIN_BITS = 6            # lanes with at least this many index bits add their top 4 hash bits to the slot              # bit-flip hill climbing on the best candidate
-N_CANDIDATES = 24               # injective hashes collected per lane before the best one is kept
+N_CANDIDATES = int(os.environ.get("RS1_NCAND", "80"))               # injective hashes collected per lane before the best one is kept
+EFFORT = int(os.environ.get("RS1_EFFORT", "2"))   # multiplies the length of the random search
 MERGE_GROUPS = True             # dinucleotide groups at disjoint positions: one bit select + one multiply for the set
 
 
@@ -132,6 +133,20 @@ def expected_wavefronts(slots, offset):
         u = np.unique(row)
         total += np.bincount(u & 15, minlength=16).max()
     return 2.0 * total / len(s)
+
+
+SWIZZLE_SPARE = (8, 16, 24, 32, 48, 64)    # spare slots tried for a swizzled table (its size is 2^bits + spare)
+
+
+def slot_of(h, bits, mul):
+    """table slot of the 32-bit hash h (uint64 array holding values < 2^32).
+    mul == 0 (narrow tables): the top `bits` bits.  Otherwise the high word of h * mul, mul = 2^bits + spare
+    -- ONE multiply-high on the device: the top bits, plus the top few bits again (which spreads the probable
+    states over the shared-memory banks), plus a carry out of the low part; find_hash demands that the
+    result is injective over the lane's states, and the table has `mul` slots."""
+    if mul:
+        return (h * np.uint64(mul)) >> np.uint64(32)
+    return h >> np.uint64(32 - bits)
 
 
 def find_hash(entries, seed, offset):
@@ -176,8 +191,9 @@ def find_hash(entries, seed, offset):
         return m
 
     for bits in (need, need + 1, need + 2):
-        found = []
-        for t in range(6000 if bits == need else 800):
+        muls = [(1 << bits) + sp for sp in SWIZZLE_SPARE] if bits >= SWIZZLE_MIN_BITS else [0]
+        found = []                                  # (magics, mul)
+        for t in range((6000 if bits == need else 800) * EFFORT):
             acc = np.zeros((batch, len(states)), dtype=np.uint64)
             mags = [None] * len(glist)
             for st_ in sets:
@@ -185,36 +201,28 @@ def find_hash(entries, seed, offset):
                 for gi in st_:
                     mags[gi] = mg
                     acc += (pat[gi][None, :] * mg[:, None]) & m32
-            h = (acc & m32) >> np.uint64(32 - bits)
-            h.sort(axis=1)
-            ok = (np.diff(h.astype(np.int64), axis=1) != 0).all(axis=1) if len(states) > 1 else np.ones(batch, bool)
-            for k in np.nonzero(ok)[0]:
-                found.append([int(mags[gi][k]) for gi in range(len(glist))])
-            if len(found) >= N_CANDIDATES or (found and t > 1500):
+            acc &= m32
+            for mul in muls:
+                h = slot_of(acc, bits, mul)
+                h.sort(axis=1)
+                ok = (np.diff(h.astype(np.int64), axis=1) != 0).all(axis=1) if len(states) > 1 else np.ones(batch, bool)
+                for k in np.nonzero(ok)[0]:
+                    found.append(([int(mags[gi][k]) for gi in range(len(glist))], mul))
+            if len(found) >= N_CANDIDATES or (found and t > 1500 * EFFORT):
                 break
         if found:
-            def cost_of(mg):
+            def cost_of(mg, mul):
                 hh = np.zeros(len(mc), dtype=np.uint64)
                 for gi in range(len(glist)):
                     hh += (mc_pat[gi] * np.uint64(mg[gi])) & m32
-                sl = ((hh & m32) >> np.uint64(32 - bits)).astype(np.int64)
-                if bits >= SWIZZLE_MIN_BITS:
-                    sl += sl >> (bits - 4)
-                return expected_wavefronts(sl, offset)
+                return expected_wavefronts(slot_of(hh & m32, bits, mul).astype(np.int64), offset)
 
-            def injective(mg):
-                acc = np.zeros(len(states), dtype=np.uint64)
-                for gi in range(len(glist)):
-                    acc += (pat[gi] * np.uint64(mg[gi])) & m32
-                h = (acc & m32) >> np.uint64(32 - bits)
-                return len(np.unique(h)) == len(states)
-
-            best = min(((cost_of(mg), mg) for mg in found[:N_CANDIDATES]), key=lambda t: t[0])
+            cost, (mg, mul) = min(((cost_of(*c), c) for c in found[:N_CANDIDATES]), key=lambda t: t[0])
             import sys
             print(f"lane hash: {len(states)} states, {bits} bits, {len(found)} candidates, expected wavefronts "
-                  f"{best[0]:.2f}{' (additive swizzle)' if bits >= SWIZZLE_MIN_BITS else ''}", file=sys.stderr)
-            return bits, [(c1, sum(1 << bit_of(entries[i]) for i in idxs), best[1][gi])
-                          for gi, (c1, idxs) in enumerate(glist)], sets
+                  f"{cost:.2f}" + (f" (table of {mul} slots)" if mul else ""), file=sys.stderr)
+            return bits, mul, [(c1, sum(1 << bit_of(entries[i]) for i in idxs), mg[gi])
+                               for gi, (c1, idxs) in enumerate(glist)], sets
     raise SystemExit("no perfect hash found")
 
 
@@ -237,9 +245,9 @@ def main():
     emit("// shifted left by one); forced: the entry matches every scanned 30-mer (PAM bases) and has no bit")
     emit("struct Rs1Entry { int pos; int first_base; double weight; int bit; int forced; };     // first_base < 0: first-order term")
     emit("struct Rs1Group { int first_base; unsigned mask; unsigned magic; };")
-    emit("// table slot of a set of matching entries: s = (sum over groups of x_g * magic  mod 2^32) >> (32 - bits),")
-    emit("// then s + (s >> (bits - 4)) if swizzle: injective (the table has 16 spare slots), costs no ALU instruction")
-    emit("// (the add rides on the multiply-high) and spreads the probable states over the shared-memory banks")
+    emit("// table slot of a set of matching entries: h = sum over groups of x_g * magic  mod 2^32, slot = h >> (32 - bits),")
+    emit("// or, if swizzle != 0, slot = (h * swizzle) >> 32 with swizzle = 2^bits + spare: one multiply-high, injective by")
+    emit("// search, spreads the probable states over the shared-memory banks; the table then has `swizzle` slots")
     emit("struct Rs1Lane { const char *name; int lane_base; int n_entries; int n_table; int bits; int swizzle; int offset; "
          "int n_groups; Rs1Group groups[4]; Rs1Entry entries[16]; };")
     descs, code, offset, consts = [], [], 0, []
@@ -258,14 +266,14 @@ def main():
         assert all(e[0] < (tail[0][0] if tail else 99) for e in entries if e[3]), "forced entry after a tail entry"
         second = name[0] == "d"
         if table_free or any(e[3] for e in entries):
-            bits, groups, sets = find_hash(table_free, seed=100 + li, offset=offset)
+            bits, mul, groups, sets = find_hash(table_free, seed=100 + li, offset=offset)
         else:
-            bits, groups, sets = -1, [], []
+            bits, mul, groups, sets = -1, 0, [], []
         n_table = len(entries) - len(tail)          # forced + tabulated entries come first
         ents = ", ".join(f"{{{p}, {-1 if c1 is None else c1}, {hexf(v)}, {bit_of((p, c1))}, {int(f)}}}"
                          for p, c1, v, f, _ in entries)
         grps = ", ".join(f"{{{-1 if c1 is None else c1}, 0x{m:x}u, 0x{mg:x}u}}" for c1, m, mg in groups)
-        descs.append(f'    {{"{name}", {base}, {len(entries)}, {n_table}, {bits}, {int(bits >= SWIZZLE_MIN_BITS)}, {offset}, {len(groups)}, {{{grps}}}, {{{ents}}}}}')
+        descs.append(f'    {{"{name}", {base}, {len(entries)}, {n_table}, {bits}, {mul}, {offset}, {len(groups)}, {{{grps}}}, {{{ents}}}}}')
         # ---- device code of this lane
         if bits >= 0:
             terms = []
@@ -281,9 +289,9 @@ def main():
                     sel = f"RS1_SEL(0x{union:x}u, {sel}, {shift_name[c1n]})"
                     union |= mn
                 terms.append(f"({sel} & {mask_name[base]} & 0x{union:x}u) * 0x{mg:x}u")
-            top = "RS1_SWZ" if bits >= SWIZZLE_MIN_BITS else "RS1_TOP"
-            code.append(f"    double {name} = RS1_LD(T, {offset}u, {top}(" + " + ".join(terms) + f", {bits}));")
-            offset += (1 << bits) + (16 if bits >= SWIZZLE_MIN_BITS else 0)
+            top, arg = ("RS1_SWZ", f"{mul}u") if mul else ("RS1_TOP", f"{bits}")
+            code.append(f"    double {name} = RS1_LD(T, {offset}u, {top}(" + " + ".join(terms) + f", {arg}));")
+            offset += mul if mul else 1 << bits
         else:
             code.append(f"    double {name} = 0.0;")
         for p, c1, v, _, _ in tail:

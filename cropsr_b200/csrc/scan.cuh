@@ -34,6 +34,9 @@
 namespace cg = cooperative_groups;
 
 // ------------------------------------------------------------------ geometry
+#ifndef CRP_CTAS_PER_SM
+#define CRP_CTAS_PER_SM 4                                   // resident CTAs per SM the scan kernel is compiled for (64 registers)
+#endif
 static constexpr int kThreads = 256;
 static constexpr int kWarps = kThreads / 32;
 static constexpr int kTileWords = 2 * kThreads;            // every thread owns word tid and word tid + 256
@@ -42,6 +45,10 @@ static constexpr int kRecWords = kTileWords + 3;           // descriptor + halo 
 static constexpr uint32_t kRecBytes = kRecWords * 16;      // 8240, one bulk copy
 static constexpr int kStages = 2;                          // staged tiles per CTA
 static constexpr int kListCap = 1024;                      // hits per strand of a tile compacted in one go
+#ifndef CRP_PIPELINED_EMIT
+#define CRP_PIPELINED_EMIT 0                                // 1: hit lists double-buffered, the lists of tile n + 1 are built behind the candidates of tile n
+#endif
+static constexpr int kListBufs = CRP_PIPELINED_EMIT ? 2 : 1;
 static constexpr int kPrefWords = 10;                      // per tile: 8 warp prefixes, tile total, pad (80 B, one bulk copy)
 static constexpr uint32_t kNoTile = 0xFFFFFFFFu;
 static constexpr int kMaxRange = 32;                       // tiles of a CTA's count range whose (tile, chunk) counts are scanned in one go
@@ -445,11 +452,11 @@ struct Window {
 // relative to the first halo position (the hit lists hold this biased value).
 static constexpr uint32_t kWinBiasPlus = 7u, kWinBiasMinus = 30u;
 template <bool kMinus>
-__device__ __forceinline__ Window extract_window(const uint4 *__restrict__ rec, uint32_t ws, uint32_t t, uint32_t L) {
+CRP_HD Window extract_window(const uint4 *__restrict__ rec, uint32_t ws, uint32_t t, uint32_t L) {
     const uint32_t wi = 1u + (ws >> 5), sh = ws;            // shf.r.wrap uses the low 5 bits of the amount
     const uint4 lo = rec[wi], hi = rec[wi + 1];
-    const uint32_t p0 = __funnelshift_r(lo.x, hi.x, sh), p1 = __funnelshift_r(lo.y, hi.y, sh);
-    const uint32_t lw = __funnelshift_r(lo.z, hi.z, sh), ot = __funnelshift_r(lo.w, hi.w, sh);
+    const uint32_t p0 = crp_funnel_r(lo.x, hi.x, sh), p1 = crp_funnel_r(lo.y, hi.y, sh);
+    const uint32_t lw = crp_funnel_r(lo.z, hi.z, sh), ot = crp_funnel_r(lo.w, hi.w, sh);
     const uint32_t special = ot & p0;       // 'U' / 'Z': "other" bytes that still score
     const uint32_t valid = ~ot | special;
     Window w;
@@ -458,9 +465,9 @@ __device__ __forceinline__ Window extract_window(const uint4 *__restrict__ rec, 
         w.s1 = p1 & 0x3FFFFFFFu;
         w.valid = valid & 0x3FFFFFFFu;
     } else {
-        w.s0 = __brev(p0 ^ ~(lw | ot)) >> 2;                 // A<->T, C<->G of upper-case bases flips the low code bit
-        w.s1 = __brev(p1) >> 2;
-        w.valid = __brev(valid) >> 2;
+        w.s0 = crp_brev(p0 ^ ~(lw | ot)) >> 2;               // A<->T, C<->G of upper-case bases flips the low code bit
+        w.s1 = crp_brev(p1) >> 2;
+        w.valid = crp_brev(valid) >> 2;
     }
     // flags without predicates: valid <= 0x3FFFFFFF, so bit 30 of valid + 1 is set iff all 30 bases
     // score; x <= 0x3FFFFFFF, so bit 30 of x + 0x3FFFFFFF is set iff x != 0
@@ -474,6 +481,69 @@ __device__ __forceinline__ Window extract_window(const uint4 *__restrict__ rec, 
 
 __device__ __forceinline__ unsigned long long unpack_counts(uint32_t c) {   // (plus | minus << 16) -> plus << 32 | minus
     return ((unsigned long long)(c & 0xFFFFu) << 32) | (c >> 16);
+}
+
+// The emit phase's twin of extract_window + rs1_canonical: the same packed word and the same x from the same
+// staged record, arranged for the instruction mix of the candidate loop, whose bound is the integer-ALU pipe
+// (LOP3 / SHF / IADD3 issue every other cycle; multiplies run beside them on the FMA pipe):
+//   * the class masks come straight from the shifted planes (one LOP3 each) and may carry junk in bits 30 / 31;
+//   * '+' windows are shifted by ws - 2 (the hit list holds that: kWinBiasPlusHot), so that BREV alone aligns them;
+//   * the word index, the truncation flag and the flag merges are multiplies / multiply-highs;
+//   * flags are selected into the words (bit 31 of either flag source is provably clear).
+// xt = L - (28 | 5) - (token position of list value 0): list value ws is truncated iff xt - ws < 0 (all < 2^31).
+static constexpr uint32_t kWinBiasPlusHot = kWinBiasPlus - 2u;
+template <bool kMinus>
+CRP_HD double score_hit(const double *__restrict__ tab, const uint4 *__restrict__ rec, uint32_t ws, uint32_t xt,
+                        unsigned long long &packed) {
+    const uint32_t wbyte = crp_umulhi(ws, 1u << 27) * 16u;  // 16 * (ws >> 5)
+    const uint4 lo = *reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(rec) + 16 + wbyte);
+    const uint4 hi = *reinterpret_cast<const uint4 *>(reinterpret_cast<const char *>(rec) + 32 + wbyte);
+    const uint32_t p0 = crp_funnel_r(lo.x, hi.x, ws), p1 = crp_funnel_r(lo.y, hi.y, ws);
+    const uint32_t lw = crp_funnel_r(lo.z, hi.z, ws), ot = crp_funnel_r(lo.w, hi.w, ws);
+    uint32_t xs;                                            // xt - ws, on the FMA pipe
+#ifdef __CUDA_ARCH__
+    asm("mad.lo.u32 %0, %1, 0xFFFFFFFF, %2;" : "=r"(xs) : "r"(ws), "r"(xt));
+#else
+    xs = xt - ws;
+#endif
+    const uint32_t trunc = crp_umulhi(xs, 2u);              // its sign bit
+    constexpr uint32_t kWin = kMinus ? 0x3FFFFFFFu : 0xFFFFFFFCu;    // the window's 30 bits in the shifted planes
+    uint32_t mA, mT, mC, mG, w0, w1;
+    if (kMinus) {
+        const uint32_t s0 = p0 & ~ot;                       // U scores as A, Z as C: "other" bytes lose the low code bit
+        const uint32_t e = ~(p0 ^ ot);                      // low code bit clear AND the base scores (valid = ~ot | p0)
+        mA = e & ~p1, mC = e & p1, mT = s0 & ~p1, mG = s0 & p1;
+        w0 = s0, w1 = p1;
+    } else {
+        uint32_t q0;                                        // p0 ^ ~(lw | ot): A<->T, C<->G of upper-case bases flips the low code bit
+#ifdef __CUDA_ARCH__
+        asm("lop3.b32 %0, %1, %2, %3, 0xE1;" : "=r"(q0) : "r"(p0), "r"(lw), "r"(ot));   // one LOP3, not one shared with irr + one
+#else
+        q0 = p0 ^ ~(lw | ot);
+#endif
+        const uint32_t s0 = crp_brev(q0), s1 = crp_brev(p1), valid = crp_brev(~ot | p0);
+        mA = ~s1 & ~s0 & valid, mT = ~s1 & s0 & valid, mC = s1 & ~s0 & valid, mG = s1 & s0 & valid;
+        w0 = s0, w1 = s1;
+    }
+    // flag sources: a value <= 0x3FFFFFFF plus 0x3FFFFFFF has bit 30 set iff it is not zero, and bit 31 clear
+    const uint32_t irr = (lw | ot) & kWin, uns = ot & ~p0 & kWin;
+    const uint32_t y0 = (kMinus ? irr : crp_umulhi(irr, 1u << 30)) + 0x3FFFFFFFu;
+    const uint32_t f1 = (kMinus ? uns : crp_umulhi(uns, 1u << 30)) + 0x3FFFFFFFu;
+    static_assert(CRP_PACKED_IRREGULAR == (1ull << 30) && CRP_PACKED_TRUNCATED == (1ull << 31) && CRP_PACKED_UNSCORED == (1ull << 62),
+                  "flag bits of the packed word");
+    uint32_t f0, lo32, hi32;
+#ifdef __CUDA_ARCH__
+    asm("mad.lo.u32 %0, %1, 0x80000000, %2;" : "=r"(f0) : "r"(trunc), "r"(y0));         // bit 31 of y0 is clear: the add is an OR
+    // (w & 0x3FFFFFFF) | (f & 0xC0000000) as ONE bit select each
+    asm("lop3.b32 %0, %1, 0x3FFFFFFF, %2, 0xE2;" : "=r"(lo32) : "r"(w0), "r"(f0));
+    asm("lop3.b32 %0, %1, 0x3FFFFFFF, %2, 0xE2;" : "=r"(hi32) : "r"(w1), "r"(f1));
+#else
+    f0 = trunc * 0x80000000u + y0;
+    lo32 = (w0 & 0x3FFFFFFFu) | (f0 & 0xC0000000u);
+    hi32 = (w1 & 0x3FFFFFFFu) | (f1 & 0xC0000000u);
+#endif
+    packed = ((unsigned long long)hi32 << 32) | lo32;
+    return rs1_canonical_masks(tab, mA, mT, mC, mG);
 }
 
 // store v at p iff cond != 0, as a predicated store (no branch, no divergence)
@@ -519,34 +589,52 @@ __device__ __forceinline__ void list_hits_window(uint16_t *__restrict__ list, ui
     }
 }
 
-// one thread per listed hit of one strand of a tile: window, score, coalesced stores
+// listed hit i of one strand of a tile: window, score, stores (coalesced across the lanes of a warp)
+template <bool kScore, bool kMinus>
+__device__ __forceinline__ void emit_one(const ScanArgs &a, const double *__restrict__ tab, const uint4 *__restrict__ rec,
+                                         const uint16_t *__restrict__ list, uint32_t i, uint32_t row0, uint32_t t_start,
+                                         uint32_t L) {
+    uint32_t *const pos = kMinus ? a.pos_minus : a.pos_plus;
+    unsigned long long *const packed = kMinus ? a.packed_minus : a.packed_plus;
+    double *const xs = kMinus ? a.x_minus : a.x_plus;
+    constexpr uint32_t kBias = kMinus ? kWinBiasMinus : kWinBiasPlusHot;
+    const uint32_t xt = L - (kMinus ? 28u : 5u) - (t_start - kBias);
+    const uint32_t ws = list[i], t = t_start - kBias + ws;
+    const uint32_t row = row0 + i;
+    CRP_CHECK(a, i < (uint32_t)kListCap, 1);                                 // inside the hit list
+    CRP_CHECK(a, ws >= kBias && 2u + (ws >> 5) < (uint32_t)kRecWords, 2);   // window inside the record
+    CRP_CHECK(a, row < (uint32_t)a.capacity && t < L, 3);                    // inside the stream, inside the token
+    CRP_CHECK(a, i == 0 || list[i - 1] < ws, 4);                             // positions ascend
+    __stcs(pos + row, t);
+    if (kScore) {
+        unsigned long long word;
+        const double x = score_hit<kMinus>(tab, rec, ws, xt, word);
+#ifdef CRP_CHECKED
+        {   // the generic path (extras, rescore) must agree bit for bit
+            const Window w = extract_window<kMinus>(rec, ws + (kMinus ? 0u : 2u), t, L);
+            CRP_CHECK(a, w.packed == word, 14);
+            CRP_CHECK(a, __double_as_longlong(rs1_canonical(tab, w.s0, w.s1, w.valid)) == __double_as_longlong(x), 15);
+        }
+#endif
+        __stcs(packed + row, word);
+        __stcs(xs + row, x);
+    }
+}
+
+// rows of a strand stream fit 32 bits: the scan state packs the two strand counts of a shard into one
+// 64-bit word (plus << 32 | minus), and launch_scan clamps the capacity.  -> hits of the list that have a row
+__device__ __forceinline__ uint32_t rows_left(const ScanArgs &a, uint32_t count, uint32_t row0) {
+    const uint32_t cap = (uint32_t)a.capacity;
+    return row0 >= cap ? 0u : min(count, cap - row0);
+}
+
+// one thread per listed hit of one strand (dense tiles: a window of kListCap ranks at a time)
 template <bool kScore, bool kMinus>
 __device__ __forceinline__ void emit_strand(const ScanArgs &a, const double *__restrict__ tab,
                                             const uint4 *__restrict__ rec, const uint16_t *__restrict__ list,
                                             uint32_t count, uint32_t row0, uint32_t t_start, uint32_t L, uint32_t slot) {
-    // rows of a strand stream fit 32 bits: the scan state packs the two strand counts of a
-    // shard into one 64-bit word (plus << 32 | minus), and launch_scan clamps the capacity
-    const uint32_t cap = (uint32_t)a.capacity;
-    if (row0 >= cap) return;
-    if (count > cap - row0) count = cap - row0;
-    uint32_t *const pos = kMinus ? a.pos_minus : a.pos_plus;
-    unsigned long long *const packed = kMinus ? a.packed_minus : a.packed_plus;
-    double *const xs = kMinus ? a.x_minus : a.x_plus;
-    for (uint32_t i = slot; i < count; i += kThreads) {
-        const uint32_t ws = list[i], t = t_start - (kMinus ? kWinBiasMinus : kWinBiasPlus) + ws;
-        const uint32_t row = row0 + i;
-        CRP_CHECK(a, i < (uint32_t)kListCap, 1);                                 // inside the hit list
-        CRP_CHECK(a, ws >= (kMinus ? kWinBiasMinus : kWinBiasPlus) && 2u + (ws >> 5) < (uint32_t)kRecWords, 2);   // window inside the record
-        CRP_CHECK(a, row < cap && t < L, 3);                                     // inside the stream, inside the token
-        CRP_CHECK(a, i == 0 || list[i - 1] < ws, 4);                             // positions ascend
-        __stcs(pos + row, t);
-        if (kScore) {
-            const Window w = extract_window<kMinus>(rec, ws, t, L);
-            const double x = rs1_canonical(tab, w.s0, w.s1, w.valid);
-            __stcs(packed + row, w.packed);
-            __stcs(xs + row, x);
-        }
-    }
+    count = rows_left(a, count, row0);
+    for (uint32_t i = slot; i < count; i += kThreads) emit_one<kScore, kMinus>(a, tab, rec, list, i, row0, t_start, L);
 }
 
 // Ring of staged tiles of a CTA.  full[s] completes when the bulk copies of slot s (the tile
@@ -605,7 +693,7 @@ k_scan_score(const ScanArgs a) {
     auto stage = [&](int s) { return reinterpret_cast<uint4 *>(s_dyn + (size_t)s * kRecBytes); };
     uint16_t *const s_list = reinterpret_cast<uint16_t *>(s_dyn + kStages * kRecBytes);
     unsigned long long *const s_rangepref =
-        reinterpret_cast<unsigned long long *>(s_dyn + kStages * kRecBytes + 2 * (size_t)kListCap * sizeof(uint16_t));
+        reinterpret_cast<unsigned long long *>(s_dyn + kStages * kRecBytes + kListBufs * 2 * (size_t)kListCap * sizeof(uint16_t));
     __shared__ __align__(16) double s_tab[kScore ? RS1_TABLE_DOUBLES : 1];   // static: LDS takes the table offset as an immediate
     __shared__ Ring ring;
     __shared__ uint32_t s_cnt[kMaxRange][kWarps];
@@ -819,6 +907,129 @@ k_scan_score(const ScanArgs a) {
         if (pre) mbar_arrive(&ring.full[0]);                   // tile 0 came through ring.pre: skip that phase of slot 0
         else produce_emit(0, 0);
     }
+#if CRP_PIPELINED_EMIT
+    // One barrier per tile: between two barriers every warp first emits its share of the candidates of tile n
+    // (lists of buffer n & 1, record in slot n % 2) and then builds the lists of tile n + 1 (buffer (n + 1) & 1,
+    // record in the other slot, whose copy was issued at the barrier and landed behind the candidates).  A warp
+    // with few candidates goes straight on to its front end and the other way round, so the two kinds of
+    // imbalance meet in one barrier instead of two, and bodies (integer ALU) overlap front ends (LSU, XU).
+    struct TileCtx {
+        uint32_t np, nm, base_p, base_m, t_start, L;
+        bool live, dense;
+    };
+    auto lists = [&](uint32_t n, bool minus) { return s_list + ((n & 1u) * 2u + (minus ? 1u : 0u)) * kListCap; };
+    // ranks of the first hits of this lane's two words inside the tile (per strand); false: the chunk has no hit
+    auto chunk_ranks = [&](int s, const uint4 *rec, const TileDesc td, Hits &h, uint32_t &epA, uint32_t &emA, uint32_t &epB,
+                           uint32_t &emB, uint32_t np, uint32_t nm) -> bool {
+        const uint32_t wordA = 64 * warp + lane;
+        const bool busy = ring.pref[s][warp + 1] != ring.pref[s][warp];          // warp-uniform (see below)
+        if (!busy) {
+#ifdef CRP_CHECKED
+            const Hits hh = tile_hits(rec, td, l, wordA);
+            CRP_CHECK(a, (hh.pA | hh.pB | hh.mA | hh.mB) == 0u, 13);
+#endif
+            return false;
+        }
+        const unsigned long long off = ring.pref[s][warp] - ring.pref[s][0];
+        h = tile_hits(rec, td, l, wordA);
+        const uint32_t cA = __popc(h.pA) | (__popc(h.mA) << 16), cB = __popc(h.pB) | (__popc(h.mB) << 16);
+        uint32_t iA = cA, iB = cB;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t vA = __shfl_up_sync(0xFFFFFFFFu, iA, o), vB = __shfl_up_sync(0xFFFFFFFFu, iB, o);
+            if (lane >= o) {
+                iA += vA;
+                iB += vB;
+            }
+        }
+        const uint32_t totA = __shfl_sync(0xFFFFFFFFu, iA, 31);
+        const uint32_t xA = iA - cA, xB = totA + iB - cB;
+        const uint32_t op = (uint32_t)(off >> 32), om = (uint32_t)off;
+        epA = op + (xA & 0xFFFFu), emA = om + (xA >> 16), epB = op + (xB & 0xFFFFu), emB = om + (xB >> 16);
+#ifdef CRP_CHECKED
+        {
+            const uint32_t mine = totA + __shfl_sync(0xFFFFFFFFu, iB, 31);
+            const unsigned long long nxt = ring.pref[s][warp + 1] - ring.pref[s][warp];
+            CRP_CHECK(a, (uint32_t)(nxt >> 32) == (mine & 0xFFFFu) && (uint32_t)nxt == (mine >> 16), 7);
+            if (np <= (uint32_t)kListCap && nm <= (uint32_t)kListCap)
+                CRP_CHECK(a, epA + __popc(h.pA) <= np && epB + __popc(h.pB) <= np && emA + __popc(h.mA) <= nm && emB + __popc(h.mB) <= nm, 10);
+        }
+#endif
+        (void)np, (void)nm;
+        return true;
+    };
+    // front end of tile number n of this CTA: wait for its record, take its place in the streams from the
+    // prefix block, compact its hits into list buffer n & 1 (dense tiles are listed window by window in `bodies`)
+    auto front = [&](uint32_t n, bool first_pre) -> TileCtx {
+        const int s = n % kStages;
+        TileCtx c = {0u, 0u, 0u, 0u, 0u, 0u, false, false};
+        if (first_pre) mbar_wait(&ring.pre, 0u);
+        else mbar_wait(&ring.full[s], (n / kStages) & 1u);
+        if (!first_pre && ring.tile[s] == kNoTile) return c;
+        c.live = true;
+        const uint4 *rec = stage(s);
+        const uint4 d = rec[0];
+        const TileDesc td = {d.x, d.y, d.z, d.w};
+        const unsigned long long tile_pref = ring.pref[s][0];
+        const unsigned long long base = (first_pre ? s_rangepref[t_pre / k] : ring.rbase[s]) + tile_pref;
+        const unsigned long long tot = ring.pref[s][kWarps] - tile_pref;
+        c.np = (uint32_t)(tot >> 32), c.nm = (uint32_t)tot;
+        c.base_p = (uint32_t)(base >> 32), c.base_m = (uint32_t)base;
+        c.t_start = td.t_start, c.L = td.L;
+        c.dense = c.np > (uint32_t)kListCap || c.nm > (uint32_t)kListCap;
+        CRP_CHECK(a, first_pre || ring.tile[s] < nt, 8);
+        CRP_CHECK(a, (unsigned long long)c.base_p + c.np <= 0xFFFFFFFFull && (unsigned long long)c.base_m + c.nm <= 0xFFFFFFFFull, 9);
+        if (!c.dense) {
+            Hits h = {0u, 0u, 0u, 0u};
+            uint32_t epA = 0, emA = 0, epB = 0, emB = 0;
+            if (chunk_ranks(s, rec, td, h, epA, emA, epB, emB, c.np, c.nm)) {
+                const uint32_t wordA = 64 * warp + lane;
+                list_hits(lists(n, false) + epA, h.pA, 32u * wordA + kWinBiasPlusHot);
+                list_hits(lists(n, false) + epB, h.pB, 32u * (wordA + 32) + kWinBiasPlusHot);
+                list_hits(lists(n, true) + emA, h.mA, 32u * wordA + kWinBiasMinus);
+                list_hits(lists(n, true) + emB, h.mB, 32u * (wordA + 32) + kWinBiasMinus);
+            }
+        }
+        return c;
+    };
+    TileCtx cur = front(0u, pre);
+    __syncthreads();
+    for (uint32_t n = 0; cur.live; ++n) {
+        const int s = n % kStages;
+        // next tile of this CTA: its copies land while this tile's candidates are emitted (slot s^1 was
+        // released by the barrier that ended tile n - 1)
+        if (tid == 0) produce_emit(n + 1, s ^ 1);
+        const uint4 *rec = stage(s);
+        if (!cur.dense) {
+            emit_strand<kScore, false>(a, s_tab, rec, lists(n, false), cur.np, cur.base_p, cur.t_start, cur.L, tid);
+            emit_strand<kScore, true>(a, s_tab, rec, lists(n, true), cur.nm, cur.base_m, cur.t_start, cur.L, tid ^ (kThreads / 2));
+        } else {                                               // dense tile: windows of kListCap ranks, in step
+            const uint4 d = rec[0];
+            const TileDesc td = {d.x, d.y, d.z, d.w};
+            Hits h = {0u, 0u, 0u, 0u};
+            uint32_t epA = 0, emA = 0, epB = 0, emB = 0;
+            const bool busy = chunk_ranks(s, rec, td, h, epA, emA, epB, emB, cur.np, cur.nm);
+            const uint32_t wordA = 64 * warp + lane;
+            for (uint32_t lo = 0; lo < cur.np || lo < cur.nm; lo += kListCap) {
+                const uint32_t cp = cur.np > lo ? min(cur.np - lo, (uint32_t)kListCap) : 0u;
+                const uint32_t cm = cur.nm > lo ? min(cur.nm - lo, (uint32_t)kListCap) : 0u;
+                if (lo) __syncthreads();
+                if (busy) {
+                    list_hits_window(lists(n, false), h.pA, epA, 32u * wordA + kWinBiasPlusHot, lo);
+                    list_hits_window(lists(n, false), h.pB, epB, 32u * (wordA + 32) + kWinBiasPlusHot, lo);
+                    list_hits_window(lists(n, true), h.mA, emA, 32u * wordA + kWinBiasMinus, lo);
+                    list_hits_window(lists(n, true), h.mB, emB, 32u * (wordA + 32) + kWinBiasMinus, lo);
+                }
+                __syncthreads();
+                emit_strand<kScore, false>(a, s_tab, rec, lists(n, false), cp, cur.base_p + lo, cur.t_start, cur.L, tid);
+                emit_strand<kScore, true>(a, s_tab, rec, lists(n, true), cm, cur.base_m + lo, cur.t_start, cur.L, tid);
+            }
+        }
+        const TileCtx nxt = front(n + 1, false);
+        __syncthreads();                                       // lists of tile n + 1 complete; slot s and list buffer n & 1 free
+        cur = nxt;
+    }
+#else
     uint16_t *const list_p = s_list, *const list_m = s_list + kListCap;
     for (uint32_t n = 0;; ++n) {
         const int s = n % kStages;
@@ -883,8 +1094,8 @@ k_scan_score(const ScanArgs a) {
 #endif
         if (np <= (uint32_t)kListCap && nm <= (uint32_t)kListCap) {
             if (busy) {
-                list_hits(list_p + epA, h.pA, 32u * wordA + kWinBiasPlus);
-                list_hits(list_p + epB, h.pB, 32u * (wordA + 32) + kWinBiasPlus);
+                list_hits(list_p + epA, h.pA, 32u * wordA + kWinBiasPlusHot);
+                list_hits(list_p + epB, h.pB, 32u * (wordA + 32) + kWinBiasPlusHot);
                 list_hits(list_m + emA, h.mA, 32u * wordA + kWinBiasMinus);
                 list_hits(list_m + emB, h.mB, 32u * (wordA + 32) + kWinBiasMinus);
             }
@@ -897,8 +1108,8 @@ k_scan_score(const ScanArgs a) {
                 const uint32_t cm = nm > lo ? min(nm - lo, (uint32_t)kListCap) : 0u;
                 if (lo) __syncthreads();
                 if (busy) {
-                    list_hits_window(list_p, h.pA, epA, 32u * wordA + kWinBiasPlus, lo);
-                    list_hits_window(list_p, h.pB, epB, 32u * (wordA + 32) + kWinBiasPlus, lo);
+                    list_hits_window(list_p, h.pA, epA, 32u * wordA + kWinBiasPlusHot, lo);
+                    list_hits_window(list_p, h.pB, epB, 32u * (wordA + 32) + kWinBiasPlusHot, lo);
                     list_hits_window(list_m, h.mA, emA, 32u * wordA + kWinBiasMinus, lo);
                     list_hits_window(list_m, h.mB, emB, 32u * (wordA + 32) + kWinBiasMinus, lo);
                 }
@@ -909,6 +1120,7 @@ k_scan_score(const ScanArgs a) {
         }
         __syncthreads();                                       // slot s and the lists are free again
     }
+#endif
     dbg_stamp(5);
     // sharded scan: the counts of every rank are in this rank's buffer before the kernel -- and the
     // copy to the host behind it -- ends (they were sent a whole emit phase ago)

@@ -361,3 +361,20 @@ def test_cli_help_and_missing_system(built_lib, capsys):
         cli.main(["-f", "x.fa"])
     assert e.value.code == "Please select at least one CRISPR system: Cas9"
     assert cli.parse_devices("0-3") == [0, 1, 2, 3] and cli.parse_devices("0,2,5") == [0, 2, 5]
+
+
+def test_candidate_scoring_source_on_the_cpu(tmp_path):
+    """tests/host_emu.cu compiles the per-candidate functions of the scan kernel -- the SAME source,
+    __host__ __device__ -- for the host and checks the table-driven Rule-Set-1 lanes against the dense
+    replay of OpenBLAS' canonical lane order, and the emit loop's score_hit against the generic
+    extract_window + rs1_canonical pair, bit for bit (reference: CROPSR.py:285-313 through SURVEY 8c)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not found")
+    exe = str(tmp_path / "host_emu")
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-std=c++17", "-o", exe,
+                    os.path.join(ROOT, "tests", "host_emu.cu")], check=True, capture_output=True, timeout=600)
+    r = subprocess.run([exe, "300000", "300000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr

@@ -36,4 +36,9 @@ for i, (a, s) in enumerate(ins):
         body = [x[1] for x in ins[j:i + 1]]
         ops = collections.Counter(re.sub(r"^@!?U?P\d\s+", "", b).split()[0].split(".")[0] for b in body)
         if len(body) > 40:
+            if ops.get("DADD") and len(body) < 250:      # a candidate body: instructions per issue pipe
+                alu = sum(ops.get(k, 0) for k in ("LOP3", "SHF", "IADD3", "LEA", "ISETP", "VIADD", "VIADDMNMX", "SEL", "PRMT", "PLOP3", "IABS", "BREV"))
+                fma = sum(v for k, v in ops.items() if k.startswith("IMAD") or k in ("FFMA", "FMUL", "FADD"))
+                print(f"  body: ALU pipe {alu}  FMA pipe {fma}  FP64 {ops.get('DADD', 0) + ops.get('DFMA', 0) + ops.get('DMUL', 0)}  "
+                      f"LDS {ops.get('LDS', 0)}  STG {ops.get('STG', 0)}  total {len(body)}")
             print(f"loop {tgt:#x}..{a:#x}: {len(body)} instr  " + " ".join(f"{k}={v}" for k, v in ops.most_common(14)))
