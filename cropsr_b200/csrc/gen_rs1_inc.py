@@ -47,6 +47,8 @@ BASES = rs1.BASES
 A, T, C, G = 0, 1, 2, 3
 MAX_TABLE_ENTRIES = 10          # leading free entries of a lane covered by its table
 TABLE_ENTRIES = {"fG": 9}       # per-lane override (keeps the tables of one CTA at ~25 KB)
+for _kv in filter(None, os.environ.get("RS1_TABLE_ENTRIES", "").split(",")):      # e.g. RS1_TABLE_ENTRIES=fC=9
+    TABLE_ENTRIES[_kv.split("=")[0]] = int(_kv.split("=")[1])
 # Every 30-mer the scan scores carries the PAM the way the reference orients it: '+' windows
 # are reverse-complemented (.GG -> CC.), '-' windows are read forwards (CC.), so bases 2 and 3
 # are upper-case C on both strands (CROPSR.py:415-433; tests/test_oracle_golden.py pins it).

@@ -9,4 +9,4 @@ for w in arabidopsis; do
 done
 for v in ${BIG_VARIANTS:-tools/variants/*.so}; do CROPSR_B200_LIB=$v timeout 400 python tools/variant_scan.py maize 8; done
 } 2>&1 | grep -v "^$" | tee gpurun_out/variants.txt
-timeout 600 python -m pytest tests -x -q -m gpu -k "checked_build or whole_candidate_table_of_configs1 or random_fastas or tile_boundaries or extras_and_annotation" 2>&1 | tail -5 | tee gpurun_out/variants_pytest.txt
+CROPSR_B200_LIB=${PYTEST_LIB:-} timeout 600 python -m pytest tests -x -q -m gpu -k "${PYTEST_K:-checked_build or whole_candidate_table_of_configs1 or random_fastas or tile_boundaries or extras_and_annotation}" 2>&1 | tail -5 | tee gpurun_out/variants_pytest.txt
