@@ -32,7 +32,7 @@
 
 #define CRP_ABI_VERSION 7
 
-static constexpr size_t kScanSmemFixed = (size_t)kStages * kRecBytes + kListBufs * 2 * (size_t)kListCap * sizeof(uint16_t);
+static constexpr size_t kScanSmemFixed = (size_t)kStages * kRecBytes + 2 * (size_t)kListCap * sizeof(uint16_t);
 
 // ------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
@@ -94,7 +94,8 @@ struct crp_genome {
     bool committed = false;
     uint64_t n_positions = 0;          // owned positions
     uint4 *records = nullptr;          // n_tiles tile records (scan.cuh)
-    unsigned char *pam = nullptr;      // n_tiles PAM records (count phase of the scan)
+    unsigned char *pam = nullptr;      // n_tiles PAM records (count phase of the scan: tiles at the ends of a token)
+    TileHdr *hdr = nullptr;            // n_tiles tile headers (count phase of the scan: descriptor + chunk counts)
     uint32_t n_tiles = 0;
     uint32_t *d_seg_first = nullptr, *d_seg_count = nullptr;
     float ms_h2d = 0.f, ms_pack = 0.f;
@@ -895,7 +896,8 @@ static int commit_enqueue(crp_genome *g) {
     if (dev_alloc(&d_ascii, ascii_bytes + 64, st) != cudaSuccess ||
         (!one && dev_alloc(&d_descs, (descs.size() + 1) * sizeof(PackDesc), st) != cudaSuccess) ||
         dev_alloc(&g->records, rec_bytes + 16, st) != cudaSuccess ||
-        dev_alloc(&g->pam, (size_t)g->n_tiles * kPamBytes + 16, st) != cudaSuccess) {
+        dev_alloc(&g->pam, (size_t)g->n_tiles * kPamBytes + 16, st) != cudaSuccess ||
+        dev_alloc(&g->hdr, ((size_t)g->n_tiles + 1) * sizeof(TileHdr), st) != cudaSuccess) {
         cudaGetLastError();
         dev_free(d_ascii, st);
         dev_free(d_descs, st);
@@ -966,7 +968,8 @@ static int commit_enqueue(crp_genome *g) {
         PackDesc first = descs[0];
         if (one) first.td.n = (uint32_t)(g->segs[0].end - g->segs[0].begin);     // positions of the whole segment
         const uint64_t want = (n_items + 255) / 256, cap = (uint64_t)g_ctx.sm_count * 16;
-        k_pack<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(d_ascii, d_descs, first, n_items, g->records, g->pam);
+        CUDA_TRY(cudaMemsetAsync(g->hdr, 0, (size_t)g->n_tiles * sizeof(TileHdr), st));      // chunk counts are accumulated
+        k_pack<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(d_ascii, d_descs, first, n_items, g->records, g->pam, g->hdr);
         g_ctx.launches++;
         CUDA_TRY(cudaGetLastError());
     }
@@ -1016,6 +1019,7 @@ int crp_genome_free(crp_genome *g) {
     cudaStream_t st = stream_of(g);
     dev_free(g->records, st);
     dev_free(g->pam, st);
+    dev_free(g->hdr, st);
     dev_free(g->d_ascii, st);
     pinned_put(g->h_bad);
     dev_free(g->d_seg_first, st);
@@ -1067,7 +1071,7 @@ static int plan_scan(const crp_genome *g, bool scored, ScanPlan *p) {
     p->fn = scored ? (const void *)k_scan_score<true> : (const void *)k_scan_score<false>;
     const unsigned grid_max = (unsigned)g_ctx.sm_count * CRP_CTAS_PER_SM;
     p->smem = kScanSmemFixed + (size_t)grid_max * sizeof(unsigned long long);
-    if (p->smem < (size_t)kCountStages * kPamBytes) p->smem = (size_t)kCountStages * kPamBytes;   // the count ring reuses all of it
+    static_assert(kScanSmemFixed >= (size_t)kHdrBatch * sizeof(TileHdr), "the count phase stages its tile headers in the emit phase's tile slots");
     static int per_sm_cache[2] = {0, 0};       // occupancy of the two instantiations, queried once
     int &per_sm = per_sm_cache[scored ? 1 : 0];
     if (per_sm == 0) {
@@ -1093,6 +1097,7 @@ static int launch_scan(const crp_genome *g, crp_result *r, const ScanPlan &p) {
     ScanArgs a;
     a.records = g->records;
     a.pam = g->pam;
+    a.hdr = g->hdr;
     a.n_tiles = g->n_tiles;
     a.static_eighths = 4;
     if (const char *e = getenv("CRP_STATIC_EIGHTHS")) a.static_eighths = (uint32_t)atoi(e) > 8 ? 8 : (uint32_t)atoi(e);

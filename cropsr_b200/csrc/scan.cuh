@@ -45,10 +45,6 @@ static constexpr int kRecWords = kTileWords + 3;           // descriptor + halo 
 static constexpr uint32_t kRecBytes = kRecWords * 16;      // 8240, one bulk copy
 static constexpr int kStages = 2;                          // staged tiles per CTA
 static constexpr int kListCap = 1024;                      // hits per strand of a tile compacted in one go
-#ifndef CRP_PIPELINED_EMIT
-#define CRP_PIPELINED_EMIT 0                                // 1: hit lists double-buffered, the lists of tile n + 1 are built behind the candidates of tile n
-#endif
-static constexpr int kListBufs = CRP_PIPELINED_EMIT ? 2 : 1;
 static constexpr int kPrefWords = 10;                      // per tile: 8 warp prefixes, tile total, pad (80 B, one bulk copy)
 static constexpr uint32_t kNoTile = 0xFFFFFFFFu;
 static constexpr int kMaxRange = 32;                       // tiles of a CTA's count range whose (tile, chunk) counts are scanned in one go
@@ -60,8 +56,17 @@ static constexpr uint32_t kAlign = 128;                    // positions; segment
 // upper-case C) -- 0.25 byte per base
 static constexpr int kPamWords = kTileWords + 1;           // uint2 {upper G, upper C} each
 static constexpr uint32_t kPamBytes = (16 + kPamWords * 8 + 15) / 16 * 16;   // 4128, one bulk copy
-static constexpr int kCountStages = 6;                     // staged PAM records per CTA in the count phase: the tile
-                                                           // slots, the hit lists and the range prefixes are all idle then
+static constexpr int kCountStages = 6;                     // mbarriers of the ring control block (the emit phase uses kStages of them)
+// Tile header, read by the count phase: the descriptor and the PAM hits of the tile's eight 2,048-position
+// chunks (plus | minus << 16) counted by k_pack under every bound that does not depend on the guide
+// length -- ownership, t <= L - 3, '-' t >= 2.  Only a tile that reaches into the first l + 5 or the last
+// l - 7 positions of its token (CROPSR.py:419 / :430) is counted again at scan time, from its PAM record.
+struct __align__(16) TileHdr {
+    uint4 desc;
+    uint32_t cnt[8];
+};
+static_assert(sizeof(TileHdr) == 48, "bulk copies move multiples of 16 bytes");
+static constexpr int kHdrBatch = 256;                      // tile headers of a CTA's count range staged at once (12 KB)
 static_assert(kRecBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
 
 // record word 0
@@ -80,6 +85,15 @@ struct PackDesc {
 };
 
 // ------------------------------------------------------------------ k_pack
+// bits b of a 32-position word starting at token position t0 with lo <= t0+b <= hi
+__device__ __forceinline__ uint32_t range_mask(int32_t t0, int32_t lo, int32_t hi) {
+    int32_t a = lo - t0, b = hi - t0;
+    if (a < 0) a = 0;
+    if (b > 31) b = 31;
+    if (a > b) return 0u;
+    return (0xFFFFFFFFu >> (31 - b)) & (0xFFFFFFFFu << a);
+}
+
 // byte -> nibble: bit0 code low, bit1 code high (A0 T1 C2 G3), bit2 lower-case, bit3 other.
 // 'U' and 'Z' are "other" bytes that still score (reference replace chains,
 // CROPSR.py:120,128,458): they carry the code of T resp. G.
@@ -105,9 +119,11 @@ __host__ __device__ inline uint32_t classify(uint32_t c) {
 // BYTE lane (code low | code high << 8 | lower << 16 | other << 24): eight consecutive bases
 // accumulate as  acc += entry << k  (one IMAD each, no bit twiddling), which leaves 8 positions
 // of every plane in one byte of acc, and byte permutes assemble the 32-position planes.
+// hdr (zeroed before the launch): the descriptor again and the chunk counts of TileHdr -- every thread adds the
+// hits of its word, one atomic per (warp, chunk).
 __global__ void __launch_bounds__(256)
 k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, const PackDesc one, uint64_t n_items,
-       uint4 *__restrict__ records, unsigned char *__restrict__ pam) {
+       uint4 *__restrict__ records, unsigned char *__restrict__ pam, TileHdr *__restrict__ hdr) {
     __shared__ uint32_t lut[256];
     {
         const uint32_t nib = classify(threadIdx.x);
@@ -131,6 +147,7 @@ k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, co
             const uint4 d = make_uint4(pd.td.t_start, pd.td.L, pd.td.n, pd.td.segment);
             records[it] = d;
             *reinterpret_cast<uint4 *>(pam + tile * kPamBytes) = d;
+            hdr[tile].desc = d;
             continue;
         }
         const int64_t p0 = (int64_t)pd.td.t_start + ((int64_t)k - 2) * 32;   // token position of bit 0
@@ -168,7 +185,29 @@ k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, co
         records[it] = make_uint4(o0, o1, ol, oo);
         if (k >= 2) {                       // tile words and the right halo: the planes of the PAM tests
             const uint32_t up = ~(ol | oo);
-            reinterpret_cast<uint2 *>(pam + tile * kPamBytes + 16)[k - 2] = make_uint2(o0 & o1 & up, ~o0 & o1 & up);
+            const uint32_t g = o0 & o1 & up, c = ~o0 & o1 & up;
+            reinterpret_cast<uint2 *>(pam + tile * kPamBytes + 16)[k - 2] = make_uint2(g, c);
+            if (k < 2 + (uint32_t)kTileWords) {          // a tile word: its hits under the guide-independent bounds
+                uint32_t gn = 0, cn = 0;                 // upper-case G / C at the two positions after the word
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int64_t q = p0 + 32 + j;
+                    if (q >= lo && q < hi) {
+                        const uint32_t ch = ascii[pd.ascii_off + (uint64_t)(q - lo)];
+                        gn |= (uint32_t)(ch == 'G') << j;
+                        cn |= (uint32_t)(ch == 'C') << j;
+                    }
+                }
+                const int32_t tw = (int32_t)p0;
+                const int32_t hi_p = min((int32_t)pd.td.L - 3, (int32_t)pd.td.t_start + (int32_t)pd.td.n - 1);
+                const uint32_t hp = __funnelshift_r(g, gn, 1) & __funnelshift_r(g, gn, 2) & range_mask(tw, 0, hi_p);
+                const uint32_t hm = c & __funnelshift_r(c, cn, 1) & range_mask(tw, 2, hi_p);
+                const uint32_t v = __popc(hp) | (__popc(hm) << 16);
+                const unsigned long long key = tile * 8ull + (k - 2) / 64u;
+                const unsigned peers = __match_any_sync(__activemask(), key);
+                const uint32_t sum = __reduce_add_sync(peers, v);
+                if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1) && sum) atomicAdd(&hdr[tile].cnt[(k - 2) / 64u], sum);
+            }
         }
     }
 }
@@ -255,15 +294,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         : "memory");
 }
 
-// bits b of a 32-position word starting at token position t0 with lo <= t0+b <= hi
-__device__ __forceinline__ uint32_t range_mask(int32_t t0, int32_t lo, int32_t hi) {
-    int32_t a = lo - t0, b = hi - t0;
-    if (a < 0) a = 0;
-    if (b > 31) b = 31;
-    if (a > b) return 0u;
-    return (0xFFFFFFFFu >> (31 - b)) & (0xFFFFFFFFu << a);
-}
-
 struct Hits {
     uint32_t pA, mA, pB, mB;   // '+' / '-' hit masks of the lane's two words (A: first half of the warp chunk, B: second)
 };
@@ -346,7 +376,8 @@ __device__ __forceinline__ void warp_count_tile(const unsigned char *__restrict_
 
 struct ScanArgs {
     const uint4 *records;            // n_tiles records of kRecWords words
-    const unsigned char *pam;        // n_tiles PAM records of kPamBytes bytes (count phase)
+    const unsigned char *pam;        // n_tiles PAM records of kPamBytes bytes (count phase, tiles at the ends of a token)
+    const TileHdr *hdr;              // n_tiles tile headers (count phase)
     uint32_t n_tiles;
     uint32_t static_eighths;         // share of the tiles dealt round-robin, in 1/8 (the rest are ticketed)
     int guide_len;
@@ -693,7 +724,7 @@ k_scan_score(const ScanArgs a) {
     auto stage = [&](int s) { return reinterpret_cast<uint4 *>(s_dyn + (size_t)s * kRecBytes); };
     uint16_t *const s_list = reinterpret_cast<uint16_t *>(s_dyn + kStages * kRecBytes);
     unsigned long long *const s_rangepref =
-        reinterpret_cast<unsigned long long *>(s_dyn + kStages * kRecBytes + kListBufs * 2 * (size_t)kListCap * sizeof(uint16_t));
+        reinterpret_cast<unsigned long long *>(s_dyn + kStages * kRecBytes + 2 * (size_t)kListCap * sizeof(uint16_t));
     __shared__ __align__(16) double s_tab[kScore ? RS1_TABLE_DOUBLES : 1];   // static: LDS takes the table offset as an immediate
     __shared__ Ring ring;
     __shared__ uint32_t s_cnt[kMaxRange][kWarps];
@@ -722,69 +753,72 @@ k_scan_score(const ScanArgs a) {
 
     // ================================================= count phase: tiles [r_lo, r_lo + n_mine)
     const uint32_t r_lo = min(nt, cta * k), n_mine = min(nt, r_lo + k) - r_lo;
-    auto pam_stage = [&](int s) { return s_dyn + (size_t)s * kPamBytes; };
-    auto produce_count = [&](uint32_t n) {            // n < n_mine
-        const int s = n % kCountStages;
-        *reinterpret_cast<volatile uint32_t *>(&ring.tile[s]) = n;    // which tile of the range the slot is (being) filled with
-        mbar_expect(&ring.full[s], kPamBytes);
-        bulk_copy(pam_stage(s), a.pam + (size_t)(r_lo + n) * kPamBytes, kPamBytes, &ring.full[s]);
-    };
     if (cta == 0 && tid == 0) {                                    // read after the grid barrier
         a.tickets[0] = 0;
         a.tickets[1] = 0;
     }
     ring_reset(ring, true, true);
     dbg_stamp(1);
-    if (tid == 0)
-        for (uint32_t n = 0; n < (uint32_t)kCountStages && n < n_mine; ++n) produce_count(n);
-    // Tile n of the range goes to warp n % 8, which counts all of it and then refills the slot
-    // with tile n + 6: no hand-over between warps, ~250 instructions per tile instead of 8 x 80.
-    // A warp only visits its own tiles, so it may find the slot several refills behind; the
-    // parity of an mbarrier cannot tell those apart, the slot's tile number can.
-    // The range is walked in batches of kMaxRange tiles: their (tile, chunk) counts are scanned
-    // together and the running prefix of the range carries over.
+    // The headers of the range arrive by ONE bulk copy per kHdrBatch tiles (48 bytes per tile instead of the
+    // 4 KB PAM record the count phase used to stream: k_pack has already counted every chunk under the bounds
+    // that do not depend on the guide length).  A tile that reaches into the first l + 5 or the last l - 7
+    // positions of its token -- two per token for any sensible l -- is counted here, by one warp, straight from
+    // its PAM record in global memory.  Counts are scanned in batches of kMaxRange tiles as before.
+    const TileHdr *const s_hdr = reinterpret_cast<const TileHdr *>(s_dyn);
     unsigned long long range_run = 0;
-    for (uint32_t b_lo = 0;; b_lo += kMaxRange) {
-        const uint32_t b_n = min(n_mine - min(n_mine, b_lo), (uint32_t)kMaxRange);
-        for (uint32_t n = b_lo + warp; n < b_lo + b_n; n += kWarps) {
-            const int s = n % kCountStages;
-            while (*reinterpret_cast<volatile uint32_t *>(&ring.tile[s]) != n) __nanosleep(32);
-            mbar_wait(&ring.full[s], (n / kCountStages) & 1u);
-            CRP_CHECK(a, n - b_lo < (uint32_t)kMaxRange && r_lo + n < nt, 5);
-            CRP_CHECK(a, *reinterpret_cast<const uint32_t *>(pam_stage(s)) == reinterpret_cast<const uint32_t *>(a.pam + (size_t)(r_lo + n) * kPamBytes)[0], 6);   // the slot holds tile n's record
-            warp_count_tile(pam_stage(s), l, lane, s_cnt[n - b_lo]);
-            __syncwarp();
-            if (lane == 0 && n + kCountStages < n_mine) produce_count(n + kCountStages);
+    for (uint32_t h_lo = 0, hb = 0; h_lo < n_mine; h_lo += kHdrBatch, ++hb) {
+        const uint32_t h_n = min(n_mine - h_lo, (uint32_t)kHdrBatch);
+        if (tid == 0) {
+            mbar_expect(&ring.full[0], h_n * (uint32_t)sizeof(TileHdr));
+            bulk_copy(s_dyn, a.hdr + (size_t)(r_lo + h_lo), h_n * (uint32_t)sizeof(TileHdr), &ring.full[0]);
         }
-        __syncthreads();
-        {   // exclusive scan over the (tile, warp) counts of the batch: thread tid owns tile tid / 8, warp tid % 8
-            const uint32_t j = tid / kWarps, wq = tid % kWarps;
-            const unsigned long long mine = j < b_n ? unpack_counts(s_cnt[j][wq]) : 0ull;
-            unsigned long long incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += v;
+        mbar_wait(&ring.full[0], hb & 1u);
+        for (uint32_t b_lo = 0; b_lo < h_n; b_lo += kMaxRange) {
+            const uint32_t b_n = min(h_n - b_lo, (uint32_t)kMaxRange);
+            for (uint32_t j = warp; j < b_n; j += kWarps) {        // tiles at a token end: counted from the PAM record
+                const uint4 d = s_hdr[b_lo + j].desc;
+                const int32_t t0 = (int32_t)d.x, L = (int32_t)d.y;
+                if (t0 < l + 5 || t0 + kTile - 1 > L - l + 7) {
+                    CRP_CHECK(a, r_lo + h_lo + b_lo + j < nt, 5);
+                    CRP_CHECK(a, reinterpret_cast<const uint32_t *>(a.pam + (size_t)(r_lo + h_lo + b_lo + j) * kPamBytes)[0] == d.x, 6);   // the same tile
+                    warp_count_tile(a.pam + (size_t)(r_lo + h_lo + b_lo + j) * kPamBytes, l, lane, s_cnt[j]);
+                }
             }
-            if (lane == 31) s_scan[warp] = incl;
             __syncthreads();
-            unsigned long long before = range_run, total = 0;
+            {   // exclusive scan over the (tile, warp) counts of the batch: thread tid owns tile tid / 8, warp tid % 8
+                const uint32_t j = tid / kWarps, wq = tid % kWarps;
+                unsigned long long mine = 0ull;
+                if (j < b_n) {
+                    const uint4 d = s_hdr[b_lo + j].desc;
+                    const int32_t t0 = (int32_t)d.x, L = (int32_t)d.y;
+                    const bool edge = t0 < l + 5 || t0 + kTile - 1 > L - l + 7;
+                    mine = unpack_counts(edge ? s_cnt[j][wq] : s_hdr[b_lo + j].cnt[wq]);
+                }
+                unsigned long long incl = mine;
 #pragma unroll
-            for (int q = 0; q < kWarps; ++q) {
-                const unsigned long long x = s_scan[q];
-                if (q < warp) before += x;
-                total += x;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                if (lane == 31) s_scan[warp] = incl;
+                __syncthreads();
+                unsigned long long before = range_run, total = 0;
+#pragma unroll
+                for (int q = 0; q < kWarps; ++q) {
+                    const unsigned long long x = s_scan[q];
+                    if (q < warp) before += x;
+                    total += x;
+                }
+                if (j < b_n) {
+                    unsigned long long *pf = a.warp_pref + (size_t)(r_lo + h_lo + b_lo + j) * kPrefWords;
+                    pf[wq] = before + incl - mine;
+                    if (wq == kWarps - 1) pf[kWarps] = before + incl;      // prefix at the end of the tile
+                    asm volatile("fence.proxy.async.global;" ::: "memory");   // read back by bulk copies after the grid barrier
+                }
+                range_run += total;
+                __syncthreads();                                   // s_cnt, s_scan (and, after the last batch, the headers) are free
             }
-            if (j < b_n) {
-                unsigned long long *pf = a.warp_pref + (size_t)(r_lo + b_lo + j) * kPrefWords;
-                pf[wq] = before + incl - mine;
-                if (wq == kWarps - 1) pf[kWarps] = before + incl;      // prefix at the end of the tile
-                asm volatile("fence.proxy.async.global;" ::: "memory");   // read back by bulk copies after the grid barrier
-            }
-            range_run += total;
-            __syncthreads();                                       // s_cnt and s_scan are free for the next batch
         }
-        if (b_lo + kMaxRange >= n_mine) break;
     }
     if (tid == 0) a.cta_tot[cta] = range_run;
     // The first emit tile of this CTA is known (static share): its record is fetched across the
@@ -907,129 +941,6 @@ k_scan_score(const ScanArgs a) {
         if (pre) mbar_arrive(&ring.full[0]);                   // tile 0 came through ring.pre: skip that phase of slot 0
         else produce_emit(0, 0);
     }
-#if CRP_PIPELINED_EMIT
-    // One barrier per tile: between two barriers every warp first emits its share of the candidates of tile n
-    // (lists of buffer n & 1, record in slot n % 2) and then builds the lists of tile n + 1 (buffer (n + 1) & 1,
-    // record in the other slot, whose copy was issued at the barrier and landed behind the candidates).  A warp
-    // with few candidates goes straight on to its front end and the other way round, so the two kinds of
-    // imbalance meet in one barrier instead of two, and bodies (integer ALU) overlap front ends (LSU, XU).
-    struct TileCtx {
-        uint32_t np, nm, base_p, base_m, t_start, L;
-        bool live, dense;
-    };
-    auto lists = [&](uint32_t n, bool minus) { return s_list + ((n & 1u) * 2u + (minus ? 1u : 0u)) * kListCap; };
-    // ranks of the first hits of this lane's two words inside the tile (per strand); false: the chunk has no hit
-    auto chunk_ranks = [&](int s, const uint4 *rec, const TileDesc td, Hits &h, uint32_t &epA, uint32_t &emA, uint32_t &epB,
-                           uint32_t &emB, uint32_t np, uint32_t nm) -> bool {
-        const uint32_t wordA = 64 * warp + lane;
-        const bool busy = ring.pref[s][warp + 1] != ring.pref[s][warp];          // warp-uniform (see below)
-        if (!busy) {
-#ifdef CRP_CHECKED
-            const Hits hh = tile_hits(rec, td, l, wordA);
-            CRP_CHECK(a, (hh.pA | hh.pB | hh.mA | hh.mB) == 0u, 13);
-#endif
-            return false;
-        }
-        const unsigned long long off = ring.pref[s][warp] - ring.pref[s][0];
-        h = tile_hits(rec, td, l, wordA);
-        const uint32_t cA = __popc(h.pA) | (__popc(h.mA) << 16), cB = __popc(h.pB) | (__popc(h.mB) << 16);
-        uint32_t iA = cA, iB = cB;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t vA = __shfl_up_sync(0xFFFFFFFFu, iA, o), vB = __shfl_up_sync(0xFFFFFFFFu, iB, o);
-            if (lane >= o) {
-                iA += vA;
-                iB += vB;
-            }
-        }
-        const uint32_t totA = __shfl_sync(0xFFFFFFFFu, iA, 31);
-        const uint32_t xA = iA - cA, xB = totA + iB - cB;
-        const uint32_t op = (uint32_t)(off >> 32), om = (uint32_t)off;
-        epA = op + (xA & 0xFFFFu), emA = om + (xA >> 16), epB = op + (xB & 0xFFFFu), emB = om + (xB >> 16);
-#ifdef CRP_CHECKED
-        {
-            const uint32_t mine = totA + __shfl_sync(0xFFFFFFFFu, iB, 31);
-            const unsigned long long nxt = ring.pref[s][warp + 1] - ring.pref[s][warp];
-            CRP_CHECK(a, (uint32_t)(nxt >> 32) == (mine & 0xFFFFu) && (uint32_t)nxt == (mine >> 16), 7);
-            if (np <= (uint32_t)kListCap && nm <= (uint32_t)kListCap)
-                CRP_CHECK(a, epA + __popc(h.pA) <= np && epB + __popc(h.pB) <= np && emA + __popc(h.mA) <= nm && emB + __popc(h.mB) <= nm, 10);
-        }
-#endif
-        (void)np, (void)nm;
-        return true;
-    };
-    // front end of tile number n of this CTA: wait for its record, take its place in the streams from the
-    // prefix block, compact its hits into list buffer n & 1 (dense tiles are listed window by window in `bodies`)
-    auto front = [&](uint32_t n, bool first_pre) -> TileCtx {
-        const int s = n % kStages;
-        TileCtx c = {0u, 0u, 0u, 0u, 0u, 0u, false, false};
-        if (first_pre) mbar_wait(&ring.pre, 0u);
-        else mbar_wait(&ring.full[s], (n / kStages) & 1u);
-        if (!first_pre && ring.tile[s] == kNoTile) return c;
-        c.live = true;
-        const uint4 *rec = stage(s);
-        const uint4 d = rec[0];
-        const TileDesc td = {d.x, d.y, d.z, d.w};
-        const unsigned long long tile_pref = ring.pref[s][0];
-        const unsigned long long base = (first_pre ? s_rangepref[t_pre / k] : ring.rbase[s]) + tile_pref;
-        const unsigned long long tot = ring.pref[s][kWarps] - tile_pref;
-        c.np = (uint32_t)(tot >> 32), c.nm = (uint32_t)tot;
-        c.base_p = (uint32_t)(base >> 32), c.base_m = (uint32_t)base;
-        c.t_start = td.t_start, c.L = td.L;
-        c.dense = c.np > (uint32_t)kListCap || c.nm > (uint32_t)kListCap;
-        CRP_CHECK(a, first_pre || ring.tile[s] < nt, 8);
-        CRP_CHECK(a, (unsigned long long)c.base_p + c.np <= 0xFFFFFFFFull && (unsigned long long)c.base_m + c.nm <= 0xFFFFFFFFull, 9);
-        if (!c.dense) {
-            Hits h = {0u, 0u, 0u, 0u};
-            uint32_t epA = 0, emA = 0, epB = 0, emB = 0;
-            if (chunk_ranks(s, rec, td, h, epA, emA, epB, emB, c.np, c.nm)) {
-                const uint32_t wordA = 64 * warp + lane;
-                list_hits(lists(n, false) + epA, h.pA, 32u * wordA + kWinBiasPlusHot);
-                list_hits(lists(n, false) + epB, h.pB, 32u * (wordA + 32) + kWinBiasPlusHot);
-                list_hits(lists(n, true) + emA, h.mA, 32u * wordA + kWinBiasMinus);
-                list_hits(lists(n, true) + emB, h.mB, 32u * (wordA + 32) + kWinBiasMinus);
-            }
-        }
-        return c;
-    };
-    TileCtx cur = front(0u, pre);
-    __syncthreads();
-    for (uint32_t n = 0; cur.live; ++n) {
-        const int s = n % kStages;
-        // next tile of this CTA: its copies land while this tile's candidates are emitted (slot s^1 was
-        // released by the barrier that ended tile n - 1)
-        if (tid == 0) produce_emit(n + 1, s ^ 1);
-        const uint4 *rec = stage(s);
-        if (!cur.dense) {
-            emit_strand<kScore, false>(a, s_tab, rec, lists(n, false), cur.np, cur.base_p, cur.t_start, cur.L, tid);
-            emit_strand<kScore, true>(a, s_tab, rec, lists(n, true), cur.nm, cur.base_m, cur.t_start, cur.L, tid ^ (kThreads / 2));
-        } else {                                               // dense tile: windows of kListCap ranks, in step
-            const uint4 d = rec[0];
-            const TileDesc td = {d.x, d.y, d.z, d.w};
-            Hits h = {0u, 0u, 0u, 0u};
-            uint32_t epA = 0, emA = 0, epB = 0, emB = 0;
-            const bool busy = chunk_ranks(s, rec, td, h, epA, emA, epB, emB, cur.np, cur.nm);
-            const uint32_t wordA = 64 * warp + lane;
-            for (uint32_t lo = 0; lo < cur.np || lo < cur.nm; lo += kListCap) {
-                const uint32_t cp = cur.np > lo ? min(cur.np - lo, (uint32_t)kListCap) : 0u;
-                const uint32_t cm = cur.nm > lo ? min(cur.nm - lo, (uint32_t)kListCap) : 0u;
-                if (lo) __syncthreads();
-                if (busy) {
-                    list_hits_window(lists(n, false), h.pA, epA, 32u * wordA + kWinBiasPlusHot, lo);
-                    list_hits_window(lists(n, false), h.pB, epB, 32u * (wordA + 32) + kWinBiasPlusHot, lo);
-                    list_hits_window(lists(n, true), h.mA, emA, 32u * wordA + kWinBiasMinus, lo);
-                    list_hits_window(lists(n, true), h.mB, emB, 32u * (wordA + 32) + kWinBiasMinus, lo);
-                }
-                __syncthreads();
-                emit_strand<kScore, false>(a, s_tab, rec, lists(n, false), cp, cur.base_p + lo, cur.t_start, cur.L, tid);
-                emit_strand<kScore, true>(a, s_tab, rec, lists(n, true), cm, cur.base_m + lo, cur.t_start, cur.L, tid);
-            }
-        }
-        const TileCtx nxt = front(n + 1, false);
-        __syncthreads();                                       // lists of tile n + 1 complete; slot s and list buffer n & 1 free
-        cur = nxt;
-    }
-#else
     uint16_t *const list_p = s_list, *const list_m = s_list + kListCap;
     for (uint32_t n = 0;; ++n) {
         const int s = n % kStages;
@@ -1120,7 +1031,6 @@ k_scan_score(const ScanArgs a) {
         }
         __syncthreads();                                       // slot s and the lists are free again
     }
-#endif
     dbg_stamp(5);
     // sharded scan: the counts of every rank are in this rank's buffer before the kernel -- and the
     // copy to the host behind it -- ends (they were sent a whole emit phase ago)

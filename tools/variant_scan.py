@@ -41,4 +41,4 @@ for i in range(n + 3):
         digest = h.hexdigest()[:16]
     r.free()
 ms = np.array(ms) * 1e3
-print(f"{os.environ.get('CROPSR_B200_LIB', 'default'):<40} {workload} median {np.median(ms):7.2f} us  min {ms.min():7.2f} us  digest {digest}")
+print(f"{os.environ.get('CROPSR_B200_LIB', 'default'):<40} {workload} median {np.median(ms):7.2f} us  min {ms.min():7.2f} us  digest {digest}  pack {g.timing()['pack_ms'] * 1e3:.1f} us")
