@@ -963,7 +963,7 @@ static int commit_enqueue(crp_genome *g) {
     if (!one && !descs.empty())
         CUDA_TRY(cudaMemcpyAsync(d_descs, descs.data(), descs.size() * sizeof(PackDesc), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaEventRecord(g->ev[1], st));
-    const uint64_t n_items = (uint64_t)g->n_tiles * kRecWords;
+    const uint64_t n_items = (uint64_t)g->n_tiles * kPackItems;
     if (n_items) {
         PackDesc first = descs[0];
         if (one) first.td.n = (uint32_t)(g->segs[0].end - g->segs[0].begin);     // positions of the whole segment

@@ -1,6 +1,7 @@
 // Device side of libcropsr_b200: pack, scan + score, segment counts, rescore (sm_100a).
 //
-// HBM layout of a packed genome shard: an array of TILE RECORDS, one per 16384 token
+// HBM layout of a packed genome shard: an array of TILE RECORDS (plus, per tile, a PAM record and a
+// header, below), one per 16384 token
 // positions of a segment, each record self-contained so that ONE bulk (TMA) copy stages
 // everything a CTA needs for the tile:
 //     word 0            descriptor {t_start, token length L, owned positions n, segment}
@@ -11,11 +12,12 @@
 // G3, CROPSR.py:300-302), lower-case, other byte}: 0.5 byte per base.
 //
 // k_scan_score is one cooperative, persistent launch:
-//   count phase   every CTA counts the PAM hits of a contiguous range of tiles (bandwidth
-//                 bound: bulk copies + a few bit ops per word) and publishes the range total
-//                 and the range-local exclusive prefix of every tile (ranges of any length are
-//                 walked in batches of kMaxRange tiles with a running prefix: one count phase,
-//                 one grid barrier, one tail for a genome of any size);
+//   count phase   every CTA takes the PAM hit counts of a contiguous range of tiles from their 48-byte
+//                 headers (k_pack counted every 2,048-position chunk; only the tiles at the ends of a
+//                 token, where the bounds depend on the guide length, are counted again from their PAM
+//                 records) and publishes the range total and the range-local exclusive prefix of every
+//                 chunk (ranges of any length are walked in batches of 256 tiles with a running prefix:
+//                 one count phase, one grid barrier, one tail for a genome of any size);
 //   grid barrier, every CTA scans the range totals into shared memory;
 //   emit phase    tiles are handed out dynamically; the global output offset of a tile is
 //                 range prefix + tile prefix (one load), so there is no ordering between
@@ -47,7 +49,6 @@ static constexpr int kStages = 2;                          // staged tiles per C
 static constexpr int kListCap = 1024;                      // hits per strand of a tile compacted in one go
 static constexpr int kPrefWords = 10;                      // per tile: 8 warp prefixes, tile total, pad (80 B, one bulk copy)
 static constexpr uint32_t kNoTile = 0xFFFFFFFFu;
-static constexpr int kMaxRange = 32;                       // tiles of a CTA's count range whose (tile, chunk) counts are scanned in one go
 static constexpr int kMaxPeers = 8;                        // GPUs of one box
 static constexpr uint32_t kAlign = 128;                    // positions; segment placement granularity
 
@@ -66,7 +67,9 @@ struct __align__(16) TileHdr {
     uint32_t cnt[8];
 };
 static_assert(sizeof(TileHdr) == 48, "bulk copies move multiples of 16 bytes");
-static constexpr int kHdrBatch = 256;                      // tile headers of a CTA's count range staged at once (12 KB)
+static constexpr uint32_t kPackItems = 544;                // k_pack: threads per tile (17 warps; 515 of them write a record word)
+static_assert(kPackItems % 32 == 0 && kPackItems >= (uint32_t)kRecWords, "whole warps per tile");
+static constexpr int kHdrBatch = 256;                      // tile headers of a CTA's count range staged and scanned at once (12 KB)
 static_assert(kRecBytes % 16 == 0, "bulk copies move multiples of 16 bytes");
 
 // record word 0
@@ -119,8 +122,9 @@ __host__ __device__ inline uint32_t classify(uint32_t c) {
 // BYTE lane (code low | code high << 8 | lower << 16 | other << 24): eight consecutive bases
 // accumulate as  acc += entry << k  (one IMAD each, no bit twiddling), which leaves 8 positions
 // of every plane in one byte of acc, and byte permutes assemble the 32-position planes.
-// hdr (zeroed before the launch): the descriptor again and the chunk counts of TileHdr -- every thread adds the
-// hits of its word, one atomic per (warp, chunk).
+// hdr (zeroed before the launch): the descriptor again and the chunk counts of TileHdr -- the 16 warps that
+// pack the 512 tile words of a tile add the hits of their 32 words with one atomic each.
+// n_items = tiles * kPackItems.
 __global__ void __launch_bounds__(256)
 k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, const PackDesc one, uint64_t n_items,
        uint4 *__restrict__ records, unsigned char *__restrict__ pam, TileHdr *__restrict__ hdr) {
@@ -131,84 +135,90 @@ k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, co
     }
     __syncthreads();
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t it = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += stride) {
-        const uint64_t tile = it / kRecWords;
-        const uint32_t k = (uint32_t)(it - tile * kRecWords);
-        PackDesc pd;
-        if (descs) {
-            pd = descs[tile];
-        } else {
-            pd = one;
-            const uint32_t done = (uint32_t)tile * (uint32_t)kTile;
-            pd.td.t_start = one.td.t_start + done;
-            pd.td.n = one.td.n - done < (uint32_t)kTile ? one.td.n - done : (uint32_t)kTile;
-        }
-        if (k == 0) {
-            const uint4 d = make_uint4(pd.td.t_start, pd.td.L, pd.td.n, pd.td.segment);
-            records[it] = d;
-            *reinterpret_cast<uint4 *>(pam + tile * kPamBytes) = d;
-            hdr[tile].desc = d;
-            continue;
-        }
-        const int64_t p0 = (int64_t)pd.td.t_start + ((int64_t)k - 2) * 32;   // token position of bit 0
-        const int64_t lo = pd.stage_begin, hi = pd.stage_end;
-        uint32_t o0 = 0, o1 = 0, ol = 0, oo = 0;
-        if (p0 >= lo && p0 + 32 <= hi) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(ascii + pd.ascii_off + (uint64_t)(p0 - lo));
-            const uint4 a = __ldg(src), b = __ldg(src + 1);
-            const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            uint32_t acc[4];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {                  // 8 bases -> one byte of every plane
-                uint32_t s = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) s += lut[(v[2 * g + (j >> 2)] >> (8 * (j & 3))) & 0xFFu] << j;
-                acc[g] = s;
+    for (uint64_t item = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += stride) {
+        // items of a tile: its 512 tile words (16 warps: every warp sits inside ONE chunk of one tile), then the
+        // descriptor, the two halo words and 29 idle slots (the 17th warp)
+        const uint64_t tile = item / kPackItems;
+        const uint32_t i = (uint32_t)(item - tile * kPackItems);
+        const uint32_t k = i < (uint32_t)kTileWords ? i + 2u : i == (uint32_t)kTileWords ? 0u : i == (uint32_t)kTileWords + 1u ? 1u : (uint32_t)kTileWords + 2u;
+        const uint64_t it = tile * kRecWords + k;              // record word
+        uint32_t hits = 0;                                     // (plus | minus << 16) of a tile word
+        if (i < (uint32_t)kTileWords + 3u) {
+            PackDesc pd;
+            if (descs) {
+                pd = descs[tile];
+            } else {
+                pd = one;
+                const uint32_t done = (uint32_t)tile * (uint32_t)kTile;
+                pd.td.t_start = one.td.t_start + done;
+                pd.td.n = one.td.n - done < (uint32_t)kTile ? one.td.n - done : (uint32_t)kTile;
             }
-            const uint32_t t01 = __byte_perm(acc[0], acc[1], 0x5140), t23 = __byte_perm(acc[2], acc[3], 0x5140);
-            const uint32_t u01 = __byte_perm(acc[0], acc[1], 0x7362), u23 = __byte_perm(acc[2], acc[3], 0x7362);
-            o0 = __byte_perm(t01, t23, 0x5410);
-            o1 = __byte_perm(t01, t23, 0x7632);
-            ol = __byte_perm(u01, u23, 0x5410);
-            oo = __byte_perm(u01, u23, 0x7632);
-        } else {
-            for (int bit = 0; bit < 32; ++bit) {
-                const int64_t p = p0 + bit;
-                uint32_t e = 1u << 24;
-                if (p >= lo && p < hi) e = lut[ascii[pd.ascii_off + (uint64_t)(p - lo)]];
-                o0 |= (e & 1u) << bit;
-                o1 |= ((e >> 8) & 1u) << bit;
-                ol |= ((e >> 16) & 1u) << bit;
-                oo |= ((e >> 24) & 1u) << bit;
-            }
-        }
-        records[it] = make_uint4(o0, o1, ol, oo);
-        if (k >= 2) {                       // tile words and the right halo: the planes of the PAM tests
-            const uint32_t up = ~(ol | oo);
-            const uint32_t g = o0 & o1 & up, c = ~o0 & o1 & up;
-            reinterpret_cast<uint2 *>(pam + tile * kPamBytes + 16)[k - 2] = make_uint2(g, c);
-            if (k < 2 + (uint32_t)kTileWords) {          // a tile word: its hits under the guide-independent bounds
-                uint32_t gn = 0, cn = 0;                 // upper-case G / C at the two positions after the word
+            if (k == 0) {
+                const uint4 d = make_uint4(pd.td.t_start, pd.td.L, pd.td.n, pd.td.segment);
+                records[it] = d;
+                *reinterpret_cast<uint4 *>(pam + tile * kPamBytes) = d;
+                hdr[tile].desc = d;
+            } else {
+                const int64_t p0 = (int64_t)pd.td.t_start + ((int64_t)k - 2) * 32;   // token position of bit 0
+                const int64_t lo = pd.stage_begin, hi = pd.stage_end;
+                uint32_t o0 = 0, o1 = 0, ol = 0, oo = 0;
+                if (p0 >= lo && p0 + 32 <= hi) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(ascii + pd.ascii_off + (uint64_t)(p0 - lo));
+                    const uint4 a = __ldg(src), b = __ldg(src + 1);
+                    const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                    uint32_t acc[4];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int64_t q = p0 + 32 + j;
-                    if (q >= lo && q < hi) {
-                        const uint32_t ch = ascii[pd.ascii_off + (uint64_t)(q - lo)];
-                        gn |= (uint32_t)(ch == 'G') << j;
-                        cn |= (uint32_t)(ch == 'C') << j;
+                    for (int g = 0; g < 4; ++g) {                  // 8 bases -> one byte of every plane
+                        uint32_t s = 0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) s += lut[(v[2 * g + (j >> 2)] >> (8 * (j & 3))) & 0xFFu] << j;
+                        acc[g] = s;
+                    }
+                    const uint32_t t01 = __byte_perm(acc[0], acc[1], 0x5140), t23 = __byte_perm(acc[2], acc[3], 0x5140);
+                    const uint32_t u01 = __byte_perm(acc[0], acc[1], 0x7362), u23 = __byte_perm(acc[2], acc[3], 0x7362);
+                    o0 = __byte_perm(t01, t23, 0x5410);
+                    o1 = __byte_perm(t01, t23, 0x7632);
+                    ol = __byte_perm(u01, u23, 0x5410);
+                    oo = __byte_perm(u01, u23, 0x7632);
+                } else {
+                    for (int bit = 0; bit < 32; ++bit) {
+                        const int64_t p = p0 + bit;
+                        uint32_t e = 1u << 24;
+                        if (p >= lo && p < hi) e = lut[ascii[pd.ascii_off + (uint64_t)(p - lo)]];
+                        o0 |= (e & 1u) << bit;
+                        o1 |= ((e >> 8) & 1u) << bit;
+                        ol |= ((e >> 16) & 1u) << bit;
+                        oo |= ((e >> 24) & 1u) << bit;
                     }
                 }
-                const int32_t tw = (int32_t)p0;
-                const int32_t hi_p = min((int32_t)pd.td.L - 3, (int32_t)pd.td.t_start + (int32_t)pd.td.n - 1);
-                const uint32_t hp = __funnelshift_r(g, gn, 1) & __funnelshift_r(g, gn, 2) & range_mask(tw, 0, hi_p);
-                const uint32_t hm = c & __funnelshift_r(c, cn, 1) & range_mask(tw, 2, hi_p);
-                const uint32_t v = __popc(hp) | (__popc(hm) << 16);
-                const unsigned long long key = tile * 8ull + (k - 2) / 64u;
-                const unsigned peers = __match_any_sync(__activemask(), key);
-                const uint32_t sum = __reduce_add_sync(peers, v);
-                if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1) && sum) atomicAdd(&hdr[tile].cnt[(k - 2) / 64u], sum);
+                records[it] = make_uint4(o0, o1, ol, oo);
+                if (k >= 2) {                       // tile words and the right halo: the planes of the PAM tests
+                    const uint32_t up = ~(ol | oo);
+                    const uint32_t g = o0 & o1 & up, c = ~o0 & o1 & up;
+                    reinterpret_cast<uint2 *>(pam + tile * kPamBytes + 16)[k - 2] = make_uint2(g, c);
+                    if (i < (uint32_t)kTileWords) {          // a tile word: its hits under the guide-independent bounds
+                        uint32_t gn = 0, cn = 0;             // upper-case G / C at the two positions after the word
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const int64_t q = p0 + 32 + j;
+                            if (q >= lo && q < hi) {
+                                const uint32_t ch = ascii[pd.ascii_off + (uint64_t)(q - lo)];
+                                gn |= (uint32_t)(ch == 'G') << j;
+                                cn |= (uint32_t)(ch == 'C') << j;
+                            }
+                        }
+                        const int32_t tw = (int32_t)p0;
+                        const int32_t hi_p = min((int32_t)pd.td.L - 3, (int32_t)pd.td.t_start + (int32_t)pd.td.n - 1);
+                        const uint32_t hp = __funnelshift_r(g, gn, 1) & __funnelshift_r(g, gn, 2) & range_mask(tw, 0, hi_p);
+                        const uint32_t hm = c & __funnelshift_r(c, cn, 1) & range_mask(tw, 2, hi_p);
+                        hits = __popc(hp) | (__popc(hm) << 16);
+                    }
+                }
             }
         }
+        // the warp is whole here (n_items is a multiple of 32) and inside one chunk: one add per warp
+        const uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, hits);
+        if ((threadIdx.x & 31) == 0 && sum) atomicAdd(&hdr[tile].cnt[i / 64u], sum);
     }
 }
 
@@ -334,19 +344,13 @@ __device__ __forceinline__ Hits tile_hits(const uint4 *__restrict__ rec, const T
                             bn.x & bn.y & uBn, ~b.x & b.y & uB, ~bn.x & bn.y & uBn, td, l, wordA);
 }
 
-// the same from a staged PAM record (count phase)
-__device__ __forceinline__ Hits tile_hits_pam(const unsigned char *__restrict__ rec, const TileDesc td, int l, int wordA) {
-    const uint2 *w = reinterpret_cast<const uint2 *>(rec + 16);
-    const uint2 a = w[wordA], an = w[wordA + 1], b = w[wordA + 32], bn = w[wordA + 33];
-    return hits_from_planes(a.x, an.x, a.y, an.y, b.x, bn.x, b.y, bn.y, td, l, wordA);
-}
-
-// Count phase: ONE warp counts a whole staged PAM record.  Lane l owns the words 32 i + l
-// (i = 0 .. 15); warp chunk c of the tile (what a warp of the emit phase compacts) is the words
-// [64 c, 64 c + 64), i.e. iterations 2 c and 2 c + 1.  cnt[c] = (plus | minus << 16) of chunk c.
+// Count phase, tiles at the ends of a token: ONE warp counts a whole PAM record straight from global memory.
+// Lane l owns the words 32 i + l (i = 0 .. 15); warp chunk c of the tile (what a warp of the emit phase
+// compacts) is the words [64 c, 64 c + 64), i.e. iterations 2 c and 2 c + 1.  cnt[c] = (plus | minus << 16)
+// of chunk c.  The loads of eight iterations are issued together: two round trips to memory per tile.
 __device__ __forceinline__ void warp_count_tile(const unsigned char *__restrict__ rec, int l, int lane,
                                                 uint32_t *__restrict__ cnt) {
-    const uint4 d = *reinterpret_cast<const uint4 *>(rec);
+    const uint4 d = __ldg(reinterpret_cast<const uint4 *>(rec));
     const uint2 *w = reinterpret_cast<const uint2 *>(rec + 16);
     const int32_t t0 = (int32_t)d.x, L = (int32_t)d.y;
     const int32_t last_owned = t0 + (int32_t)d.z - 1;
@@ -354,23 +358,32 @@ __device__ __forceinline__ void warp_count_tile(const unsigned char *__restrict_
     const int32_t hi_m = min(L - l + 7, hi_p);
     const bool edge = t0 < l + 5 || t0 + kTile - 1 > hi_m;         // warp-uniform
 #pragma unroll
-    for (int c = 0; c < kWarps; ++c) {
-        uint32_t n = 0;
+    for (int half = 0; half < 2; ++half) {
+        uint2 a[8], an[8];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int word = 64 * c + 32 * h + lane;
-            const uint2 a = w[word], an = w[word + 1];
-            uint32_t p = __funnelshift_r(a.x, an.x, 1) & __funnelshift_r(a.x, an.x, 2);
-            uint32_t m = a.y & __funnelshift_r(a.y, an.y, 1);
-            if (edge) {
-                const int32_t tw = t0 + 32 * word;
-                p &= range_mask(tw, l + 5, hi_p);
-                m &= range_mask(tw, 2, hi_m);
-            }
-            n += __popc(p) | (__popc(m) << 16);
+        for (int i = 0; i < 8; ++i) {
+            const int word = 32 * (8 * half + i) + lane;
+            a[i] = __ldg(w + word);
+            an[i] = __ldg(w + word + 1);
         }
-        n = __reduce_add_sync(0xFFFFFFFFu, n);
-        if (lane == 0) cnt[c] = n;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t n = 0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = 2 * c + h, word = 32 * (8 * half + i) + lane;
+                uint32_t p = __funnelshift_r(a[i].x, an[i].x, 1) & __funnelshift_r(a[i].x, an[i].x, 2);
+                uint32_t m = a[i].y & __funnelshift_r(a[i].y, an[i].y, 1);
+                if (edge) {
+                    const int32_t tw = t0 + 32 * word;
+                    p &= range_mask(tw, l + 5, hi_p);
+                    m &= range_mask(tw, 2, hi_m);
+                }
+                n += __popc(p) | (__popc(m) << 16);
+            }
+            n = __reduce_add_sync(0xFFFFFFFFu, n);
+            if (lane == 0) cnt[4 * half + c] = n;
+        }
     }
 }
 
@@ -727,7 +740,6 @@ k_scan_score(const ScanArgs a) {
         reinterpret_cast<unsigned long long *>(s_dyn + kStages * kRecBytes + 2 * (size_t)kListCap * sizeof(uint16_t));
     __shared__ __align__(16) double s_tab[kScore ? RS1_TABLE_DOUBLES : 1];   // static: LDS takes the table offset as an immediate
     __shared__ Ring ring;
-    __shared__ uint32_t s_cnt[kMaxRange][kWarps];
     __shared__ unsigned long long s_scan[kWarps];
 
     cg::grid_group grid = cg::this_grid();
@@ -763,8 +775,10 @@ k_scan_score(const ScanArgs a) {
     // 4 KB PAM record the count phase used to stream: k_pack has already counted every chunk under the bounds
     // that do not depend on the guide length).  A tile that reaches into the first l + 5 or the last l - 7
     // positions of its token -- two per token for any sensible l -- is counted here, by one warp, straight from
-    // its PAM record in global memory.  Counts are scanned in batches of kMaxRange tiles as before.
-    const TileHdr *const s_hdr = reinterpret_cast<const TileHdr *>(s_dyn);
+    // its PAM record in global memory, and its counts replace those of the staged header.  Then thread j owns
+    // tile j of the batch: its eight chunk counts, one CTA-wide scan of the tile totals, one prefix block.
+    TileHdr *const s_hdr = reinterpret_cast<TileHdr *>(s_dyn);
+    static_assert(kHdrBatch == kThreads, "one tile header per thread");
     unsigned long long range_run = 0;
     for (uint32_t h_lo = 0, hb = 0; h_lo < n_mine; h_lo += kHdrBatch, ++hb) {
         const uint32_t h_n = min(n_mine - h_lo, (uint32_t)kHdrBatch);
@@ -773,51 +787,51 @@ k_scan_score(const ScanArgs a) {
             bulk_copy(s_dyn, a.hdr + (size_t)(r_lo + h_lo), h_n * (uint32_t)sizeof(TileHdr), &ring.full[0]);
         }
         mbar_wait(&ring.full[0], hb & 1u);
-        for (uint32_t b_lo = 0; b_lo < h_n; b_lo += kMaxRange) {
-            const uint32_t b_n = min(h_n - b_lo, (uint32_t)kMaxRange);
-            for (uint32_t j = warp; j < b_n; j += kWarps) {        // tiles at a token end: counted from the PAM record
-                const uint4 d = s_hdr[b_lo + j].desc;
-                const int32_t t0 = (int32_t)d.x, L = (int32_t)d.y;
-                if (t0 < l + 5 || t0 + kTile - 1 > L - l + 7) {
-                    CRP_CHECK(a, r_lo + h_lo + b_lo + j < nt, 5);
-                    CRP_CHECK(a, reinterpret_cast<const uint32_t *>(a.pam + (size_t)(r_lo + h_lo + b_lo + j) * kPamBytes)[0] == d.x, 6);   // the same tile
-                    warp_count_tile(a.pam + (size_t)(r_lo + h_lo + b_lo + j) * kPamBytes, l, lane, s_cnt[j]);
-                }
+        for (uint32_t j = warp; j < h_n; j += kWarps) {
+            const uint4 d = s_hdr[j].desc;
+            const int32_t t0 = (int32_t)d.x, L = (int32_t)d.y;
+            if (t0 < l + 5 || t0 + kTile - 1 > L - l + 7) {            // warp-uniform
+                CRP_CHECK(a, r_lo + h_lo + j < nt, 5);
+                CRP_CHECK(a, reinterpret_cast<const uint32_t *>(a.pam + (size_t)(r_lo + h_lo + j) * kPamBytes)[0] == d.x, 6);   // the same tile
+                warp_count_tile(a.pam + (size_t)(r_lo + h_lo + j) * kPamBytes, l, lane, s_hdr[j].cnt);
             }
-            __syncthreads();
-            {   // exclusive scan over the (tile, warp) counts of the batch: thread tid owns tile tid / 8, warp tid % 8
-                const uint32_t j = tid / kWarps, wq = tid % kWarps;
-                unsigned long long mine = 0ull;
-                if (j < b_n) {
-                    const uint4 d = s_hdr[b_lo + j].desc;
-                    const int32_t t0 = (int32_t)d.x, L = (int32_t)d.y;
-                    const bool edge = t0 < l + 5 || t0 + kTile - 1 > L - l + 7;
-                    mine = unpack_counts(edge ? s_cnt[j][wq] : s_hdr[b_lo + j].cnt[wq]);
-                }
-                unsigned long long incl = mine;
+        }
+        __syncthreads();
+        {
+            unsigned long long c[kWarps], mine = 0ull;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                if (lane == 31) s_scan[warp] = incl;
-                __syncthreads();
-                unsigned long long before = range_run, total = 0;
+            for (int q = 0; q < kWarps; ++q) {
+                c[q] = (uint32_t)tid < h_n ? unpack_counts(s_hdr[tid].cnt[q]) : 0ull;
+                mine += c[q];
+            }
+            unsigned long long incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) s_scan[warp] = incl;
+            __syncthreads();
+            unsigned long long before = range_run, total = 0;
+#pragma unroll
+            for (int q = 0; q < kWarps; ++q) {
+                const unsigned long long x = s_scan[q];
+                if (q < warp) before += x;
+                total += x;
+            }
+            if ((uint32_t)tid < h_n) {
+                unsigned long long *pf = a.warp_pref + (size_t)(r_lo + h_lo + tid) * kPrefWords;
+                unsigned long long run = before + incl - mine;             // prefix at the start of my tile
 #pragma unroll
                 for (int q = 0; q < kWarps; ++q) {
-                    const unsigned long long x = s_scan[q];
-                    if (q < warp) before += x;
-                    total += x;
+                    pf[q] = run;
+                    run += c[q];
                 }
-                if (j < b_n) {
-                    unsigned long long *pf = a.warp_pref + (size_t)(r_lo + h_lo + b_lo + j) * kPrefWords;
-                    pf[wq] = before + incl - mine;
-                    if (wq == kWarps - 1) pf[kWarps] = before + incl;      // prefix at the end of the tile
-                    asm volatile("fence.proxy.async.global;" ::: "memory");   // read back by bulk copies after the grid barrier
-                }
-                range_run += total;
-                __syncthreads();                                   // s_cnt, s_scan (and, after the last batch, the headers) are free
+                pf[kWarps] = run;                                          // prefix at the end of the tile
+                asm volatile("fence.proxy.async.global;" ::: "memory");   // read back by bulk copies after the grid barrier
             }
+            range_run += total;
+            __syncthreads();                                       // s_scan and the staged headers are free
         }
     }
     if (tid == 0) a.cta_tot[cta] = range_run;
