@@ -125,7 +125,7 @@ __host__ __device__ inline uint32_t classify(uint32_t c) {
 // hdr (zeroed before the launch): the descriptor again and the chunk counts of TileHdr -- the 16 warps that
 // pack the 512 tile words of a tile add the hits of their 32 words with one atomic each.
 // n_items = tiles * kPackItems.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, const PackDesc one, uint64_t n_items,
        uint4 *__restrict__ records, unsigned char *__restrict__ pam, TileHdr *__restrict__ hdr) {
     __shared__ uint32_t lut[256];
@@ -143,6 +143,10 @@ k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, co
         const uint32_t k = i < (uint32_t)kTileWords ? i + 2u : i == (uint32_t)kTileWords ? 0u : i == (uint32_t)kTileWords + 1u ? 1u : (uint32_t)kTileWords + 2u;
         const uint64_t it = tile * kRecWords + k;              // record word
         uint32_t hits = 0;                                     // (plus | minus << 16) of a tile word
+        uint32_t pg = 0, pc = 0;                               // upper-case G / C planes of my word
+        TileDesc td = {0u, 0u, 0u, 0u};
+        uint64_t ascii_off = 0;
+        uint32_t stage_lo = 0, stage_hi = 0;
         if (i < (uint32_t)kTileWords + 3u) {
             PackDesc pd;
             if (descs) {
@@ -153,6 +157,7 @@ k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, co
                 pd.td.t_start = one.td.t_start + done;
                 pd.td.n = one.td.n - done < (uint32_t)kTile ? one.td.n - done : (uint32_t)kTile;
             }
+            td = pd.td, ascii_off = pd.ascii_off, stage_lo = pd.stage_begin, stage_hi = pd.stage_end;
             if (k == 0) {
                 const uint4 d = make_uint4(pd.td.t_start, pd.td.L, pd.td.n, pd.td.segment);
                 records[it] = d;
@@ -196,25 +201,36 @@ k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, co
                     const uint32_t up = ~(ol | oo);
                     const uint32_t g = o0 & o1 & up, c = ~o0 & o1 & up;
                     reinterpret_cast<uint2 *>(pam + tile * kPamBytes + 16)[k - 2] = make_uint2(g, c);
-                    if (i < (uint32_t)kTileWords) {          // a tile word: its hits under the guide-independent bounds
-                        uint32_t gn = 0, cn = 0;             // upper-case G / C at the two positions after the word
+                    pg = g, pc = c;
+                }
+            }
+        }
+        // ---- hits of the tile words under the guide-independent bounds.  The warp is whole here (n_items is a
+        // multiple of 32), its lanes hold 32 consecutive words of ONE chunk: the two positions after a word are
+        // the next lane's, the last lane reads its two bytes.
+        if (i < (uint32_t)kTileWords) {
+            uint32_t gn = __shfl_down_sync(0xFFFFFFFFu, pg, 1), cn = __shfl_down_sync(0xFFFFFFFFu, pc, 1);
+            const int64_t p0 = (int64_t)td.t_start + (int64_t)i * 32;
+            if ((threadIdx.x & 31) == 31) {
+                gn = 0, cn = 0;
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const int64_t q = p0 + 32 + j;
-                            if (q >= lo && q < hi) {
-                                const uint32_t ch = ascii[pd.ascii_off + (uint64_t)(q - lo)];
-                                gn |= (uint32_t)(ch == 'G') << j;
-                                cn |= (uint32_t)(ch == 'C') << j;
-                            }
-                        }
-                        const int32_t tw = (int32_t)p0;
-                        const int32_t hi_p = min((int32_t)pd.td.L - 3, (int32_t)pd.td.t_start + (int32_t)pd.td.n - 1);
-                        const uint32_t hp = __funnelshift_r(g, gn, 1) & __funnelshift_r(g, gn, 2) & range_mask(tw, 0, hi_p);
-                        const uint32_t hm = c & __funnelshift_r(c, cn, 1) & range_mask(tw, 2, hi_p);
-                        hits = __popc(hp) | (__popc(hm) << 16);
+                for (int j = 0; j < 2; ++j) {
+                    const int64_t q = p0 + 32 + j;
+                    if (q >= (int64_t)stage_lo && q < (int64_t)stage_hi) {
+                        const uint32_t ch = ascii[ascii_off + (uint64_t)(q - stage_lo)];
+                        gn |= (uint32_t)(ch == 'G') << j;
+                        cn |= (uint32_t)(ch == 'C') << j;
                     }
                 }
             }
+            uint32_t hp = __funnelshift_r(pg, gn, 1) & __funnelshift_r(pg, gn, 2), hm = pc & __funnelshift_r(pc, cn, 1);
+            const int32_t tw = (int32_t)p0;
+            const int32_t hi_p = min((int32_t)td.L - 3, (int32_t)td.t_start + (int32_t)td.n - 1);
+            if (tw < 2 || tw + 31 > hi_p) {                    // first word of a token, last words of a token or of a segment
+                hp &= range_mask(tw, 0, hi_p);
+                hm &= range_mask(tw, 2, hi_p);
+            }
+            hits = __popc(hp) | (__popc(hm) << 16);
         }
         // the warp is whole here (n_items is a multiple of 32) and inside one chunk: one add per warp
         const uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, hits);
