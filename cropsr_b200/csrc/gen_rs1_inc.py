@@ -235,7 +235,12 @@ def hexf(v):
 def main():
     out = []
     emit = out.append
-    emit("// GENERATED by gen_rs1_inc.py from cropsr_b200/rs1.py -- do not edit.")
+    emit("// GENERATED by gen_rs1_inc.py from cropsr_b200/rs1.py -- do not edit.  Regenerate with `make regen` (minutes: the")
+    emit("// hash search is seeded, so the same rs1.py gives this file bit for bit); tests/test_host_logic.py compares the")
+    emit("// digest below with the rs1.py in the tree.")
+    import hashlib
+    with open(os.path.join(here, "..", "rs1.py"), "rb") as f:
+        emit(f"// rs1.py sha256 {hashlib.sha256(f.read()).hexdigest()}")
     emit(f"#define RS1_INTERCEPT {hexf(rs1.INTERCEPT)} /* {rs1.INTERCEPT!r} */")
     emit(f"#define RS1_LOW_GC {hexf(rs1.LOW_GC)} /* {rs1.LOW_GC!r} */")
     w1, w2 = rs1.dense_first(), rs1.dense_second()

@@ -113,6 +113,21 @@ def test_random_fastas_match_oracle(eng, seed):
     _check_against_oracle(eng, text, 20)
 
 
+@pytest.mark.parametrize("guide_len", [1, 1000, 20000, 40000, 70000, 200000])
+def test_guide_lengths_that_span_tiles(eng, guide_len):
+    """The bounds of CROPSR.py:419 / :430 reach guide_len + 5 positions into a token and guide_len - 7 back
+    from its end.  With a long guide several tiles at either end of a token are counted from their PAM
+    records at scan time; all the others take the counts k_pack wrote into their tile headers, which hold
+    for every guide length.  Positions only (the reference scores 20-mers)."""
+    rng = np.random.default_rng(77)
+    alphabet = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)
+    p = np.array([15, 15, 30, 30, 2, 2, 2, 2, 2], dtype=float)
+    recs = [(f"long{k}", rng.choice(alphabet, size=n, p=p / p.sum()).tobytes().decode())
+            for k, n in enumerate((70001, 40000, 16380, 300))]
+    text = "".join(f">{h}\n{s}\n" for h, s in recs)
+    _check_against_oracle(eng, text, guide_len)
+
+
 def test_tile_boundaries_and_dense_hits(eng):
     # PAMs straddling every 8192-position tile edge; poly-G / poly-C worst-case density
     body = bytearray(b"AT" * 20000)

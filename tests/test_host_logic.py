@@ -378,3 +378,15 @@ def test_candidate_scoring_source_on_the_cpu(tmp_path):
                     os.path.join(ROOT, "tests", "host_emu.cu")], check=True, capture_output=True, timeout=600)
     r = subprocess.run([exe, "300000", "300000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
+
+
+def test_generated_rs1_tables_belong_to_the_weights_in_the_tree():
+    """csrc/rs1_weights.inc is generated from cropsr_b200/rs1.py (minutes of hash search, so it is committed
+    and not rebuilt on every make): it records the sha256 of the rs1.py it was made from."""
+    import hashlib
+    with open(os.path.join(ROOT, "cropsr_b200", "rs1.py"), "rb") as f:
+        want = hashlib.sha256(f.read()).hexdigest()
+    with open(os.path.join(ROOT, "cropsr_b200", "csrc", "rs1_weights.inc")) as f:
+        head = f.read(2000)
+    m = re.search(r"rs1\.py sha256 ([0-9a-f]{64})", head)
+    assert m and m.group(1) == want, "rs1.py changed: run `make -C cropsr_b200/csrc regen`"
