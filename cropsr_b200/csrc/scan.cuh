@@ -57,7 +57,8 @@ static constexpr uint32_t kAlign = 128;                    // positions; segment
 // upper-case C) -- 0.25 byte per base
 static constexpr int kPamWords = kTileWords + 1;           // uint2 {upper G, upper C} each
 static constexpr uint32_t kPamBytes = (16 + kPamWords * 8 + 15) / 16 * 16;   // 4128, one bulk copy
-static constexpr int kCountStages = 6;                     // mbarriers of the ring control block (the emit phase uses kStages of them)
+static constexpr int kCountStages = 6;                     // slots of the ring control block: sized for the PAM-record ring the count phase
+                                                           // ran until it moved to tile headers; it now uses mbarrier 0, the emit phase kStages
 // Tile header, read by the count phase: the descriptor and the PAM hits of the tile's eight 2,048-position
 // chunks (plus | minus << 16) counted by k_pack under every bound that does not depend on the guide
 // length -- ownership, t <= L - 3, '-' t >= 2.  Only a tile that reaches into the first l + 5 or the last
@@ -701,13 +702,13 @@ __device__ __forceinline__ void emit_strand(const ScanArgs &a, const double *__r
 // record and, in the emit phase, the tile's prefix block) have landed.
 struct __align__(16) Ring {
     unsigned long long pref[kStages][kPrefWords];   // bulk-copy destination (emit phase)
-    unsigned long long full[kCountStages];          // mbarriers (the emit phase uses the first kStages)
+    unsigned long long full[kCountStages];          // mbarriers (count phase: [0], the header copies; emit phase: the first kStages)
     unsigned long long pre;                         // first emit tile, fetched before the grid barrier
     unsigned long long rbase[kStages];              // global prefix of the count range of the staged tile (emit phase)
     uint32_t tile[kCountStages];                    // staged tile, or kNoTile: the sequence has ended
-    uint32_t done[kCountStages];                    // warps finished with the slot (count phase)
+    uint32_t done[kCountStages];                    // (reset, not read: left from the PAM-record ring)
 };
-static_assert(kCountStages >= kStages, "the ring control block is sized by the count phase");
+static_assert(kCountStages >= kStages, "the ring control block holds the emit phase's slots");
 
 __device__ __forceinline__ void mbar_inval(unsigned long long *bar) {
     asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
