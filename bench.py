@@ -388,7 +388,10 @@ def main():
                        "guide_len": 20, "sharding": f"ONE genome, {world} contiguous shard(s), tile-aligned, halo 32/32",
                        "collective": "ncclAllGather of per-segment counts inside the library, on the scan stream, "
                                      "inside the timed events" if world > 1 else "none (1 GPU)",
-                       "l2": "flushed between steps (512 MiB memset)", "host_numa_node": numa_node},
+                       "l2": "flushed between steps (512 MiB memset)", "host_numa_node": numa_node,
+                       "resident": "the packed genome as k_pack leaves it: tile records (0.5 B/base), PAM records, and 48-byte tile "
+                                   "headers with the PAM hit counts of every 2,048-position chunk under the guide-independent bounds "
+                                   "(the scan's count phase reads the headers; building them is part of `ingest` and of `e2e`)"},
             "e2e": {"value": n_bases_total / (e2e * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": e2e,
                     "ms_each_step_this_rank": [round(v, 3) for v in e2e_ms],
                     "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h_total,
