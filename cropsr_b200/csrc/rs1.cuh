@@ -66,6 +66,13 @@ CRP_HD uint32_t crp_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {   // shf.r
     return (uint32_t)(((((unsigned long long)hi) << 32) | lo) >> (sh & 31u));
 #endif
 }
+CRP_HD int crp_popc(uint32_t a) {
+#ifdef __CUDA_ARCH__
+    return __popc(a);
+#else
+    return __builtin_popcount(a);
+#endif
+}
 CRP_HD double crp_dadd(double a, double b) {
 #ifdef __CUDA_ARCH__
     return __dadd_rn(a, b);

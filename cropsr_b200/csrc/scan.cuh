@@ -90,12 +90,25 @@ struct PackDesc {
 
 // ------------------------------------------------------------------ k_pack
 // bits b of a 32-position word starting at token position t0 with lo <= t0+b <= hi
-__device__ __forceinline__ uint32_t range_mask(int32_t t0, int32_t lo, int32_t hi) {
+CRP_HD uint32_t range_mask(int32_t t0, int32_t lo, int32_t hi) {
     int32_t a = lo - t0, b = hi - t0;
     if (a < 0) a = 0;
     if (b > 31) b = 31;
     if (a > b) return 0u;
     return (0xFFFFFFFFu >> (31 - b)) & (0xFFFFFFFFu << a);
+}
+
+// PAM hits of one tile word under the bounds that hold for every guide length (what a tile header counts):
+// g / c = upper-case G / C of the word's 32 positions, gn / cn = of the two positions after it, tw = token
+// position of bit 0.  '+' t <= min(L - 3, last owned position); '-' 2 <= t <= the same.  -> plus | minus << 16
+CRP_HD uint32_t pack_word_hits(uint32_t g, uint32_t c, uint32_t gn, uint32_t cn, int32_t tw, const TileDesc td) {
+    uint32_t hp = crp_funnel_r(g, gn, 1) & crp_funnel_r(g, gn, 2), hm = c & crp_funnel_r(c, cn, 1);
+    const int32_t hi_p = min((int32_t)td.L - 3, (int32_t)td.t_start + (int32_t)td.n - 1);
+    if (tw < 2 || tw + 31 > hi_p) {                    // first word of a token, last words of a token or of a segment
+        hp &= range_mask(tw, 0, hi_p);
+        hm &= range_mask(tw, 2, hi_p);
+    }
+    return (uint32_t)crp_popc(hp) | ((uint32_t)crp_popc(hm) << 16);
 }
 
 // byte -> nibble: bit0 code low, bit1 code high (A0 T1 C2 G3), bit2 lower-case, bit3 other.
@@ -224,14 +237,7 @@ k_pack(const uint8_t *__restrict__ ascii, const PackDesc *__restrict__ descs, co
                     }
                 }
             }
-            uint32_t hp = __funnelshift_r(pg, gn, 1) & __funnelshift_r(pg, gn, 2), hm = pc & __funnelshift_r(pc, cn, 1);
-            const int32_t tw = (int32_t)p0;
-            const int32_t hi_p = min((int32_t)td.L - 3, (int32_t)td.t_start + (int32_t)td.n - 1);
-            if (tw < 2 || tw + 31 > hi_p) {                    // first word of a token, last words of a token or of a segment
-                hp &= range_mask(tw, 0, hi_p);
-                hm &= range_mask(tw, 2, hi_p);
-            }
-            hits = __popc(hp) | (__popc(hm) << 16);
+            hits = pack_word_hits(pg, pc, gn, cn, (int32_t)p0, td);
         }
         // the warp is whole here (n_items is a multiple of 32) and inside one chunk: one add per warp
         const uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, hits);
@@ -332,14 +338,13 @@ struct Hits {
 //   bounds (CROPSR.py:419 / :430): '+' t >= l+5;  '-' 2 <= t <= L-l+7
 //   plus ownership: t inside the n positions of the tile that the segment owns.
 // All positions fit int32: L < 2^31 - 2^15 (crp_genome_add_segment), 1 <= l <= 10^6.
-__device__ __forceinline__ Hits hits_from_planes(uint32_t gA, uint32_t gAn, uint32_t cA, uint32_t cAn, uint32_t gB,
-                                                 uint32_t gBn, uint32_t cB, uint32_t cBn, const TileDesc td, int l,
-                                                 int wordA) {
+CRP_HD Hits hits_from_planes(uint32_t gA, uint32_t gAn, uint32_t cA, uint32_t cAn, uint32_t gB, uint32_t gBn, uint32_t cB,
+                             uint32_t cBn, const TileDesc td, int l, int wordA) {
     Hits h;
-    h.pA = __funnelshift_r(gA, gAn, 1) & __funnelshift_r(gA, gAn, 2);
-    h.pB = __funnelshift_r(gB, gBn, 1) & __funnelshift_r(gB, gBn, 2);
-    h.mA = cA & __funnelshift_r(cA, cAn, 1);
-    h.mB = cB & __funnelshift_r(cB, cBn, 1);
+    h.pA = crp_funnel_r(gA, gAn, 1) & crp_funnel_r(gA, gAn, 2);
+    h.pB = crp_funnel_r(gB, gBn, 1) & crp_funnel_r(gB, gBn, 2);
+    h.mA = cA & crp_funnel_r(cA, cAn, 1);
+    h.mB = cB & crp_funnel_r(cB, cBn, 1);
     const int32_t t0 = (int32_t)td.t_start, L = (int32_t)td.L;
     const int32_t last_owned = t0 + (int32_t)td.n - 1;
     const int32_t hi_p = min(L - 3, last_owned);
@@ -354,7 +359,7 @@ __device__ __forceinline__ Hits hits_from_planes(uint32_t gA, uint32_t gAn, uint
     return h;
 }
 
-__device__ __forceinline__ Hits tile_hits(const uint4 *__restrict__ rec, const TileDesc td, int l, int wordA) {
+CRP_HD Hits tile_hits(const uint4 *__restrict__ rec, const TileDesc td, int l, int wordA) {
     const uint4 a = rec[2 + wordA], an = rec[3 + wordA], b = rec[34 + wordA], bn = rec[35 + wordA];
     const uint32_t uA = ~(a.z | a.w), uAn = ~(an.z | an.w), uB = ~(b.z | b.w), uBn = ~(bn.z | bn.w);   // upper-case ACGT
     return hits_from_planes(a.x & a.y & uA, an.x & an.y & uAn, ~a.x & a.y & uA, ~an.x & an.y & uAn, b.x & b.y & uB,

@@ -366,8 +366,10 @@ def test_cli_help_and_missing_system(built_lib, capsys):
 def test_candidate_scoring_source_on_the_cpu(tmp_path):
     """tests/host_emu.cu compiles the per-candidate functions of the scan kernel -- the SAME source,
     __host__ __device__ -- for the host and checks the table-driven Rule-Set-1 lanes against the dense
-    replay of OpenBLAS' canonical lane order, and the emit loop's score_hit against the generic
-    extract_window + rs1_canonical pair, bit for bit (reference: CROPSR.py:285-313 through SURVEY 8c)."""
+    replay of OpenBLAS' canonical lane order, the emit loop's score_hit against the generic
+    extract_window + rs1_canonical pair, bit for bit (reference: CROPSR.py:285-313 through SURVEY 8c), and the
+    PAM tests -- tile_hits, and the chunk counts k_pack writes into the tile headers -- against a byte-by-byte
+    reading of random tokens with the bounds of CROPSR.py:415-430, for guides of 1 to 100,000 bases."""
     import shutil
     import subprocess
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
